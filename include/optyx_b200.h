@@ -1,0 +1,156 @@
+/*
+ * optyx_b200 -- C ABI of the B200-native evaluation backend for Optyx diagrams.
+ *
+ * This is the drop-in boundary for the ONE hot path of the reference:
+ *   diagram.eval(backend)  ->  dense leaf arrays  ->  pairwise contractions
+ *   ->  (sliced sum)  ->  prob_dist
+ * (reference: optyx/core/backends.py:457-550 QuimbBackend.eval/_process_term,
+ *  optyx/core/diagram.py:536-590 Box.truncation, backends.py:196-356
+ *  EvalResult.prob_dist).  The reference reaches its arithmetic through
+ * quimb/cotengra/numpy; a maintainer binds these entry points with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every pointer named *_dev is DEVICE memory owned by the caller (torch
+ *    CUDA tensors -> data_ptr()); the library never allocates or frees it;
+ *  - every entry point is stream-ordered on `stream` (a cudaStream_t passed as
+ *    void*), launches kernels only, and performs no host synchronisation;
+ *  - return value 0 = ok, non-zero = error; b2_last_error() gives the text;
+ *  - complex numbers are interleaved (re, im); dtype B2_C128 = 2 x f64,
+ *    B2_C64 = 2 x f32;  tensors are C-ordered unless strides are given;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with an error.
+ */
+#ifndef OPTYX_B200_H
+#define OPTYX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+#define B2_C128 0
+#define B2_C64 1
+
+/* ---- leaf kinds: what Box.truncation builds (diagram.py:536-590) -------- */
+#define B2_K_ONEHOT 1    /* Create/Select           zw.py:450-460, 567-573   */
+#define B2_K_ONES 2      /* free end of a spider    diagram.py:705-707       */
+#define B2_K_VEC 3       /* Z-box diagonal (host values) zw.py:320-329, 641-646 */
+#define B2_K_DENSE 4     /* array boxes (host values)    diagram.py:542-548  */
+#define B2_K_SUM 5       /* W: sqrt(multinomial)    zw.py:231-244            */
+#define B2_K_ADD 6       /* Add                     zw.py:676-683            */
+#define B2_K_MUL 7       /* Multiply                zw.py:720-727            */
+#define B2_K_DIV 8       /* Divide                  zw.py:763-772            */
+#define B2_K_MOD2 9      /* Mod2                    zw.py:818-825            */
+#define B2_K_DUALRAIL 10 /* DualRail                diagram.py:904-913       */
+#define B2_K_PTD 11      /* PhotonThresholdDetector diagram.py:975-983       */
+#define B2_K_EMBED 12    /* EmbeddingTensor         diagram.py:1005-1027     */
+
+#define B2_MAX_LEAF_RANK 8
+
+/* One leaf of the arena.  `offset`/`nelem` are in complex elements inside ONE
+ * arena (one eval); `poff` indexes the per-eval params buffer (complex128). */
+typedef struct {
+    int32_t kind;
+    int32_t ndim;
+    int32_t dims[B2_MAX_LEAF_RANK];
+    int32_t ipar;
+    int32_t reserved;
+    int64_t offset;
+    int64_t nelem;
+    int64_t poff;
+} b2_leaf_desc;
+
+/* ---- pairwise contraction ------------------------------------------------
+ * C[out modes] (+)= alpha * sum_{red modes} A[...] * B[...]
+ * Modes 0..n_out-1 index C (C order: last fastest), modes n_out..n_out+n_red-1
+ * are summed.  A mode absent from an operand has stride 0 (broadcast).  This
+ * one form covers what quimb/cotengra do per tree node (transpose + tensordot
+ * / einsum with batch indices; reference call sites backends.py:514, 539-545),
+ * hyper-indices (spiders), diagonal views (an index wired twice to one leaf:
+ * strides add) and index slicing (base pointer offsets).                     */
+#define B2_MAX_MODES 64
+
+typedef struct {
+    int32_t n_out;
+    int32_t n_red;
+    int32_t dim[B2_MAX_MODES];
+    int64_t sa[B2_MAX_MODES];   /* element strides into A (0 = absent)        */
+    int64_t sb[B2_MAX_MODES];   /* element strides into B (0 = absent)        */
+    int64_t sc[B2_MAX_MODES];   /* element strides into C (out modes only)    */
+} b2_modes;
+
+/* GEMM-shaped view of the same contraction for the tiled tensor-core kernel:
+ * modes are grouped [batch | M | N | K]; within a group mode 0 is the fastest
+ * varying in the flattened group index.                                      */
+typedef struct {
+    int32_t n_batch, n_m, n_n, n_k;
+    int32_t dim[B2_MAX_MODES];
+    int64_t sa[B2_MAX_MODES];
+    int64_t sb[B2_MAX_MODES];
+    int64_t sc[B2_MAX_MODES];
+} b2_gemm_modes;
+
+/* version / errors */
+int b2_abi_version(void);
+const char* b2_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int b2_device_sms(void);
+
+/* (1) array build: fill `batch` arenas of `arena_elems` complex elements each
+ * from `n_leaves` descriptors (device table, sorted by offset).
+ * params_dev: complex128 host-computed values, `params_stride` elements per
+ * eval (0 = shared by all evals of the batch).                               */
+int b2_build_leaves(const b2_leaf_desc* desc_dev, int32_t n_leaves,
+                    int64_t arena_elems, const void* params_dev,
+                    int64_t params_stride, void* arena_dev,
+                    int64_t arena_stride, int32_t batch, int32_t dtype,
+                    void* stream);
+
+/* (2a) thin / bandwidth-bound pairs: one thread per output element.
+ * accumulate != 0: C += alpha * (...)                                        */
+int b2_contract_direct(const b2_modes* modes, const void* a_dev,
+                       const void* b_dev, void* c_dev, double alpha_re,
+                       double alpha_im, int32_t accumulate, int32_t dtype,
+                       void* stream);
+
+/* (2b) large dense pairs: tiled gather -> shared memory -> FP64 DMMA
+ * (complex128) complex GEMM with fused index permutation on load and store.  */
+int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev,
+                     const void* b_dev, void* c_dev, double alpha_re,
+                     double alpha_im, int32_t accumulate, int32_t dtype,
+                     void* stream);
+
+/* (3) slice / Sum-term accumulation: y += alpha * x over n complex elements  */
+int b2_axpy(int64_t n, double alpha_re, double alpha_im, const void* x_dev,
+            void* y_dev, int32_t dtype, void* stream);
+int b2_fill_zero(int64_t n, void* y_dev, int32_t dtype, void* stream);
+
+/* (4) prob_dist (backends.py:291-356).
+ * AMP: p[i] = |t[i]|^2, nz[i] = (t[i] != 0)            (_prob_dist_pure)
+ * DM : axis kinds per result axis: 1 = measured (bit/mode), 2 = ket half,
+ *      3 = bra half of an unmeasured quantum wire (always adjacent pairs).
+ *      p[meas] = sum over unmeasured diagonal of Re t, with the reference's
+ *      tiny-negative clamp; seen[meas] = any non-zero entry with that key;
+ *      max_imag_dev[0] = max |Im| over the entries that were summed.
+ * p_dev is float64 for both dtypes.                                          */
+int b2_probs_amp(int64_t n, const void* t_dev, double* p_dev,
+                 uint8_t* nz_dev, int32_t dtype, void* stream);
+int b2_probs_dm(int32_t ndim, const int32_t* dims, const int32_t* axis_kind,
+                const void* t_dev, double* p_dev, uint8_t* seen_dev,
+                double* max_imag_dev, int32_t dtype, void* stream);
+
+/* micro-benchmarks used by bench.py to measure the FP64 pipes of this GPU:
+ * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = DMMA m16n8k16 (falls back to 1 if the
+ * shape is unavailable).  Launches `iters` dependent-chain iterations on a
+ * full grid; returns the number of FLOPs one launch performs in *flops_out.  */
+int b2_fp64_peak_kernel(int32_t kind, int32_t iters, double* sink_dev,
+                        double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTYX_B200_H */

@@ -1,0 +1,192 @@
+"""Tensor-network IR handed from the host-side diagram compiler to the
+CUDA executor (and, as plain data, to the CPU oracle in ``oracle/``).
+
+The reference goes ``diagram.Diagram.to_tensor`` -> ``discopy.tensor.Diagram``
+-> ``.to_quimb()`` -> quimb ``TensorNetwork`` (optyx/core/diagram.py:301-375,
+optyx/core/backends.py:496-550).  Here the same information is a flat list of
+*leaf descriptors* (what dense truncated array to build, reference
+``Box.truncation``, diagram.py:536-590) plus integer index labels.  COPY
+tensors, swaps and identities never become leaves: a spider is a shared
+(hyper-)index, a swap is a relabel.
+
+A leaf descriptor is deliberately tiny and closed-form so the array can be
+built *on the device* by ``b2_build_leaves`` (csrc/leaf_build.cu).  Values that
+the reference computes with arbitrary host Python (``s ** k`` for ``Endo``,
+user arrays, classical-function truth tables) travel in ``params`` unchanged.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+# ---- leaf kinds (mirrored in include/optyx_b200.h and oracle/leaves.py) ----
+K_ONEHOT = 1    # rank 1: e_pos (all zero if pos >= d)      Create/Select zw.py:450-460, 567-573
+K_ONES = 2      # rank 1: all ones (free end of a spider)
+K_VEC = 3       # rank 1: host values (diagonal of a Z box)  zw.py:320-329, 641-646
+K_DENSE = 4     # any rank: host values, C order              diagram.py:542-548, zx.py:304-309
+K_SUM = 5       # [n, n_1..n_k]: sqrt(multinomial) iff sum n_i == n   W  zw.py:231-244
+K_ADD = 6       # [s, n_1..n_k]: 1 iff sum n_i == s                   Add zw.py:676-683
+K_MUL = 7       # [p, a, b]: 1 iff a*b == p                           Multiply zw.py:720-727
+K_DIV = 8       # [q, a, b]: 1 iff b != 0 and a == q*b                Divide zw.py:763-772
+K_MOD2 = 9      # [b, n]: 1 iff n % 2 == b                            Mod2 zw.py:818-825
+K_DUALRAIL = 10  # [b, m0, m1]: 1 iff (m0, m1) == (1-b, b)            diagram.py:904-913
+K_PTD = 11      # [b, n]: 1 iff b == min(n, 1)                        diagram.py:975-983
+K_EMBED = 12    # [i, j]: 1 iff i == j (rectangular identity)         diagram.py:1005-1027
+
+KIND_NAMES = {
+    K_ONEHOT: "onehot", K_ONES: "ones", K_VEC: "vec", K_DENSE: "dense",
+    K_SUM: "w", K_ADD: "add", K_MUL: "mul", K_DIV: "div", K_MOD2: "mod2",
+    K_DUALRAIL: "dualrail", K_PTD: "ptd", K_EMBED: "embed",
+}
+
+MAX_LEAF_RANK = 8
+
+
+@dataclass
+class Leaf:
+    """One dense leaf: ``kind`` + ``shape`` say what to build, ``inds`` how
+    it is wired.  ``ipar`` is an integer parameter (one-hot position);
+    ``params`` complex values for VEC/DENSE kinds (C order)."""
+    kind: int
+    shape: Tuple[int, ...]
+    inds: Tuple[int, ...]
+    ipar: int = 0
+    params: np.ndarray | None = None
+    name: str = ""
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+
+
+@dataclass
+class Network:
+    """Leaves + wiring.  ``dims[i]`` is the extent of index ``i``;
+    ``output_inds`` are the open indices in result-axis order (``dom + cod``
+    wires of the tensor diagram, backends.py:485-491) and may repeat an index
+    (e.g. a bare ``Spider(1, 2)``).  ``scalar`` multiplies the result
+    (product of all ``Scalar`` boxes and closed loops)."""
+    leaves: List[Leaf] = field(default_factory=list)
+    dims: Dict[int, int] = field(default_factory=dict)
+    output_inds: Tuple[int, ...] = ()
+    scalar: complex = 1.0 + 0j
+    n_dom: int = 0          # how many of output_inds belong to the domain
+
+    @property
+    def output_shape(self) -> Tuple[int, ...]:
+        return tuple(self.dims[i] for i in self.output_inds)
+
+    def structure_key(self) -> tuple:
+        """Hashable description of everything except VEC/DENSE values and the
+        scalar: two networks with equal keys share a contraction plan."""
+        return (
+            tuple((l.kind, l.shape, l.inds, l.ipar) for l in self.leaves),
+            self.output_inds,
+        )
+
+    def arena_elems(self) -> int:
+        return sum(l.size for l in self.leaves)
+
+    def validate(self) -> None:
+        for leaf in self.leaves:
+            assert len(leaf.shape) == len(leaf.inds), leaf
+            assert len(leaf.shape) <= MAX_LEAF_RANK, leaf
+            for d, i in zip(leaf.shape, leaf.inds):
+                assert self.dims[i] == d, (leaf, i, self.dims[i])
+            if leaf.kind in (K_VEC, K_DENSE):
+                assert leaf.params is not None and leaf.params.size == leaf.size
+        for i in self.output_inds:
+            assert i in self.dims
+
+
+class NetworkBuilder:
+    """Accumulates leaves while the diagram compiler walks the boxes.
+
+    Wires carry integer index labels.  ``merge`` implements a spider
+    (``tensor.Spider`` emitted at diagram.py:689, 705-707; zw.py:357-359) by
+    union-find, so COPY tensors are never materialised."""
+
+    def __init__(self):
+        self._parent: List[int] = []
+        self._dim: List[int] = []
+        self.leaves: List[Leaf] = []
+        self.scalar: complex = 1.0 + 0j
+
+    # -- indices ------------------------------------------------------------
+    def new_index(self, dim: int) -> int:
+        self._parent.append(len(self._parent))
+        self._dim.append(int(dim))
+        return len(self._parent) - 1
+
+    def find(self, i: int) -> int:
+        root = i
+        while self._parent[root] != root:
+            root = self._parent[root]
+        while self._parent[i] != root:
+            self._parent[i], i = root, self._parent[i]
+        return root
+
+    def dim(self, i: int) -> int:
+        return self._dim[self.find(i)]
+
+    def merge(self, inds: Sequence[int]) -> int:
+        """Identify all ``inds`` (they must have equal extent)."""
+        roots = [self.find(i) for i in inds]
+        d = self._dim[roots[0]]
+        for r in roots[1:]:
+            assert self._dim[r] == d, "spider legs must have equal dimension"
+            if r != roots[0]:
+                self._parent[r] = roots[0]
+        return roots[0]
+
+    # -- leaves -------------------------------------------------------------
+    def add(self, kind: int, inds: Sequence[int], ipar: int = 0,
+            params=None, name: str = "") -> None:
+        shape = tuple(self.dim(i) for i in inds)
+        if params is not None:
+            params = np.ascontiguousarray(params, dtype=np.complex128).reshape(-1)
+        self.leaves.append(Leaf(kind, shape, tuple(inds), ipar, params, name))
+
+    def mul_scalar(self, value: complex) -> None:
+        self.scalar = self.scalar * complex(value)
+
+    # -- finish ---------------------------------------------------------------
+    def finish(self, dom_inds: Sequence[int], cod_inds: Sequence[int]) -> Network:
+        out = tuple(self.find(i) for i in list(dom_inds) + list(cod_inds))
+        leaves: List[Leaf] = []
+        used = set()
+        for leaf in self.leaves:
+            inds = tuple(self.find(i) for i in leaf.inds)
+            used.update(inds)
+            leaves.append(Leaf(leaf.kind, leaf.shape, inds, leaf.ipar,
+                               leaf.params, leaf.name))
+        scalar = self.scalar
+        # an open index touched by no leaf is the free end of a spider: ones
+        for i in dict.fromkeys(out):
+            if i not in used:
+                leaves.append(Leaf(K_ONES, (self._dim[i],), (i,), 0, None, "ones"))
+                used.add(i)
+        # a closed index touched by no leaf is a loop: Spider(0,0,Dim(d)) = d
+        roots = {self.find(i) for i in range(len(self._parent))}
+        for r in roots:
+            if r not in used:
+                scalar = scalar * self._dim[r]
+        # compact relabel
+        relabel: Dict[int, int] = {}
+        for leaf in leaves:
+            for i in leaf.inds:
+                relabel.setdefault(i, len(relabel))
+        for i in out:
+            relabel.setdefault(i, len(relabel))
+        net = Network(
+            leaves=[Leaf(l.kind, l.shape, tuple(relabel[i] for i in l.inds),
+                         l.ipar, l.params, l.name) for l in leaves],
+            dims={relabel[i]: self._dim[i] for i in relabel},
+            output_inds=tuple(relabel[i] for i in out),
+            scalar=scalar,
+            n_dom=len(dom_inds),
+        )
+        net.validate()
+        return net

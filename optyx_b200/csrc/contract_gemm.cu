@@ -1,0 +1,248 @@
+// Piece (2b): large dense pairwise contraction as a fused index-permute +
+// complex GEMM on the FP64 tensor pipe.
+//
+//   C[b, m, n] (+)= alpha * sum_k A[b, m, k] * B[b, k, n]
+//
+// b, m, n, k are *flattened groups of tensor modes*; each mode carries its own
+// element stride into A, B and C, so the transposes the reference performs as
+// separate numpy passes before BLAS zgemm (tensordot under quimb/cotengra,
+// reached from optyx/core/backends.py:514 / 539-545) never touch HBM: the
+// gather happens on the way into shared memory (cp.async, 16 B per complex128
+// element, 4-stage ring) and the scatter on the way out of the accumulators.
+//
+// FP64 has no tcgen05 kind on sm_100a; the FP64 tensor path is the warp-level
+// DMMA `mma.sync.aligned.m8n8k4.f64`.  A complex product is 4 real DMMAs on the
+// (re, im) halves of interleaved fragments loaded with one LDS.128 each.
+//
+// CTA tile 64 x 64 x 8 (complex), 4 warps as 2 x 2, warp tile 32 x 32:
+// per k4 step a warp issues 64 DMMAs for 16 LDS.128 -> the math pipe is the
+// only busy unit.  Shared pitch 66 (x16 B) makes fragment loads conflict-free.
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr int BM = 64, BN = 64, BK = 8, STAGES = 4, PITCH = 66, GEMM_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// flat group index -> three offsets; mode 0 of the group varies fastest
+__device__ __forceinline__ void decode3(long long flat, const b2_gemm_modes& g, int first, int count,
+                                        long long& oa, long long& ob, long long& oc) {
+    oa = ob = oc = 0;
+    for (int m = 0; m < count; ++m) {
+        const int d = g.dim[first + m];
+        const long long q = flat / d;
+        const long long i = flat - q * d;
+        flat = q;
+        oa += i * g.sa[first + m];
+        ob += i * g.sb[first + m];
+        oc += i * g.sc[first + m];
+    }
+}
+
+struct gemm_smem {
+    double2 a[STAGES][BK][PITCH];
+    double2 b[STAGES][BK][PITCH];
+    long long row_a[BM], row_c[BM], col_b[BN], col_c[BN];
+    long long k_a[STAGES][BK], k_b[STAGES][BK];
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
+                          const double2* __restrict__ B, double2* __restrict__ Cout,
+                          long long M, long long N, long long K, int tiles_m, int a_kfast,
+                          int b_kfast, double alpha_re, double alpha_im, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    gemm_smem& sm = *reinterpret_cast<gemm_smem*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const long long tile = blockIdx.x;
+    const long long m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    const int f_b = 0, f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+
+    long long ba, bb, bc;
+    decode3(blockIdx.y, g, f_b, g.n_batch, ba, bb, bc);
+    A += ba; B += bb; Cout += bc;
+
+    // per-tile row / column offsets (index permutation, decoded once per CTA)
+    if (tid < BM) {
+        long long oa, ob, oc;
+        const long long m = m0 + tid;
+        decode3(m < M ? m : 0, g, f_m, g.n_m, oa, ob, oc);
+        sm.row_a[tid] = oa; sm.row_c[tid] = oc;
+    } else {
+        const int t = tid - BM;
+        long long oa, ob, oc;
+        const long long n = n0 + t;
+        decode3(n < N ? n : 0, g, f_n, g.n_n, oa, ob, oc);
+        sm.col_b[t] = ob; sm.col_c[t] = oc;
+    }
+    const int nchunks = (int)((K + BK - 1) / BK);
+
+    auto decode_k = [&](int chunk) {
+        if (tid < BK) {
+            long long oa, ob, oc;
+            const long long k = (long long)chunk * BK + tid;
+            decode3(k < K ? k : 0, g, f_k, g.n_k, oa, ob, oc);
+            sm.k_a[chunk % STAGES][tid] = oa;
+            sm.k_b[chunk % STAGES][tid] = ob;
+        }
+    };
+    auto issue = [&](int chunk) {
+        const int st = chunk % STAGES;
+        const long long kbase = (long long)chunk * BK;
+        #pragma unroll
+        for (int p = 0; p < (BM * BK) / GEMM_THREADS; ++p) {
+            const int e = tid + p * GEMM_THREADS;
+            int i, j;
+            if (a_kfast) { j = e % BK; i = e / BK; } else { i = e % BM; j = e / BM; }
+            const bool ok = (m0 + i < M) && (kbase + j < K);
+            const double2* src = ok ? A + sm.row_a[i] + sm.k_a[st][j] : A;
+            cp_async16(&sm.a[st][j][i], src, ok ? 16 : 0);
+        }
+        #pragma unroll
+        for (int p = 0; p < (BN * BK) / GEMM_THREADS; ++p) {
+            const int e = tid + p * GEMM_THREADS;
+            int i, j;
+            if (b_kfast) { j = e % BK; i = e / BK; } else { i = e % BN; j = e / BN; }
+            const bool ok = (n0 + i < N) && (kbase + j < K);
+            const double2* src = ok ? B + sm.col_b[i] + sm.k_b[st][j] : B;
+            cp_async16(&sm.b[st][j][i], src, ok ? 16 : 0);
+        }
+    };
+
+    for (int c = 0; c < STAGES - 1; ++c) if (c < nchunks) decode_k(c);
+    __syncthreads();
+    for (int c = 0; c < STAGES - 1; ++c) {
+        if (c < nchunks) issue(c);
+        cp_async_commit();
+    }
+
+    double cre[4][4][2], cim[4][4][2];
+    #pragma unroll
+    for (int r = 0; r < 4; ++r)
+        #pragma unroll
+        for (int c = 0; c < 4; ++c) { cre[r][c][0] = cre[r][c][1] = 0; cim[r][c][0] = cim[r][c][1] = 0; }
+
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const int nxt = c + STAGES - 1;
+        if (nxt < nchunks) decode_k(nxt);
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (nxt < nchunks) issue(nxt);
+        cp_async_commit();
+        const int st = c % STAGES;
+        #pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double2 af[4], bf[4];
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) af[r] = sm.a[st][k4 + fk][wm * 32 + r * 8 + frow];
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) bf[q] = sm.b[st][k4 + fk][wn * 32 + q * 8 + frow];
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double nai = -af[r].y;
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    dmma884(cre[r][q][0], cre[r][q][1], af[r].x, bf[q].x);
+                    dmma884(cre[r][q][0], cre[r][q][1], nai, bf[q].y);
+                    dmma884(cim[r][q][0], cim[r][q][1], af[r].x, bf[q].y);
+                    dmma884(cim[r][q][0], cim[r][q][1], af[r].y, bf[q].x);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: scale, scatter through the C permutation
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = wm * 32 + r * 8 + frow;
+        if (m0 + i >= M) continue;
+        const long long ro = sm.row_c[i];
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = wn * 32 + q * 8 + fk * 2 + h;
+                if (n0 + j >= N) continue;
+                double2 v;
+                v.x = alpha_re * cre[r][q][h] - alpha_im * cim[r][q][h];
+                v.y = alpha_re * cim[r][q][h] + alpha_im * cre[r][q][h];
+                double2* dst = Cout + ro + sm.col_c[j];
+                if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                *dst = v;
+            }
+        }
+    }
+}
+
+}  // namespace b2
+
+extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, const void* b_dev,
+                                void* c_dev, double alpha_re, double alpha_im,
+                                int32_t accumulate, int32_t dtype, void* stream) {
+    using namespace b2;
+    if (!modes || !a_dev || !b_dev || !c_dev) { set_error("b2_contract_gemm: null pointer"); return 1; }
+    if (dtype != B2_C128) {
+        set_error("b2_contract_gemm: only complex128 has a tensor-core path in this build");
+        return 1;
+    }
+    const b2_gemm_modes& g = *modes;
+    const int total = g.n_batch + g.n_m + g.n_n + g.n_k;
+    if (g.n_batch < 0 || g.n_m < 0 || g.n_n < 0 || g.n_k < 0 || total > B2_MAX_MODES) {
+        set_error("b2_contract_gemm: bad mode counts");
+        return 1;
+    }
+    if (num_sms() <= 0) return 1;
+    long long Bt = 1, M = 1, N = 1, K = 1;
+    int p = 0;
+    for (int i = 0; i < g.n_batch; ++i) Bt *= g.dim[p++];
+    for (int i = 0; i < g.n_m; ++i) M *= g.dim[p++];
+    for (int i = 0; i < g.n_n; ++i) N *= g.dim[p++];
+    for (int i = 0; i < g.n_k; ++i) K *= g.dim[p++];
+    if (Bt == 0 || M == 0 || N == 0) return 0;
+    // load direction: walk the group that is contiguous in the operand
+    auto min_stride = [&](const int64_t* s, int first, int count) {
+        long long best = (1ll << 62);
+        for (int i = 0; i < count; ++i)
+            if (g.dim[first + i] > 1 && s[first + i] > 0 && s[first + i] < best) best = s[first + i];
+        return best;
+    };
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+    const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
+    const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
+    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    if (tiles_m * tiles_n > 2147483647ll || Bt > 65535) {
+        set_error("b2_contract_gemm: grid too large (tiles=%lld batch=%lld)", tiles_m * tiles_n, Bt);
+        return 1;
+    }
+    static bool attr_set = false;
+    const int smem = (int)sizeof(gemm_smem);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_c128_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt);
+    contract_gemm_c128_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
+        g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
+        a_kfast, b_kfast, alpha_re, alpha_im, accumulate);
+    return check_launch("b2_contract_gemm");
+}

@@ -1,0 +1,217 @@
+"""Device executor: leaf arena build + plan execution through the C ABI.
+
+PyTorch is used only for device memory, streams, CUDA graphs and (in
+``dist.py``) the NCCL process group; every arithmetic kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import runtime as rt
+from .core.network import K_DENSE, K_ONES, K_VEC, Network
+from .planner import ARENA, OUT, WS, Plan, Step, plan_network
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise rt.B2Error(
+            "optyx_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def leaf_table(net: Network, plan: Plan) -> Tuple[np.ndarray, np.ndarray]:
+    """Descriptor table (+ the unit leaf) and the flat params vector of one eval."""
+    n = len(net.leaves)
+    table = np.zeros(n + 1, dtype=rt.LEAF_DESC_DTYPE)
+    params: List[np.ndarray] = []
+    poff = 0
+    for k, leaf in enumerate(net.leaves):
+        row = table[k]
+        row["kind"], row["ndim"], row["ipar"] = leaf.kind, len(leaf.shape), leaf.ipar
+        row["dims"][:len(leaf.shape)] = leaf.shape
+        row["offset"], row["nelem"] = plan.leaf_offsets[k], leaf.size
+        if leaf.kind in (K_VEC, K_DENSE):
+            row["poff"] = poff
+            params.append(np.asarray(leaf.params, dtype=np.complex128).reshape(-1))
+            poff += leaf.size
+    unit = table[n]
+    unit["kind"], unit["ndim"] = K_ONES, 1
+    unit["dims"][0] = 1
+    unit["offset"], unit["nelem"] = plan.unit_offset, 1
+    pvec = np.concatenate(params) if params else np.zeros(1, dtype=np.complex128)
+    return table, pvec
+
+
+def params_vector(net: Network) -> np.ndarray:
+    ps = [np.asarray(l.params, dtype=np.complex128).reshape(-1)
+          for l in net.leaves if l.kind in (K_VEC, K_DENSE)]
+    return np.concatenate(ps) if ps else np.zeros(1, dtype=np.complex128)
+
+
+class Session:
+    """Device buffers for one plan (arena, workspace, output) and its launcher."""
+
+    def __init__(self, plan: Plan, device=None):
+        torch = require_cuda()
+        self.torch = torch
+        self.lib = rt.load()
+        self.plan = plan
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.tdtype = torch.complex128 if plan.dtype == np.complex128 else torch.complex64
+        self.code = rt.dtype_code(plan.dtype)
+        self.esize = plan.dtype.itemsize
+        b = plan.batch
+        self.arena = torch.empty(b * plan.arena_elems, dtype=self.tdtype, device=self.device)
+        self.ws = torch.empty(max(1, plan.ws_elems), dtype=self.tdtype, device=self.device)
+        self.out = torch.empty((b,) + tuple(plan.out_shape), dtype=self.tdtype,
+                               device=self.device)
+        self.desc_dev = None
+        self.params_dev = None
+        self.params_host = None
+        self.n_leaves = 0
+        self.params_stride = 0
+        self.graph = None
+        self.launches = 0
+
+    # ---- leaves -------------------------------------------------------------
+    def set_leaves(self, nets: Sequence[Network]) -> None:
+        """Upload the descriptor table (structure of nets[0]) and every eval's
+        host-computed params (pinned staging buffer, async copy)."""
+        torch = self.torch
+        plan = self.plan
+        assert len(nets) == plan.batch
+        table, p0 = leaf_table(nets[0], plan)
+        if self.desc_dev is None:
+            self.n_leaves = len(table)
+            self.desc_dev = torch.from_numpy(table.view(np.uint8).copy()).to(self.device)
+            self.params_stride = len(p0)
+            self.params_host = torch.empty((plan.batch, len(p0)), dtype=torch.complex128,
+                                           pin_memory=True)
+            self.params_dev = torch.empty((plan.batch, len(p0)), dtype=torch.complex128,
+                                          device=self.device)
+        ph = self.params_host.numpy()
+        ph[0] = p0
+        for e in range(1, plan.batch):
+            ph[e] = params_vector(nets[e])
+        self.params_dev.copy_(self.params_host, non_blocking=True)
+
+    def build_leaves(self) -> None:
+        plan = self.plan
+        stream = self.torch.cuda.current_stream().cuda_stream
+        rt.check(self.lib.b2_build_leaves(
+            self.desc_dev.data_ptr(), self.n_leaves, plan.arena_elems,
+            self.params_dev.data_ptr(), self.params_stride, self.arena.data_ptr(),
+            plan.arena_elems, plan.batch, self.code, stream), "b2_build_leaves")
+        self.launches += 1
+
+    # ---- steps --------------------------------------------------------------
+    def _ptr(self, lay, slice_vals, terms) -> int:
+        base = {ARENA: self.arena, WS: self.ws, OUT: self.out}[lay.space].data_ptr()
+        off = lay.offset
+        for pos, stride in terms:
+            off += slice_vals[pos] * stride
+        return base + off * self.esize
+
+    def _launch(self, st: Step, slice_vals, alpha: complex, accumulate: int, stream) -> None:
+        a = self._ptr(st.a, slice_vals, st.a_slice)
+        b = self._ptr(st.b, slice_vals, st.b_slice)
+        c = self._ptr(st.c, slice_vals, ())
+        if st.kernel == "gemm":
+            rt.check(self.lib.b2_contract_gemm(C.byref(st.desc), a, b, c, alpha.real, alpha.imag,
+                                               accumulate, self.code, stream), "b2_contract_gemm")
+        else:
+            rt.check(self.lib.b2_contract_direct(C.byref(st.desc), a, b, c, alpha.real,
+                                                 alpha.imag, accumulate, self.code, stream),
+                     "b2_contract_direct")
+        self.launches += 1
+
+    def contract(self, scalar: complex = 1.0, slice_range: Optional[Tuple[int, int]] = None,
+                 zero_out: bool = True) -> None:
+        """Run the plan: invariant steps once, per-slice steps for every slice id
+        in ``slice_range`` (default all), accumulating into ``self.out``."""
+        plan = self.plan
+        stream = self.torch.cuda.current_stream().cuda_stream
+        scalar = complex(scalar)
+        s0, s1 = slice_range if slice_range is not None else (0, plan.nslices)
+        if plan.needs_zero_out and zero_out:
+            rt.check(self.lib.b2_fill_zero(self.out.numel(), self.out.data_ptr(), self.code,
+                                           stream), "b2_fill_zero")
+        zeros = [0] * len(plan.sliced)
+        for st in plan.steps:
+            if not st.per_slice:
+                self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream)
+        if not plan.sliced:
+            return
+        for sid in range(s0, s1):
+            vals, rem = [0] * len(plan.sliced), sid
+            for k in range(len(plan.sliced) - 1, -1, -1):
+                vals[k] = rem % plan.sliced_dims[k]
+                rem //= plan.sliced_dims[k]
+            for st in plan.steps:
+                if st.per_slice:
+                    self._launch(st, vals, scalar if st.final else 1.0 + 0j,
+                                 1 if st.final else 0, stream)
+
+    def run(self, nets: Sequence[Network], scalar: Optional[complex] = None):
+        """Full device path for a batch of structurally identical networks."""
+        self.set_leaves(nets)
+        self.build_leaves()
+        self.contract(nets[0].scalar if scalar is None else scalar)
+        return self.out
+
+    # ---- CUDA graph ---------------------------------------------------------
+    def capture(self, scalar: complex = 1.0) -> None:
+        """Capture leaf build + all contraction launches into one CUDA graph
+        (launch-bound small networks: hundreds of tiny steps per eval)."""
+        torch = self.torch
+        assert self.desc_dev is not None, "set_leaves first"
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.build_leaves()
+            self.contract(scalar)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.build_leaves()
+            self.contract(scalar)
+        self.graph = graph
+
+    def replay(self) -> None:
+        self.graph.replay()
+
+
+_PLAN_CACHE: Dict[tuple, Plan] = {}
+
+
+def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None,
+             trials: int = 8, seed: int = 0, gemm_threshold=(16, 16, 4)) -> Plan:
+    """Plan cache keyed by network *structure* (the counterpart of cotengra's
+    ReusableHyperOptimizer the reference accepts, backends.py:49-56, 436-455)."""
+    key = (net.structure_key(), np.dtype(dtype).str, batch, target_size, trials, seed,
+           tuple(gemm_threshold))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = plan_network(net, dtype=dtype, batch=batch, trials=trials, seed=seed,
+                            target_size=target_size, gemm_threshold=gemm_threshold)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def evaluate(net: Network, dtype=np.complex128, target_size=None, **kw):
+    """One-shot convenience: plan, build, contract; returns the device tensor
+    of shape ``net.output_shape``."""
+    plan = get_plan(net, dtype=dtype, target_size=target_size, **kw)
+    sess = Session(plan)
+    out = sess.run([net])
+    return out[0]

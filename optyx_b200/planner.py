@@ -1,0 +1,540 @@
+"""Host-side contraction planner: pair order, index slicing, operand layouts and
+the per-step mode descriptors the CUDA kernels consume.
+
+The reference delegates all of this to quimb/cotengra (``quimb_tn ^ ...`` and
+``contract(optimize=hyperoptimiser)``, optyx/core/backends.py:513-545), neither
+of which is available here; this module is a from-scratch planner designed
+around the B200 kernels rather than around numpy:
+
+* hyper-indices are first class (a spider is a shared index, never a COPY
+  tensor), so a pair can have *batch* modes besides M/N/K;
+* no tensor is ever transposed in HBM: every step reads its operands through
+  per-mode strides (the permutation is fused into the gather) and the planner
+  chooses each intermediate's layout so that the big operand streams;
+* slicing fixes index values by pointer offsets into the leaf arena, so slices
+  cost no copies and slice-invariant subtrees are contracted once.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+import random
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .core.network import Network
+from .runtime import MAX_MODES, MAX_RED_DIRECT, GemmModes, Modes
+
+
+# --------------------------------------------------------------------------
+# pair order
+# --------------------------------------------------------------------------
+def _prod(dims: Dict[int, int], inds) -> float:
+    r = 1.0
+    for i in inds:
+        r *= dims[i]
+    return r
+
+
+def greedy_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: frozenset,
+                rng: Optional[random.Random] = None, temperature: float = 0.0,
+                costmod: float = 1.0) -> List[Tuple[int, int]]:
+    """SSA path (leaf ids 0..n-1, step s creates id n+s) by greedy pairing on
+    ``size(out) - costmod * (size(a) + size(b))`` with optional Gumbel noise."""
+    n = len(inputs)
+    tens: Dict[int, frozenset] = {k: frozenset(v) for k, v in enumerate(inputs)}
+    count: Dict[int, int] = {}
+    where: Dict[int, set] = {}
+    for k, s in tens.items():
+        for q in s:
+            count[q] = count.get(q, 0) + 1
+            where.setdefault(q, set()).add(k)
+    for q in output:
+        count[q] = count.get(q, 0) + 1
+    size = {k: _prod(dims, s) for k, s in tens.items()}
+
+    def out_inds(a: int, b: int) -> frozenset:
+        sa, sb = tens[a], tens[b]
+        res = []
+        for q in sa | sb:
+            here = (q in sa) + (q in sb)
+            if count[q] > here:
+                res.append(q)
+        return frozenset(res)
+
+    heap: List[tuple] = []
+    tick = 0
+
+    def push(a: int, b: int) -> None:
+        nonlocal tick
+        so = _prod(dims, out_inds(a, b))
+        sc = so - costmod * (size[a] + size[b])
+        sc = math.copysign(math.log2(1.0 + abs(sc)), sc)
+        if rng is not None and temperature > 0.0:
+            u = rng.random()
+            sc -= temperature * -math.log(-math.log(max(u, 1e-300)))
+        tick += 1
+        heapq.heappush(heap, (sc, tick, a, b))
+
+    def neighbours(a: int) -> set:
+        res = set()
+        for q in tens[a]:
+            ks = where[q]
+            if len(ks) > 24:           # huge hyper-edge: a few smallest partners do
+                ks = sorted(ks, key=lambda k: size[k])[:24]
+            res.update(ks)
+        res.discard(a)
+        return res
+
+    for a in range(n):
+        for b in neighbours(a):
+            if a < b:
+                push(a, b)
+
+    path: List[Tuple[int, int]] = []
+    nxt = n
+    while len(tens) > 1:
+        pair = None
+        while heap:
+            _, _, a, b = heapq.heappop(heap)
+            if a in tens and b in tens:
+                pair = (a, b)
+                break
+        if pair is None:                 # disconnected components: outer products
+            ks = sorted(tens, key=lambda k: size[k])
+            pair = (ks[0], ks[1])
+        a, b = pair
+        new = out_inds(a, b)
+        for k in (a, b):
+            for q in tens[k]:
+                count[q] -= 1
+                where[q].discard(k)
+            del tens[k]
+        tens[nxt] = new
+        size[nxt] = _prod(dims, new)
+        for q in new:
+            count[q] += 1
+            where.setdefault(q, set()).add(nxt)
+        path.append((a, b))
+        for c in neighbours(nxt):
+            push(nxt, c)
+        nxt += 1
+    return path
+
+
+@dataclass
+class PathInfo:
+    path: List[Tuple[int, int]]
+    sliced: Tuple[int, ...]
+    macs: float                 # complex multiply-adds per slice
+    peak: float                 # largest intermediate (elements) per slice
+    nslices: int
+    step_inds: List[frozenset] = field(default_factory=list)   # result inds per step
+
+
+def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: frozenset,
+                 path: Sequence[Tuple[int, int]], sliced: Sequence[int] = ()) -> PathInfo:
+    sl = set(sliced)
+    tens = {k: frozenset(v) for k, v in enumerate(inputs)}
+    count: Dict[int, int] = {}
+    for s in tens.values():
+        for q in s:
+            count[q] = count.get(q, 0) + 1
+    for q in output:
+        count[q] = count.get(q, 0) + 1
+    macs, peak = 0.0, 0.0
+    step_inds = []
+    nxt = len(inputs)
+    for a, b in path:
+        sa, sb = tens.pop(a), tens.pop(b)
+        union = sa | sb
+        new = frozenset(q for q in union if count[q] > (q in sa) + (q in sb))
+        for q in sa:
+            count[q] -= 1
+        for q in sb:
+            count[q] -= 1
+        for q in new:
+            count[q] += 1
+        macs += _prod(dims, [q for q in union if q not in sl])
+        peak = max(peak, _prod(dims, [q for q in new if q not in sl]))
+        tens[nxt] = new
+        step_inds.append(new)
+        nxt += 1
+    nslices = int(_prod(dims, sl)) if sl else 1
+    return PathInfo(list(path), tuple(sliced), macs, peak, nslices, step_inds)
+
+
+def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
+              minimize: str = "flops") -> PathInfo:
+    """Best of a deterministic greedy plus ``trials-1`` noisy ones."""
+    best = None
+    rng = random.Random(seed)
+    for t in range(max(1, trials)):
+        if t == 0:
+            p = greedy_path(inputs, dims, output)
+        else:
+            p = greedy_path(inputs, dims, output, rng=rng,
+                            temperature=0.3 + 0.7 * rng.random(),
+                            costmod=rng.choice([0.5, 1.0, 1.0, 2.0]))
+        info = analyse_path(inputs, dims, output, p)
+        key = (info.macs, info.peak) if minimize == "flops" else (info.peak, info.macs)
+        if best is None or key < best[0]:
+            best = (key, info)
+    return best[1]
+
+
+def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
+               max_slices: int = 1 << 20) -> PathInfo:
+    """Greedy index slicing until the largest intermediate fits ``target_size``
+    elements: repeatedly fix the index (taken from the currently largest
+    intermediates) that costs the fewest extra MACs."""
+    sliced: List[int] = []
+    cur = info
+    out = set(output)
+    while cur.peak > target_size and cur.nslices < max_slices:
+        sl = set(sliced)
+        big = sorted(cur.step_inds, key=lambda s: -_prod(dims, [q for q in s if q not in sl]))
+        cands: List[int] = []
+        for s in big[:4]:
+            for q in s:
+                if q not in sl and q not in out and dims[q] > 1 and q not in cands:
+                    cands.append(q)
+        if not cands:
+            break
+        best = None
+        for q in cands:
+            trial = analyse_path(inputs, dims, output, cur.path, sliced + [q])
+            key = (trial.peak > target_size, trial.macs * trial.nslices, trial.peak)
+            if best is None or key < best[0]:
+                best = (key, q, trial)
+        sliced.append(best[1])
+        cur = best[2]
+    return cur
+
+
+# --------------------------------------------------------------------------
+# layouts and step compilation
+# --------------------------------------------------------------------------
+ARENA, WS, OUT = 0, 1, 2
+
+
+@dataclass
+class Layout:
+    """A tensor in device memory: unique indices with element strides."""
+    inds: Tuple[int, ...]
+    strides: Tuple[int, ...]
+    space: int                   # ARENA / WS / OUT
+    offset: int                  # element offset inside that space (per eval)
+    size: int                    # elements per eval (for the batch stride)
+
+    def stride_of(self, q: int) -> int:
+        return self.strides[self.inds.index(q)] if q in self.inds else 0
+
+
+@dataclass
+class Step:
+    kernel: str                  # "direct" | "gemm"
+    desc: object                 # runtime.Modes or runtime.GemmModes
+    a: Layout
+    b: Layout
+    c: Layout
+    a_slice: List[Tuple[int, int]]   # (position in plan.sliced, stride) terms
+    b_slice: List[Tuple[int, int]]
+    per_slice: bool              # False: slice-invariant, run once
+    final: bool
+    macs: float                  # complex MACs (incl. eval batch)
+    bytes: float                 # algorithmic bytes: s * (|A| + |B| + |C|)
+    mnk: Tuple[int, int, int, int]   # (batch, M, N, K) extents
+
+
+@dataclass
+class Plan:
+    steps: List[Step]
+    sliced: Tuple[int, ...]
+    sliced_dims: Tuple[int, ...]
+    nslices: int
+    leaf_offsets: List[int]
+    arena_elems: int             # per eval, includes the unit element
+    unit_offset: int
+    ws_elems: int                # per eval
+    out_shape: Tuple[int, ...]
+    out_elems: int
+    needs_zero_out: bool
+    batch: int
+    dtype: np.dtype
+    info: PathInfo
+    total_macs: float = 0.0
+    total_bytes: float = 0.0
+
+
+class _Allocator:
+    """First-fit free-list allocator over element offsets (plan time only)."""
+
+    def __init__(self):
+        self.free: List[Tuple[int, int]] = []     # (offset, size)
+        self.top = 0
+
+    def alloc(self, size: int) -> int:
+        for k, (off, sz) in enumerate(self.free):
+            if sz >= size:
+                if sz == size:
+                    self.free.pop(k)
+                else:
+                    self.free[k] = (off + size, sz - size)
+                return off
+        off = self.top
+        self.top += size
+        return off
+
+    def release(self, off: int, size: int) -> None:
+        self.free.append((off, size))
+        self.free.sort()
+        merged: List[Tuple[int, int]] = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        self.free = merged
+
+
+def _merge_modes(modes: List[List[int]], fastest_last: bool) -> List[List[int]]:
+    """Fuse neighbouring modes [dim, sa, sb, sc] whose strides nest in all three
+    tensors.  ``fastest_last``: list is slow -> fast (C order)."""
+    modes = [m for m in modes if m[0] > 1]
+    if not modes:
+        return []
+    if not fastest_last:
+        modes = modes[::-1]
+    out = [list(modes[0])]
+    for m in modes[1:]:
+        slow = out[-1]
+        if all(slow[k] == m[k] * m[0] for k in (1, 2, 3)):
+            out[-1] = [slow[0] * m[0], m[1], m[2], m[3]]
+        else:
+            out.append(list(m))
+    if not fastest_last:
+        out = out[::-1]
+    return out
+
+
+def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int = 1,
+                 gemm_threshold: Tuple[int, int, int] = (16, 16, 4)) -> Plan:
+    """Turn a pair order into executable steps (layouts, descriptors, memory)."""
+    dtype = np.dtype(dtype)
+    esize = dtype.itemsize
+    dims = dict(net.dims)
+    sliced = tuple(info.sliced)
+    sl = set(sliced)
+    out_unique = tuple(dict.fromkeys(net.output_inds))
+    assert not (sl & set(out_unique)), "open indices are never sliced"
+
+    # ---- leaf layouts inside the arena (C order, repeated inds -> summed strides)
+    leaf_offsets, layouts = [], {}
+    off = 0
+    for k, leaf in enumerate(net.leaves):
+        leaf_offsets.append(off)
+        st = {}
+        s = 1
+        for d, q in zip(reversed(leaf.shape), reversed(leaf.inds)):
+            st[q] = st.get(q, 0) + s
+            s *= d
+        inds = tuple(dict.fromkeys(leaf.inds))
+        layouts[k] = Layout(inds, tuple(st[q] for q in inds), ARENA, off, leaf.size)
+        off += leaf.size
+    unit_offset = off
+    arena_elems = off + 1
+    unit = Layout((), (), ARENA, unit_offset, 1)
+
+    # ---- which SSA ids depend on a sliced index
+    n = len(net.leaves)
+    dep = {k: bool(set(net.leaves[k].inds) & sl) for k in range(n)}
+
+    path = list(info.path)
+    ids_live = list(range(n))
+    if n == 0:
+        path_ops = [(None, None)]
+    elif n == 1:
+        path_ops = [(0, None)]
+    else:
+        path_ops = list(path)
+
+    count: Dict[int, int] = {}
+    for leaf in net.leaves:
+        for q in set(leaf.inds):
+            count[q] = count.get(q, 0) + 1
+    for q in out_unique:
+        count[q] = count.get(q, 0) + 1
+
+    alloc = _Allocator()
+    steps: List[Step] = []
+    nxt = n
+    total_macs = total_bytes = 0.0
+
+    # final output strides (repeated open index -> summed strides)
+    out_shape = tuple(dims[q] for q in net.output_inds)
+    out_st: Dict[int, int] = {}
+    s = 1
+    for d, q in zip(reversed(out_shape), reversed(net.output_inds)):
+        out_st[q] = out_st.get(q, 0) + s
+        s *= d
+    out_elems = int(s)
+    needs_zero = len(out_unique) != len(net.output_inds)
+
+    for si, (ia, ib) in enumerate(path_ops):
+        final = si == len(path_ops) - 1
+        la = layouts.pop(ia) if ia is not None else unit
+        lb = layouts.pop(ib) if ib is not None else unit
+        da = dep.get(ia, False) if ia is not None else False
+        db = dep.get(ib, False) if ib is not None else False
+        if lb.size > la.size:              # A := the larger operand (it streams)
+            la, lb, da, db, ia, ib = lb, la, db, da, ib, ia
+        sa_set, sb_set = set(la.inds), set(lb.inds)
+        keep = []
+        for q in la.inds + tuple(x for x in lb.inds if x not in sa_set):
+            here = (q in sa_set) + (q in sb_set)
+            if count[q] > here and q not in sl:
+                keep.append(q)
+        for q in sa_set:
+            count[q] -= 1
+        for q in sb_set:
+            count[q] -= 1
+        for q in keep:
+            count[q] += 1
+        keep_set = set(keep)
+
+        def by_stride(lay: Layout, qs):
+            return sorted(qs, key=lambda q: -lay.stride_of(q))
+
+        batch_m = by_stride(la, [q for q in keep if q in sa_set and q in sb_set])
+        m_m = by_stride(la, [q for q in keep if q in sa_set and q not in sb_set])
+        n_m = by_stride(lb, [q for q in keep if q in sb_set and q not in sa_set])
+        red = [q for q in la.inds if q not in keep_set and q not in sl] + \
+              [q for q in lb.inds if q not in keep_set and q not in sl and q not in sa_set]
+
+        # ---- output layout
+        if final:
+            assert set(keep) == set(out_unique), (keep, out_unique)
+            c_inds = out_unique
+            c_strides = tuple(out_st[q] for q in c_inds)
+            lc = Layout(c_inds, c_strides, OUT, 0, out_elems)
+        else:
+            c_inds = tuple(batch_m + m_m + n_m)
+            c_strides, s = [], 1
+            for q in reversed(c_inds):
+                c_strides.append(s)
+                s *= dims[q]
+            c_strides = tuple(reversed(c_strides))
+            size_c = int(s)
+            lc = Layout(c_inds, c_strides, WS, alloc.alloc(size_c * batch), size_c)
+
+        ebatch = [[batch, la.size if la.space != ARENA else arena_elems,
+                   lb.size if lb.space != ARENA else arena_elems, lc.size]] if batch > 1 else []
+        # ---- descriptors
+        Bx = int(_prod(dims, batch_m)) * batch
+        Mx, Nx, Kx = int(_prod(dims, m_m)), int(_prod(dims, n_m)), int(_prod(dims, red))
+        macs = float(Bx) * Mx * Nx * Kx
+        sizeA = _prod(dims, [q for q in la.inds if q not in sl])
+        sizeB = _prod(dims, [q for q in lb.inds if q not in sl])
+        sizeC = _prod(dims, keep)
+        nbytes = esize * batch * (sizeA + sizeB + sizeC)
+
+        def mode(q):
+            return [dims[q], la.stride_of(q), lb.stride_of(q), lc.stride_of(q)]
+
+        use_gemm = (dtype == np.complex128 and Mx >= gemm_threshold[0]
+                    and Nx >= gemm_threshold[1] and Kx >= gemm_threshold[2])
+        desc = None
+        if not use_gemm:
+            # out modes in C *memory* order so that stores are coalesced
+            c_order = sorted(c_inds, key=lambda q: -lc.stride_of(q))
+            outm = _merge_modes(ebatch + [mode(q) for q in c_order], fastest_last=True)
+            redm = sorted([mode(q) for q in red], key=lambda m: (-m[1], -m[2]))
+            redm = _merge_modes(redm, fastest_last=True)
+            if len(redm) > MAX_RED_DIRECT:
+                use_gemm = dtype == np.complex128
+            if not use_gemm:
+                if len(outm) + len(redm) > MAX_MODES:
+                    raise ValueError("contraction step has too many modes for the kernel")
+                desc = Modes()
+                desc.n_out, desc.n_red = len(outm), len(redm)
+                for k, m in enumerate(outm + redm):
+                    desc.dim[k], desc.sa[k], desc.sb[k], desc.sc[k] = m
+        if use_gemm:
+            gb = _merge_modes(ebatch[:] + [mode(q) for q in batch_m], fastest_last=True)[::-1]
+            gm = _merge_modes(sorted([mode(q) for q in m_m], key=lambda m: m[3]), False)
+            gn = _merge_modes(sorted([mode(q) for q in n_m], key=lambda m: m[3]), False)
+            gk = _merge_modes(sorted([mode(q) for q in red],
+                                     key=lambda m: (m[1] if m[1] else 1 << 62, m[2])), False)
+            allm = gb + gm + gn + gk
+            if len(allm) > MAX_MODES:
+                raise ValueError("contraction step has too many modes for the kernel")
+            desc = GemmModes()
+            desc.n_batch, desc.n_m, desc.n_n, desc.n_k = len(gb), len(gm), len(gn), len(gk)
+            for k, m in enumerate(allm):
+                desc.dim[k], desc.sa[k], desc.sb[k], desc.sc[k] = m
+
+        a_slice = [(sliced.index(q), la.stride_of(q)) for q in la.inds if q in sl]
+        b_slice = [(sliced.index(q), lb.stride_of(q)) for q in lb.inds if q in sl]
+        per_slice = bool(da or db)
+        steps.append(Step("gemm" if use_gemm else "direct", desc, la, lb, lc,
+                          a_slice, b_slice, per_slice, final, macs, nbytes,
+                          (Bx, Mx, Nx, Kx)))
+        mult = info.nslices if per_slice else 1
+        total_macs += macs * mult
+        total_bytes += nbytes * mult
+        # release operands living in the workspace
+        for lay in (la, lb):
+            if lay.space == WS:
+                alloc.release(lay.offset, lay.size * batch)
+        layouts[nxt] = lc
+        dep[nxt] = per_slice
+        nxt += 1
+
+    # a slice-invariant buffer must survive all slices: the simple allocator
+    # above may have recycled it for a per-slice tensor.  Re-run allocation in
+    # two arenas when slicing is on.
+    if sliced:
+        _reallocate_for_slices(steps, batch)
+    ws_elems = max([st.c.offset + st.c.size * batch for st in steps if st.c.space == WS] or [0])
+
+    return Plan(steps, sliced, tuple(dims[q] for q in sliced), info.nslices, leaf_offsets,
+                arena_elems, unit_offset, int(ws_elems), out_shape, out_elems,
+                needs_zero or bool(sliced), batch, dtype, info, total_macs, total_bytes)
+
+
+def _reallocate_for_slices(steps: List[Step], batch: int) -> None:
+    """Invariant intermediates get a private region (never recycled by
+    per-slice tensors); per-slice tensors share a second, recycled region."""
+    inv = _Allocator()
+    for st in steps:
+        if st.c.space == WS and not st.per_slice:
+            st.c.offset = inv.alloc(st.c.size * batch)
+    base = inv.top
+    per = _Allocator()
+    per_slice_ids = {id(st.c) for st in steps if st.per_slice}
+    for st in steps:
+        if not st.per_slice:
+            continue
+        if st.c.space == WS:
+            st.c.offset = base + per.alloc(st.c.size * batch)
+        for lay in (st.a, st.b):
+            if lay.space == WS and id(lay) in per_slice_ids:
+                per.release(lay.offset - base, lay.size * batch)
+
+
+def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int = 8,
+                 seed: int = 0, target_size: Optional[float] = None,
+                 gemm_threshold: Tuple[int, int, int] = (16, 16, 4)) -> Plan:
+    """Path search (+ slicing to ``target_size`` elements) + compilation."""
+    inputs = [frozenset(l.inds) for l in net.leaves]
+    output = frozenset(net.output_inds)
+    if len(inputs) >= 2:
+        info = find_path(inputs, net.dims, output, trials=trials, seed=seed)
+        if target_size is not None and info.peak > target_size:
+            info = slice_path(inputs, net.dims, output, info, target_size)
+    else:
+        info = PathInfo([], (), 0.0, 0.0, 1, [])
+    return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)

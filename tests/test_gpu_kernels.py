@@ -1,0 +1,238 @@
+"""-m gpu: every CUDA kernel, called through the C ABI, against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import emulate_plan, random_network
+from oracle import evalresult as oracle_eval
+from oracle import leaves as oracle_leaves
+from oracle.contract import contract_network
+from optyx_b200 import runtime as rt
+from optyx_b200.core.network import (K_ADD, K_DENSE, K_DIV, K_DUALRAIL, K_EMBED, K_MOD2, K_MUL,
+                                     K_ONEHOT, K_ONES, K_PTD, K_SUM, K_VEC, Leaf, Network)
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _net_of_leaves(specs, rng):
+    leaves, dims, nxt = [], {}, 0
+    for kind, shape, ipar in specs:
+        inds = tuple(range(nxt, nxt + len(shape)))
+        nxt += len(shape)
+        for i, d in zip(inds, shape):
+            dims[i] = d
+        params = None
+        if kind in (K_VEC, K_DENSE):
+            n = int(np.prod(shape))
+            params = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        leaves.append(Leaf(kind, tuple(shape), inds, ipar, params))
+    return Network(leaves, dims, (), 1.0)
+
+
+LEAF_SPECS = [
+    (K_ONEHOT, (4,), 2), (K_ONEHOT, (3,), 5), (K_ONES, (7,), 0), (K_VEC, (7,), 0),
+    (K_DENSE, (2, 3, 4), 0), (K_SUM, (4, 4, 4), 0), (K_SUM, (7, 7, 7), 0), (K_SUM, (7, 3, 5), 0),
+    (K_SUM, (10, 4, 4, 4), 0), (K_SUM, (13, 7, 7), 0), (K_SUM, (5, 5), 0), (K_ADD, (7, 4, 4), 0),
+    (K_ADD, (5, 3, 3, 3), 0), (K_MUL, (10, 4, 4), 0), (K_DIV, (10, 10, 4), 0),
+    (K_MOD2, (2, 7), 0), (K_DUALRAIL, (2, 2, 2), 0), (K_DUALRAIL, (2, 3, 3), 0),
+    (K_PTD, (2, 6), 0), (K_EMBED, (3, 7), 0), (K_EMBED, (7, 2), 0), (K_SUM, (20, 10, 10, 10), 0),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("batch", [1, 3])
+def test_leaf_build_matches_oracle(dtype, batch):
+    from optyx_b200.executor import Session
+    from optyx_b200.planner import plan_network
+    rng = np.random.default_rng(1)
+    nets = [_net_of_leaves(LEAF_SPECS, np.random.default_rng(10 + e)) for e in range(batch)]
+    plan = plan_network(nets[0], dtype=dtype, batch=batch)
+    sess = Session(plan)
+    sess.set_leaves(nets)
+    sess.build_leaves()
+    arena = sess.arena.cpu().numpy().reshape(batch, plan.arena_elems)
+    for e, net in enumerate(nets):
+        for off, leaf in zip(plan.leaf_offsets, net.leaves):
+            want = oracle_leaves.build_leaf(leaf.kind, leaf.shape, leaf.ipar, leaf.params)
+            got = arena[e, off:off + leaf.size].reshape(leaf.shape)
+            # exact structure (non-zero pattern) ...
+            assert np.array_equal(got != 0, want != 0), (leaf.kind, leaf.shape)
+            # ... and values: host params pass through unchanged, sqrt(multinomial)
+            # within 1 ulp of the reference's `** 0.5`
+            tol = 4e-16 if dtype == np.complex128 else 2e-7
+            assert np.allclose(got, want, rtol=tol, atol=0), (leaf.kind, leaf.shape)
+        assert arena[e, plan.unit_offset] == 1.0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_networks_match_oracle(seed):
+    from optyx_b200.executor import Session
+    from optyx_b200.planner import plan_network
+    rng = np.random.default_rng(seed)
+    net = random_network(rng, n_leaves=int(rng.integers(1, 10)), n_inds=int(rng.integers(3, 12)),
+                         n_out=int(rng.integers(0, 4)), repeat_in_leaf=seed % 3 == 0)
+    if seed % 5 == 0:
+        net.output_inds = net.output_inds + net.output_inds[:1]
+    want = contract_network(net)
+    for thr in [(16, 16, 4), (1, 1, 1)]:
+        for tgt in [None, 8]:
+            plan = plan_network(net, target_size=tgt, gemm_threshold=thr, trials=3)
+            got = Session(plan).run([net])[0].cpu().numpy()
+            assert got.shape == want.shape
+            scale = max(1.0, np.abs(want).max())
+            assert np.abs(got - want).max() <= 1e-10 * scale, (seed, thr, tgt)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_networks_complex64(seed):
+    from optyx_b200.executor import Session
+    from optyx_b200.planner import plan_network
+    rng = np.random.default_rng(100 + seed)
+    net = random_network(rng, n_leaves=7, n_inds=9, n_out=2)
+    want = contract_network(net)
+    plan = plan_network(net, dtype=np.complex64, target_size=16 if seed % 2 else None)
+    got = Session(plan).run([net])[0].cpu().numpy()
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("batch", [2, 5])
+def test_batched_evals_share_one_plan(batch):
+    from optyx_b200.executor import Session
+    from optyx_b200.planner import plan_network
+    nets = []
+    for e in range(batch):
+        rng = np.random.default_rng(7)          # same structure ...
+        net = random_network(rng, n_leaves=8, n_inds=9, n_out=2)
+        prng = np.random.default_rng(1000 + e)  # ... different values
+        for leaf in net.leaves:
+            if leaf.params is not None:
+                leaf.params = prng.standard_normal(leaf.size) + 1j * prng.standard_normal(leaf.size)
+        nets.append(net)
+    for thr in [(16, 16, 4), (1, 1, 1)]:
+        plan = plan_network(nets[0], batch=batch, gemm_threshold=thr)
+        got = Session(plan).run(nets).cpu().numpy()
+        for e, net in enumerate(nets):
+            want = contract_network(net)
+            assert np.abs(got[e] - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
+
+
+def _gemm_case(rng, mshape, nshape, kshape, bshape=()):
+    """A[b,m,k] x B[b,k,n] with every operand stored in a random axis order."""
+    torch = _torch()
+    lib = rt.load()
+    names = {}
+    groups = {"b": bshape, "m": mshape, "n": nshape, "k": kshape}
+    for g, shp in groups.items():
+        for i, d in enumerate(shp):
+            names[f"{g}{i}"] = d
+    def tensor(groups_in):
+        axes = [f"{g}{i}" for g in groups_in for i in range(len(groups[g]))]
+        perm = list(rng.permutation(len(axes)))
+        axes = [axes[p] for p in perm]
+        shape = [names[a] for a in axes]
+        arr = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        strides, s = {}, 1
+        for a, d in zip(reversed(axes), reversed(shape)):
+            strides[a] = s
+            s *= d
+        return arr, axes, strides
+    A, axA, sA = tensor("bmk")
+    Bm, axB, sB = tensor("bkn")
+    Cz, axC, sC = tensor("bmn")
+    desc = rt.GemmModes()
+    desc.n_batch, desc.n_m, desc.n_n, desc.n_k = len(bshape), len(mshape), len(nshape), len(kshape)
+    p = 0
+    for g in "bmnk":
+        for i in range(len(groups[g])):
+            a = f"{g}{i}"
+            desc.dim[p] = names[a]
+            desc.sa[p], desc.sb[p], desc.sc[p] = sA.get(a, 0), sB.get(a, 0), sC.get(a, 0)
+            p += 1
+    letters = {a: chr(ord("a") + i) for i, a in enumerate(names)}
+    spec = "".join(letters[a] for a in axA) + "," + "".join(letters[a] for a in axB) + "->" + \
+        "".join(letters[a] for a in axC)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(Bm).cuda()
+    dC = torch.zeros(Cz.shape, dtype=torch.complex128, device="cuda")
+    alpha = 0.5 - 0.25j
+    stream = torch.cuda.current_stream().cuda_stream
+    rt.check(lib.b2_contract_gemm(C.byref(desc), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(),
+                                  alpha.real, alpha.imag, 0, rt.B2_C128, stream))
+    want = alpha * torch.einsum(spec, dA, dB)
+    return dC, want
+
+
+@pytest.mark.parametrize("case", [
+    ((64,), (64,), (8,), ()),
+    ((2, 2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2), ()),
+    ((7, 7, 3), (5, 7, 4), (7, 3, 2), (3,)),
+    ((100,), (33,), (17,), (2, 2)),
+    ((130,), (70,), (5,), ()),
+    ((2,) * 10, (2,) * 9, (2,) * 7, ()),
+])
+def test_gemm_kernel_permuted_operands(case):
+    rng = np.random.default_rng(3)
+    got, want = _gemm_case(rng, *case)
+    err = (got - want).abs().max().item()
+    assert err <= 1e-10 * max(1.0, want.abs().max().item())
+
+
+def test_probs_amp_and_dm_match_oracle():
+    torch = _torch()
+    lib = rt.load()
+    rng = np.random.default_rng(5)
+    stream = torch.cuda.current_stream().cuda_stream
+    # AMP
+    t = rng.standard_normal((3, 4, 5)) + 1j * rng.standard_normal((3, 4, 5))
+    t[rng.random(t.shape) < 0.3] = 0
+    dt = torch.from_numpy(t).cuda()
+    p = torch.empty(t.size, dtype=torch.float64, device="cuda")
+    nz = torch.empty(t.size, dtype=torch.uint8, device="cuda")
+    rt.check(lib.b2_probs_amp(t.size, dt.data_ptr(), p.data_ptr(), nz.data_ptr(), rt.B2_C128, stream))
+    want = oracle_eval.prob_dist_pure(t)
+    got = {tuple(int(i) for i in np.unravel_index(k, t.shape)): float(p[k])
+           for k in np.flatnonzero(nz.cpu().numpy())}
+    assert got.keys() == want.keys()
+    for k in want:
+        assert got[k] == want[k]          # bit-exact: same hypot()**2
+    # DM: axes (mode, qubit ket, qubit bra, bit, qmode ket, qmode bra)
+    types = ["mode", "qubit", "bit", "qmode"]
+    shape = (3, 2, 2, 2, 4, 4)
+    kinds = (1, 2, 3, 1, 2, 3)
+    dm = rng.standard_normal(shape) * (rng.random(shape) < 0.5) + 0j
+    dm[0, 0, 0, 1, 2, 2] = -1e-13           # clamp branch
+    dm[2, :, :, 1, :, :] = 0
+    dm[2, 0, 1, 1, 0, 0] = 0.25             # key seen only off-diagonal: kept with p = 0
+    ddm = torch.from_numpy(dm).cuda()
+    n_meas = 3 * 2
+    p = torch.empty(n_meas, dtype=torch.float64, device="cuda")
+    seen = torch.empty(n_meas, dtype=torch.uint8, device="cuda")
+    mx = torch.empty(1, dtype=torch.float64, device="cuda")
+    dims = (C.c_int32 * 6)(*shape)
+    kk = (C.c_int32 * 6)(*kinds)
+    rt.check(lib.b2_probs_dm(6, dims, kk, ddm.data_ptr(), p.data_ptr(), seen.data_ptr(),
+                             mx.data_ptr(), rt.B2_C128, stream))
+    want = oracle_eval.prob_dist_mixed(dm, types)
+    got = {tuple(int(i) for i in np.unravel_index(k, (3, 2))): float(p[k])
+           for k in np.flatnonzero(seen.cpu().numpy())}
+    assert got.keys() == want.keys()
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-15 * max(1.0, abs(want[k]))
+    assert want[(2, 1)] == 0.0 and got[(2, 1)] == 0.0
+
+
+def test_fp64_peak_microbench_runs():
+    torch = _torch()
+    lib = rt.load()
+    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flops = C.c_double(0)
+    for kind in (0, 1, 2):
+        rt.check(lib.b2_fp64_peak_kernel(kind, 64, sink.data_ptr(), C.byref(flops), 0))
+        assert flops.value > 0
+    torch.cuda.synchronize()

@@ -1,0 +1,55 @@
+"""CPU: planner / layouts / slicing / descriptors, via the numpy emulator of the
+kernel descriptor semantics, against the oracle on random hyper-networks."""
+import numpy as np
+import pytest
+
+from helpers import emulate_plan, random_network
+from oracle.contract import contract_network
+from optyx_b200.planner import plan_network
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_plan_emulation_matches_oracle(seed):
+    rng = np.random.default_rng(seed)
+    net = random_network(rng, n_leaves=int(rng.integers(1, 10)), n_inds=int(rng.integers(3, 12)),
+                         n_out=int(rng.integers(0, 4)), repeat_in_leaf=seed % 3 == 0)
+    if seed % 5 == 0:
+        net.output_inds = net.output_inds + net.output_inds[:1]   # repeated open index
+    want = contract_network(net)
+    other = contract_network(net, order="random", seed=seed)
+    assert np.allclose(want, other, rtol=1e-10, atol=1e-10)       # two oracle orders agree
+    for thr in [(16, 16, 4), (1, 1, 1)]:
+        for tgt in [None, 8]:
+            plan = plan_network(net, target_size=tgt, gemm_threshold=thr, trials=3)
+            got = emulate_plan(net, plan)[0]
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9), (seed, thr, tgt)
+
+
+@pytest.mark.parametrize("batch", [2, 4])
+def test_batched_plan_emulation(batch):
+    nets = []
+    for e in range(batch):
+        net = random_network(np.random.default_rng(7), n_leaves=8, n_inds=9, n_out=2)
+        prng = np.random.default_rng(1000 + e)
+        for leaf in net.leaves:
+            if leaf.params is not None:
+                leaf.params = prng.standard_normal(leaf.size) + 1j * prng.standard_normal(leaf.size)
+        nets.append(net)
+    for thr in [(16, 16, 4), (1, 1, 1)]:
+        plan = plan_network(nets[0], batch=batch, gemm_threshold=thr)
+        got = emulate_plan(nets[0], plan, nets=nets)
+        for e, net in enumerate(nets):
+            assert np.allclose(got[e], contract_network(net), rtol=1e-9, atol=1e-9)
+
+
+def test_slices_partition_across_ranks():
+    net = random_network(np.random.default_rng(3), n_leaves=9, n_inds=10, n_out=1)
+    plan = plan_network(net, target_size=4)
+    assert plan.nslices > 1
+    want = contract_network(net)
+    half = plan.nslices // 2
+    part = emulate_plan(net, plan, slice_range=(0, half))[0] + \
+        emulate_plan(net, plan, slice_range=(half, plan.nslices))[0]
+    # invariant steps do not depend on the slice range; only the accumulated output adds
+    assert np.allclose(part, want, rtol=1e-9, atol=1e-9)
