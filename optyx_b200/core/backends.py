@@ -1,0 +1,285 @@
+"""Backend boundary: ``B200Backend`` next to the reference's ``QuimbBackend``.
+
+Mirror of optyx/core/backends.py: ``StateType`` (117-125), ``EvalResult``
+(128-356), ``AbstractBackend`` (360-427).  ``B200Backend.eval`` replaces
+``QuimbBackend.eval`` / ``_process_term`` (457-550): instead of
+``to_quimb()`` + cotengra + numpy it compiles the (possibly CP-doubled) diagram
+to a leaf-descriptor network, builds the leaves in HBM, runs the contraction
+plan with the CUDA kernels and returns the same result object.  ``prob_dist``
+keeps the reference's semantics but computes ``|amp|^2`` / the partial trace on
+the device (csrc/probs.cu) when the result is still resident there.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from abc import ABC, abstractmethod
+from collections import defaultdict
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Any, Optional
+
+import numpy as np
+
+from . import channel
+from . import network as nw
+
+
+class StateType(Enum):
+    """backends.py:117-125"""
+    AMP = "amp"
+    DM = "dm"
+    PROB = "prob"
+    SINGLE_PROB = "SINGLE_PROB"
+    SINGLE_AMP = "SINGLE_AMP"
+
+
+class ResultTensor:
+    """Stand-in for ``discopy.tensor.Box("Result", dom, cod, array)``
+    (backends.py:485-491): ``array.shape == dom + cod``."""
+
+    def __init__(self, dom, cod, array):
+        self.dom, self.cod = tuple(int(d) for d in dom), tuple(int(d) for d in cod)
+        self.array = np.asarray(array).reshape(self.dom + self.cod)
+
+    def dagger(self) -> "ResultTensor":
+        n = len(self.dom)
+        axes = list(range(n, self.array.ndim)) + list(range(n))
+        return ResultTensor(self.cod, self.dom, np.conj(self.array).transpose(axes))
+
+    def __rshift__(self, other: "ResultTensor") -> "ResultTensor":
+        assert self.cod == other.dom
+        k = len(self.cod)
+        arr = np.tensordot(self.array, other.array, axes=k) if k else \
+            np.multiply.outer(self.array, other.array)
+        return ResultTensor(self.dom, other.cod, arr)
+
+
+@dataclass(frozen=True)
+class EvalResult:
+    """backends.py:128-356 (same fields, same methods, same exceptions)."""
+    _tensor: ResultTensor
+    output_types: Any
+    state_type: StateType
+    _device: Any = field(default=None, compare=False, repr=False)   # resident result
+
+    @property
+    def tensor(self) -> ResultTensor:
+        return self._tensor
+
+    def _type_names(self):
+        ot = self.output_types
+        if isinstance(ot, channel.Ty) or hasattr(ot, "inside"):
+            return list(ot.inside)
+        return [t.inside[0] if hasattr(t, "inside") else t for t in ot]
+
+    @property
+    def density_matrix(self) -> np.ndarray:
+        if len(self.tensor.dom) != 0:
+            raise ValueError("Result tensor must represent a state with no inputs. "
+                             f"Current domain: {self.tensor.dom}")
+        if self.state_type not in {StateType.AMP, StateType.DM}:
+            raise TypeError(f"Cannot get density matrix from {self.state_type}.")
+        if self.state_type is StateType.AMP:
+            return (self.tensor.dagger() >> self.tensor).array
+        return self.tensor.array
+
+    def amplitudes(self, normalise=True) -> dict:
+        if self.state_type != StateType.AMP:
+            raise TypeError(f"Cannot get amplitudes from {self.state_type}.")
+        if len(self.tensor.dom) != 0:
+            raise ValueError("Result tensor must represent a state with no inputs. "
+                             f"Current domain: {self.tensor.dom}")
+        dic = self._convert_array_to_dict(self.tensor.array)
+        if normalise:
+            norm = np.sqrt(np.sum(np.abs(list(dic.values())) ** 2))
+            return {key: value / norm for key, value in dic.items()}
+        return dic
+
+    def prob_dist(self, round_digits: int = None) -> dict:
+        if len(self.tensor.dom) != 0:
+            raise ValueError("Result tensor must represent a state with no inputs. "
+                             f"Current domain: {self.tensor.dom}")
+        if self.state_type is StateType.AMP:
+            values = self._prob_dist_pure()
+        elif self.state_type is StateType.DM:
+            values = self._prob_dist_mixed()
+        elif self.state_type is StateType.PROB:
+            values = self._convert_array_to_dict(self.tensor.array)
+        else:
+            raise ValueError(f"Unsupported state_type type: {self.state_type}. "
+                             "Must be StateType.AMP, StateType.DM, or StateType.PROB.")
+        if not np.allclose(np.sum(list(values.values())), 1, atol=1e-12):
+            total = float(np.sum(list(values.values())))
+            if total == 0:
+                raise ValueError("The probability distribution sums to zero.")
+            prob = {k: v / total for k, v in values.items()}
+        else:
+            prob = values
+        if round_digits is None:
+            return prob
+        return {k: round(v, round_digits) for k, v in prob.items()}
+
+    def single_prob(self, occupation: tuple) -> float:
+        if self.state_type == StateType.SINGLE_PROB:
+            return float(self.tensor.array)
+        return self.prob_dist().get(occupation, 0.0)
+
+    def single_amplitude(self, occupation: tuple) -> complex:
+        if self.state_type == StateType.SINGLE_AMP:
+            return complex(self.tensor.array)
+        return self.amplitudes(normalise=False).get(occupation, 0.0)
+
+    @staticmethod
+    def _convert_array_to_dict(array: np.ndarray) -> dict:
+        # backends.py:274-289
+        array = np.asarray(array)
+        nz_flat = np.flatnonzero(array)
+        if nz_flat.size == 0:
+            return {}
+        nz_vals = array.flat[nz_flat]
+        nz_multi = np.vstack(np.unravel_index(nz_flat, array.shape)).T
+        return {tuple(idx): val for idx, val in zip(nz_multi, nz_vals)}
+
+    # ---- device paths ---------------------------------------------------------
+    def _prob_dist_pure(self) -> dict:
+        """backends.py:291-304 with ``abs(v) ** 2`` evaluated by b2_probs_amp."""
+        dev = self._resident()
+        from .. import runtime as rt
+        torch = _torch()
+        lib = rt.load()
+        n = dev.numel()
+        p = torch.empty(n, dtype=torch.float64, device=dev.device)
+        nz = torch.empty(n, dtype=torch.uint8, device=dev.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        rt.check(lib.b2_probs_amp(n, dev.data_ptr(), p.data_ptr(), nz.data_ptr(),
+                                  rt.dtype_code(_np_dtype(dev)), stream), "b2_probs_amp")
+        p_h, nz_h = p.cpu().numpy(), nz.cpu().numpy()
+        flat = np.flatnonzero(nz_h)
+        if flat.size == 0:
+            return {}
+        multi = np.vstack(np.unravel_index(flat, self.tensor.array.shape)).T
+        return {tuple(idx): val for idx, val in zip(multi, p_h[flat])}
+
+    def _prob_dist_mixed(self) -> dict:
+        """backends.py:306-356 with the diagonal partial trace on the device."""
+        names = self._type_names()
+        if not any(t in {"bit", "mode"} for t in names):
+            raise ValueError("Output types must contain at least one 'bit' or 'mode'."
+                             "These will be treated as measured registers. "
+                             f"Current output types: {self.output_types}")
+        kinds = []
+        for t in names:
+            kinds.extend([1] if t in {"bit", "mode"} else [2, 3])
+        shape = self.tensor.array.shape
+        assert len(kinds) == len(shape), "result axes do not match the output types"
+        dev = self._resident()
+        from .. import runtime as rt
+        torch = _torch()
+        lib = rt.load()
+        meas_shape = tuple(d for d, k in zip(shape, kinds) if k == 1)
+        n_meas = int(np.prod(meas_shape, dtype=np.int64))
+        p = torch.empty(n_meas, dtype=torch.float64, device=dev.device)
+        seen = torch.empty(n_meas, dtype=torch.uint8, device=dev.device)
+        mx = torch.empty(1, dtype=torch.float64, device=dev.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        nd = len(shape)
+        rt.check(lib.b2_probs_dm(nd, (C.c_int32 * nd)(*shape), (C.c_int32 * nd)(*kinds),
+                                 dev.data_ptr(), p.data_ptr(), seen.data_ptr(), mx.data_ptr(),
+                                 rt.dtype_code(_np_dtype(dev)), stream), "b2_probs_dm")
+        p_h, seen_h, mx_h = p.cpu().numpy(), seen.cpu().numpy(), float(mx.cpu().numpy()[0])
+        # float(np.real_if_close(amp)) raises for a genuinely complex diagonal
+        # entry (backends.py:348); tol = 100 machine epsilons
+        if mx_h >= 100 * np.finfo(np.float64).eps:
+            raise TypeError("can't convert complex to float")
+        flat = np.flatnonzero(seen_h)
+        probs = defaultdict(float)
+        if flat.size:
+            multi = np.vstack(np.unravel_index(flat, meas_shape)).T
+            for idx, val in zip(multi, p_h[flat]):
+                probs[tuple(idx)] = float(val)
+        return probs
+
+    def _resident(self):
+        """The result on the device (uploaded again if it only lives on host)."""
+        if self._device is not None:
+            return self._device
+        from ..executor import require_cuda
+        torch = require_cuda()
+        arr = np.ascontiguousarray(self.tensor.array)
+        if arr.dtype not in (np.complex128, np.complex64):
+            arr = arr.astype(np.complex128)
+        return torch.from_numpy(arr).cuda()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_dtype(dev):
+    return np.complex64 if dev.dtype == _torch().complex64 else np.complex128
+
+
+class AbstractBackend(ABC):
+    """backends.py:360-427"""
+
+    def _get_network(self, diagram: channel.Diagram, nested_eval=None) -> nw.Network:
+        """``_get_discopy_tensor`` (backends.py:406-415): Kraus map of a pure
+        circuit, CP-doubled diagram otherwise."""
+        if diagram.is_pure:
+            return diagram.get_kraus().to_network(nested_eval=nested_eval)
+        return diagram.double().to_network(nested_eval=nested_eval)
+
+    @abstractmethod
+    def eval(self, diagram: channel.Diagram, **extra: Any) -> EvalResult:
+        """Evaluate the diagram."""
+
+
+class B200Backend(AbstractBackend):
+    """Evaluate on one B200 (or, for sliced networks, on every rank of an
+    initialised ``torch.distributed`` NCCL group -- see ``optyx_b200.dist``).
+
+    Parameters mirror ``QuimbBackend(hyperoptimiser, contraction_params)``
+    (backends.py:436-455): ``dtype`` ("complex128" / "complex64"),
+    ``target_size`` (slice until the largest intermediate has at most this
+    many elements), ``trials``/``seed`` of the path search, ``distributed``
+    (partition slices over ranks and sum with one NCCL all-reduce).
+    """
+
+    def __init__(self, dtype="complex128", target_size: Optional[int] = None, trials: int = 8,
+                 seed: int = 0, distributed: bool = False, keep_on_device: bool = True):
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.complex128), np.dtype(np.complex64)):
+            raise ValueError(f"Unsupported dtype {dtype}: use complex128 or complex64")
+        self.target_size = target_size
+        self.trials, self.seed = trials, seed
+        self.distributed = distributed
+        self.keep_on_device = keep_on_device
+        self.last_plan = None
+
+    def _nested_eval(self, net: nw.Network) -> np.ndarray:
+        from .. import executor
+        return executor.evaluate(net, dtype=np.complex128).cpu().numpy()
+
+    def eval_network(self, net: nw.Network):
+        """Device tensor of one network (plan cached by structure)."""
+        from .. import executor
+        plan = executor.get_plan(net, dtype=self.dtype, target_size=self.target_size,
+                                 trials=self.trials, seed=self.seed)
+        self.last_plan = plan
+        sess = executor.Session(plan)
+        if self.distributed:
+            from .. import dist
+            return dist.run_sliced(sess, net)
+        return sess.run([net])[0]
+
+    def eval(self, diagram: channel.Diagram, **extra: Any) -> EvalResult:
+        net = self._get_network(diagram, nested_eval=self._nested_eval)
+        dev = self.eval_network(net)
+        array = dev.cpu().numpy()
+        n = net.n_dom
+        shape = net.output_shape
+        state_type = StateType.AMP if diagram.is_pure else StateType.DM
+        return EvalResult(ResultTensor(shape[:n], shape[n:], array),
+                          output_types=diagram.cod, state_type=state_type,
+                          _device=dev if self.keep_on_device else None)

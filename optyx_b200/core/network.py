@@ -108,11 +108,14 @@ class NetworkBuilder:
     (``tensor.Spider`` emitted at diagram.py:689, 705-707; zw.py:357-359) by
     union-find, so COPY tensors are never materialised."""
 
-    def __init__(self):
+    def __init__(self, nested_eval=None):
         self._parent: List[int] = []
         self._dim: List[int] = []
         self.leaves: List[Leaf] = []
         self.scalar: complex = 1.0 + 0j
+        # callable(Network) -> ndarray used by leaves that are themselves
+        # contracted sub-networks (BitControlledBox, control.py:164-191)
+        self.nested_eval = nested_eval
 
     # -- indices ------------------------------------------------------------
     def new_index(self, dim: int) -> int:
