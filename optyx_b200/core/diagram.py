@@ -594,6 +594,11 @@ def get_max_dim_for_box(left_offset: int, box, right_offset: int, input_dims: Li
     if len(box.dom) == 0 or isinstance(box, (Swap, Endo, Divide, Multiply)):
         return UNCAPPED
     dim_for_box = 0
+    if "mode" not in box.dom.inside:
+        # an empty cone stays empty through every earlier layer (utils.py:359-373,
+        # 494-500), so the walk below would return max(0 + 1, 2): skip the
+        # O(#boxes) walk -- exact, and it makes qubit circuits O(#boxes) overall
+        return 2
     cone: List[bool] = ([False] * left_offset + [t == "mode" for t in box.dom.inside]
                         + [False] * right_offset)
     for prev_left, prev_box in prev_layers[::-1]:

@@ -186,32 +186,64 @@ def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
 
 
 def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
-               max_slices: int = 1 << 20) -> PathInfo:
+               max_slices: int = 1 << 24) -> PathInfo:
     """Greedy index slicing until the largest intermediate fits ``target_size``
-    elements: repeatedly fix the index (taken from the currently largest
-    intermediates) that costs the fewest extra MACs."""
+    elements.  Works on step x index incidence matrices (numpy): each round
+    scores every candidate index by (bits of oversize removed over all oversized
+    intermediates) per (bit of total-MAC overhead) and fixes the best one."""
+    path = info.path
+    if not path:
+        return info
+    ids = sorted({q for s in inputs for q in s})
+    col = {q: k for k, q in enumerate(ids)}
+    logd = np.array([math.log2(dims[q]) for q in ids])
+    n_steps = len(path)
+    U = np.zeros((n_steps, len(ids)), dtype=bool)      # union of the pair's indices
+    R = np.zeros((n_steps, len(ids)), dtype=bool)      # result indices
+    tens = {k: frozenset(v) for k, v in enumerate(inputs)}
+    nxt = len(inputs)
+    for k, ((a, b), res) in enumerate(zip(path, info.step_inds)):
+        for q in tens.pop(a) | tens.pop(b):
+            U[k, col[q]] = True
+        for q in res:
+            R[k, col[q]] = True
+        tens[nxt] = res
+        nxt += 1
+    Uf, Rf = U.astype(np.float64), R.astype(np.float64)
+    allowed = np.ones(len(ids), dtype=bool)
+    for q in output:
+        if q in col:
+            allowed[col[q]] = False
+    allowed &= logd > 0
+    cur_u, cur_r = Uf @ logd, Rf @ logd
+    log_target = math.log2(target_size)
     sliced: List[int] = []
-    cur = info
-    out = set(output)
-    while cur.peak > target_size and cur.nslices < max_slices:
-        sl = set(sliced)
-        big = sorted(cur.step_inds, key=lambda s: -_prod(dims, [q for q in s if q not in sl]))
-        cands: List[int] = []
-        for s in big[:4]:
-            for q in s:
-                if q not in sl and q not in out and dims[q] > 1 and q not in cands:
-                    cands.append(q)
-        if not cands:
+    log_slices = 0.0
+    while cur_r.max() > log_target + 1e-9 and log_slices < math.log2(max_slices):
+        over = cur_r > log_target + 1e-9
+        cand = np.flatnonzero(allowed & R[over].any(axis=0))
+        if cand.size == 0:
             break
-        best = None
-        for q in cands:
-            trial = analyse_path(inputs, dims, output, cur.path, sliced + [q])
-            key = (trial.peak > target_size, trial.macs * trial.nslices, trial.peak)
-            if best is None or key < best[0]:
-                best = (key, q, trial)
-        sliced.append(best[1])
-        cur = best[2]
-    return cur
+        excess_now = np.maximum(cur_r - log_target, 0.0).sum()
+        macs_now = np.logaddexp2.reduce(cur_u) + log_slices
+        # candidate scores, vectorised over candidates
+        new_r = cur_r[:, None] - Rf[:, cand] * logd[cand][None, :]
+        excess = np.maximum(new_r - log_target, 0.0).sum(axis=0)
+        new_u = cur_u[:, None] - Uf[:, cand] * logd[cand][None, :]
+        macs = np.logaddexp2.reduce(new_u, axis=0) + log_slices + logd[cand]
+        gain = excess_now - excess
+        overhead = np.maximum(macs - macs_now, 0.0)
+        score = gain / (overhead + 0.05)
+        j = int(np.argmax(score))
+        if gain[j] <= 0:
+            break
+        c = int(cand[j])
+        sliced.append(ids[c])
+        allowed[c] = False
+        cur_r = cur_r - Rf[:, c] * logd[c]
+        cur_u = cur_u - Uf[:, c] * logd[c]
+        log_slices += logd[c]
+    return analyse_path(inputs, dims, output, path, sliced)
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,147 @@
+"""-m gpu: ``diagram.eval(B200Backend())`` end to end (leaf build -> plan ->
+CUDA contractions -> prob kernels, all through the C ABI) against the oracle
+and the reference's known answers."""
+import numpy as np
+import pytest
+
+from cases import (cfg1_interferometer, cfg3_interferometer, compile_channel, distinguishable_bs,
+                   fusion_i_spider, fusion_ii_teleportation, ghz, lossy_hom, oracle_eval,
+                   random_clifford_t, statevector_clifford_t)
+from oracle import evalresult as ev
+from oracle.contract import contract_network
+from optyx_b200 import classical, photonic, qubits
+from optyx_b200.core.backends import B200Backend, EvalResult, ResultTensor, StateType
+from optyx_b200.core.channel import bit, qubit
+
+pytestmark = pytest.mark.gpu
+
+TOL128, TOL64 = 1e-10, 1e-5
+
+
+def _close(got, want, tol):
+    scale = max(1.0, float(np.abs(want).max())) if np.size(want) else 1.0
+    return np.abs(np.asarray(got) - np.asarray(want)).max() <= tol * scale
+
+
+def _types(d):
+    return list(d.cod.inside)
+
+
+def _check_prob_dist(res, arr, d):
+    st = ev.AMP if res.state_type is StateType.AMP else ev.DM
+    want = ev.prob_dist(arr, _types(d), st)
+    got = res.prob_dist()
+    assert {tuple(int(i) for i in k) for k in got} == set(want)       # exact key set
+    for k, v in got.items():
+        assert abs(v - want[tuple(int(i) for i in k)]) <= 1e-10
+
+
+CASES = {
+    "lossy_hom": lambda: lossy_hom(0.8),
+    "bs_pure": lambda: photonic.Create(1, 1) >> photonic.BS,
+    "mzi_chip_pure": lambda: photonic.Create(1, 1, 1, 1) >> photonic.seeded_ansatz(4, 4, 3),
+    "cfg1_4mode": lambda: cfg1_interferometer(4, (1, 1, 0, 0)),
+    "cfg1_6mode": lambda: cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)),
+    "ghz6_measured": lambda: ghz(6, measure=True),
+    "ghz5_noisy_open3": lambda: ghz(5, open_qubits=3, noise=0.95),
+    "ghz8_noisy_measured": lambda: ghz(8, noise=0.95, measure=True),
+    "bitflip": lambda: qubits.Z(0, 1) >> qubits.BitFlipError(0.43),
+    "hom_distinguishable": lambda: distinguishable_bs(np.array([0.6, 0.8j]), np.array([1, 0])),
+    "cfg3_small": lambda: cfg3_interferometer(width=3, n_photons=2, measured=2, depth=2),
+    "cfg3_4mode": lambda: cfg3_interferometer(width=4, n_photons=2, measured=2),
+    "clifford_t_8x6": lambda: random_clifford_t(8, 6, seed=2),
+    "fusion_ii": fusion_ii_teleportation,
+    "fusion_i": fusion_i_spider,
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_eval_matches_oracle_complex128(name):
+    d = CASES[name]()
+    want = oracle_eval(d)
+    res = d.eval(B200Backend())
+    assert res.tensor.array.shape == want.shape                        # exact bookkeeping
+    assert res.tensor.array.dtype == np.complex128
+    assert _close(res.tensor.array, want, TOL128), name
+    if len(res.tensor.dom) == 0 and (res.state_type is StateType.AMP or
+                                     any(t in ("bit", "mode") for t in _types(d))):
+        if name not in ("bitflip",) and want.ndim > 0:
+            _check_prob_dist(res, want, d)
+
+
+@pytest.mark.parametrize("name", ["lossy_hom", "cfg1_4mode", "ghz6_measured", "clifford_t_8x6",
+                                  "cfg3_small"])
+def test_eval_matches_oracle_complex64(name):
+    d = CASES[name]()
+    want = oracle_eval(d)
+    res = d.eval(B200Backend(dtype="complex64"))
+    assert res.tensor.array.dtype == np.complex64
+    assert _close(res.tensor.array, want, TOL64), name
+
+
+def test_known_answers_through_the_backend():
+    p = lossy_hom(0.8).eval(B200Backend()).prob_dist()
+    assert p[(1,)] == pytest.approx(0.2, abs=1e-12)                    # README.md:176-178
+    r = (photonic.Create(1, 1) >> photonic.BS).eval(B200Backend())
+    assert round(r.single_prob((2, 0)), 1) == 0.5                      # backends.py:41-47
+    a = (qubits.Z(0, 1) >> qubits.DephasingError(0.43)).eval(B200Backend()).tensor.array
+    assert np.allclose(a, np.array([[-.14, 1.], [1, -0.14]]))          # test_qubit.py:112-115
+    bell = qubits.Scalar(0.5 ** 0.5) @ qubits.Z(0, 2)
+    tele = (qubit @ bell >> qubits.gate("CX") @ qubit >> qubits.H() @ qubit ** 2
+            >> qubits.Measure(1) @ qubits.Measure(1) @ qubit >> bit @ classical.CtrlX
+            >> classical.CtrlZ)
+    t = tele.eval(B200Backend()).tensor.array
+    assert t.shape == (2, 2, 2, 2)
+    assert np.allclose(t, np.einsum("ac,bd->abcd", np.eye(2), np.eye(2)))   # README.md:88-93
+    p = ghz(10, measure=True).eval(B200Backend()).prob_dist()
+    assert set(tuple(int(i) for i in k) for k, v in p.items() if v > 1e-12) == \
+        {(0,) * 10, (1,) * 10}
+
+
+def test_sliced_eval_matches_unsliced_and_statevector():
+    d = random_clifford_t(10, 8, seed=5)
+    want = statevector_clifford_t(10, 8, seed=5)
+    full = d.eval(B200Backend()).tensor.array
+    backend = B200Backend(target_size=4)
+    sliced = d.eval(backend).tensor.array
+    assert backend.last_plan.nslices > 1
+    assert abs(complex(full) - want) <= 1e-10 and abs(complex(sliced) - want) <= 1e-10
+
+
+def test_reference_literal_evalresult_cases_on_device_kernels():
+    """test/test_backends.py:276-294, 331-345 through the product EvalResult
+    (host array uploaded, probs computed by the CUDA kernels)."""
+    dm = np.zeros((2, 2, 2), dtype=complex)
+    dm[0, 0, 0] = 0.499999999999 + 1e-14j
+    dm[0, 1, 1] = 0.100000000001 - 1e-14j
+    dm[1, 0, 0] = 0.2000000000005 + 1e-14j
+    dm[1, 1, 1] = 0.2000000000005 - 1e-14j
+    dm[0, 0, 1] = -1e-13
+    dm[1, 1, 0] = -1e-13
+    r = EvalResult(ResultTensor((), dm.shape, dm), ("mode", "qubit"), StateType.DM)
+    probs = r.prob_dist()
+    assert probs[(0,)] == pytest.approx(0.6, rel=1e-12)
+    assert probs[(1,)] == pytest.approx(0.4, rel=1e-12)
+    off = np.zeros((2, 2, 2))
+    off[0, 0, 1], off[1, 1, 0] = 0.6, 0.4
+    r = EvalResult(ResultTensor((), off.shape, off), ("mode", "qubit"), StateType.DM)
+    with pytest.raises(ValueError):
+        r.prob_dist()
+    v = np.array([1 / np.sqrt(2), 1j / np.sqrt(2)])
+    r = EvalResult(ResultTensor((), (2,), v), ("mode",), StateType.AMP)
+    assert r.single_prob((0,)) == pytest.approx(0.5, rel=1e-12)
+    assert r.single_prob((2,)) == 0.0
+
+
+def test_ghz_density_matrix_large_output():
+    """cfg2-shaped: 12 qubits, 7 open (2^14-entry density tensor), against the
+    closed form rho = (|0..0><0..0| + |1..1><1..1| + (2p-1)^n-weighted coherences)."""
+    n, k = 12, 7
+    d = ghz(n, open_qubits=k)
+    res = d.eval(B200Backend())
+    arr = res.tensor.array
+    assert arr.shape == (2,) * (2 * k)
+    want = np.zeros((2,) * (2 * k), dtype=complex)
+    want[(0,) * (2 * k)] = 0.5
+    want[(1,) * (2 * k)] = 0.5
+    assert _close(arr, want, TOL128)                                   # discarded qubits decohere
