@@ -38,7 +38,7 @@ def workload(name: str, small: bool = False):
     """(diagram factory, description).  ``small``: the bounded CPU sample."""
     import cases
     if name == "cfg2":
-        n, k = (20, 14) if not small else (20, 9)
+        n, k = (20, 14)        # the CPU arm runs the full-size workload too (~20 s/eval)
         return (lambda: cases.ghz(n, open_qubits=k, noise=0.95),
                 f"cfg2: {n}-qubit GHZ, DephasingError(0.95) on every qubit, CP-doubled, "
                 f"{k} qubits open / {n - k} discarded -> (2,)^{2 * k} density tensor")
@@ -143,7 +143,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        base, t = cpu_reference(args.workload, max(1, min(args.steps, 5)), 1)
+        base, t = cpu_reference(args.workload, max(1, min(args.steps, 3)), 0)
         _, desc = workload(args.workload, small=True)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
@@ -285,7 +285,7 @@ def main():
     if not args.no_sliced:
         out["sliced"] = run_sliced(world, rank)
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"], _ = cpu_reference(args.workload, 3, 1)
+        out["cpu_baseline"], _ = cpu_reference(args.workload, 2, 0)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

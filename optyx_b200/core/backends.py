@@ -273,10 +273,21 @@ class B200Backend(AbstractBackend):
             return dist.run_sliced(sess, net)
         return sess.run([net])[0]
 
+    @staticmethod
+    def _to_host(dev) -> np.ndarray:
+        """Device -> host through a pinned buffer from torch's caching host
+        allocator: the returned numpy array owns its (page-locked) block, which
+        is recycled for a later eval once the caller drops the result."""
+        torch = _torch()
+        host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
     def eval(self, diagram: channel.Diagram, **extra: Any) -> EvalResult:
         net = self._get_network(diagram, nested_eval=self._nested_eval)
         dev = self.eval_network(net)
-        array = dev.cpu().numpy()
+        array = self._to_host(dev)
         n = net.n_dom
         shape = net.output_shape
         state_type = StateType.AMP if diagram.is_pure else StateType.DM

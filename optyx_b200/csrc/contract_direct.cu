@@ -2,20 +2,30 @@
 //
 //   C[out] (+)= alpha * sum_red A[out|red] * B[out|red]
 //
-// One thread per output element (grid-stride, grid sized in multiples of the
-// SM count).  The index permutation the reference performs as a separate
-// transpose pass before BLAS (numpy.tensordot under quimb, reached from
+// The index permutation the reference performs as a separate transpose pass
+// before BLAS (numpy.tensordot under quimb, reached from
 // optyx/core/backends.py:514 / 539-545) is fused into the address computation:
-// every mode carries its own stride into A, B and C; stride 0 broadcasts.  The
-// host merges stride-compatible modes first, so a typical step decodes 2-6
-// modes per element.  C is written in its memory order (coalesced 16 B stores);
-// A/B reads are coalesced whenever the fastest output mode is also fast in the
-// operand, otherwise they are served by L1/L2.
+// every mode carries its own stride into A, B and C; stride 0 broadcasts.
+//
+// Two kernels:
+//  * tiled (default): the fastest output modes form a tile of up to 2048
+//    elements that is CONTIGUOUS in C.  Their A/B offsets depend only on the
+//    position inside the tile, so they are decoded once per CTA into shared
+//    memory, as are the offsets of the reduction modes; each persistent CTA
+//    then walks tiles (grid = SMs x resident CTAs), decoding only the outer
+//    modes per tile.  Per element: 2 LDS + R x (2 LDS + 2 LDG.128 + 4 DFMA) +
+//    one coalesced STG.128.
+//  * generic (fallback): one thread per output element with a full decode, for
+//    outputs that are not contiguous (generalised diagonals) or reductions too
+//    long for the table.
 #include "b2_common.cuh"
 
 namespace b2 {
 
 constexpr int kMaxRed = 16;
+constexpr int kTileMax = 2048;
+constexpr int kRedTableMax = 512;
+constexpr int kTiledThreads = 256;
 
 template <typename T, typename I>
 __global__ void __launch_bounds__(256)
@@ -75,6 +85,139 @@ contract_direct_kernel(const __grid_constant__ b2_modes md,
     }
 }
 
+// ---- tiled kernel -------------------------------------------------------------
+// modes [0, n_outer) are decoded per tile; modes [n_outer, n_out) span the tile
+// (contiguous in C, fastest last); modes [n_out, n_out + n_red) are summed.
+template <typename T>
+__global__ void __launch_bounds__(kTiledThreads)
+contract_direct_tiled_kernel(const __grid_constant__ b2_modes md, int n_outer, int tile,
+                             int n_red_elems, long long n_tiles,
+                             const typename cplx<T>::type* __restrict__ A,
+                             const typename cplx<T>::type* __restrict__ B,
+                             typename cplx<T>::type* __restrict__ Cout, T alpha_re, T alpha_im,
+                             int accumulate) {
+    using C = typename cplx<T>::type;
+    extern __shared__ long long tab[];
+    long long* ia = tab;                 // [tile]
+    long long* ib = tab + tile;          // [tile]
+    long long* ra = tab + 2 * tile;      // [n_red_elems]
+    long long* rb = ra + n_red_elems;    // [n_red_elems]
+    const int n_out = md.n_out, n_red = md.n_red;
+    for (int e = threadIdx.x; e < tile; e += kTiledThreads) {
+        long long oa = 0, ob = 0;
+        int rem = e;
+        for (int m = n_out - 1; m >= n_outer; --m) {
+            const int d = md.dim[m];
+            const int q = rem / d;
+            const long long i = rem - q * d;
+            rem = q;
+            oa += i * md.sa[m];
+            ob += i * md.sb[m];
+        }
+        ia[e] = oa; ib[e] = ob;
+    }
+    for (int r = threadIdx.x; r < n_red_elems; r += kTiledThreads) {
+        long long oa = 0, ob = 0;
+        int rem = r;
+        for (int m = n_out + n_red - 1; m >= n_out; --m) {
+            const int d = md.dim[m];
+            const int q = rem / d;
+            const long long i = rem - q * d;
+            rem = q;
+            oa += i * md.sa[m];
+            ob += i * md.sb[m];
+        }
+        ra[r] = oa; rb[r] = ob;
+    }
+    __syncthreads();
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        long long oa = 0, ob = 0, oc = 0;
+        long long rem = t;
+        for (int m = n_outer - 1; m >= 0; --m) {
+            const long long d = md.dim[m];
+            const long long q = rem / d;
+            const long long i = rem - q * d;
+            rem = q;
+            oa += i * md.sa[m];
+            ob += i * md.sb[m];
+            oc += i * md.sc[m];
+        }
+        const C* __restrict__ At = A + oa;
+        const C* __restrict__ Bt = B + ob;
+        C* __restrict__ Ct = Cout + oc;
+        #pragma unroll 2
+        for (int e = threadIdx.x; e < tile; e += kTiledThreads) {
+            const C* a = At + ia[e];
+            const C* b = Bt + ib[e];
+            C acc = make_c<T>((T)0, (T)0);
+            if (n_red_elems == 1) {
+                cfma(acc, a[0], b[0]);
+            } else {
+                #pragma unroll 4
+                for (int r = 0; r < n_red_elems; ++r) cfma(acc, a[ra[r]], b[rb[r]]);
+            }
+            C res;
+            res.x = alpha_re * acc.x - alpha_im * acc.y;
+            res.y = alpha_re * acc.y + alpha_im * acc.x;
+            if (accumulate) { const C old = Ct[e]; res.x += old.x; res.y += old.y; }
+            Ct[e] = res;
+        }
+    }
+}
+
+// Split the output modes of `md` into outer/inner for the tiled kernel.  The
+// inner modes are the longest C-contiguous tail whose extent fits kTileMax; one
+// mode may be split (dim = q * f) so that the tile is as large as possible.
+// Returns false when the output is not contiguous in its fastest mode.
+static bool make_tiled(const b2_modes& md, long long n_out_elems, int sms, b2_modes& out,
+                       int& n_outer, int& tile) {
+    const int no = md.n_out;
+    if (no == 0) return false;
+    if (md.sc[no - 1] != 1) return false;
+    // keep tiles small enough to give every SM a few of them
+    long long cap = kTileMax;
+    while (cap > 256 && n_out_elems / cap < (long long)sms * 4) cap >>= 1;
+    long long ext = 1;
+    int first_inner = no;             // modes [first_inner, no) fully inside the tile
+    int split_mode = -1, split_f = 1;
+    for (int m = no - 1; m >= 0; --m) {
+        if (md.sc[m] != ext) break;   // not nested-contiguous in C any more
+        const long long d = md.dim[m];
+        if (ext * d <= cap) { ext *= d; first_inner = m; continue; }
+        // partial: largest divisor f of d with ext * f <= cap
+        int best = 1;
+        for (int f = 2; (long long)f * ext <= cap && f <= d; ++f)
+            if (d % f == 0) best = f;
+        if (best > 1) { split_mode = m; split_f = best; ext *= best; }
+        break;
+    }
+    if (ext < 32) return false;       // tile too small to be worth the tables
+    if (split_mode >= 0 && md.n_out + md.n_red + 1 > B2_MAX_MODES) return false;
+    out = md;
+    if (split_mode >= 0) {
+        // shift modes after split_mode by one; insert the inner part
+        for (int m = md.n_out + md.n_red; m > split_mode + 1; --m) {
+            out.dim[m] = md.dim[m - 1]; out.sa[m] = md.sa[m - 1];
+            out.sb[m] = md.sb[m - 1]; out.sc[m] = md.sc[m - 1];
+        }
+        const int d = md.dim[split_mode];
+        out.dim[split_mode] = d / split_f;
+        out.sa[split_mode] = md.sa[split_mode] * split_f;
+        out.sb[split_mode] = md.sb[split_mode] * split_f;
+        out.sc[split_mode] = md.sc[split_mode] * split_f;
+        out.dim[split_mode + 1] = split_f;
+        out.sa[split_mode + 1] = md.sa[split_mode];
+        out.sb[split_mode + 1] = md.sb[split_mode];
+        out.sc[split_mode + 1] = md.sc[split_mode];
+        out.n_out = md.n_out + 1;
+        n_outer = split_mode + 1;
+    } else {
+        n_outer = first_inner;
+    }
+    tile = (int)ext;
+    return true;
+}
+
 template <typename T>
 int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, double ar,
                   double ai, int accumulate, cudaStream_t s) {
@@ -83,10 +226,25 @@ int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, dou
     for (int m = 0; m < md->n_out; ++m) n_out_elems *= md->dim[m];
     for (int m = 0; m < md->n_red; ++m) n_red_elems *= md->dim[md->n_out + m];
     if (n_out_elems == 0) return 0;
-    const int threads = 256;
-    long long blocks = (n_out_elems + threads - 1) / threads;
     int sms = num_sms();
     if (sms <= 0) return 1;
+
+    b2_modes tiled;
+    int n_outer = 0, tile = 0;
+    if (n_red_elems <= kRedTableMax && make_tiled(*md, n_out_elems, sms, tiled, n_outer, tile)) {
+        const long long n_tiles = n_out_elems / tile;
+        const size_t smem = (size_t)(2 * tile + 2 * n_red_elems) * sizeof(long long);
+        long long blocks = n_tiles;
+        const long long cap = (long long)sms * 6;
+        if (blocks > cap) blocks = cap;
+        contract_direct_tiled_kernel<T><<<(unsigned)blocks, kTiledThreads, smem, s>>>(
+            tiled, n_outer, tile, (int)n_red_elems, n_tiles, (const C*)a, (const C*)b, (C*)c,
+            (T)ar, (T)ai, accumulate);
+        return check_launch("b2_contract_direct(tiled)");
+    }
+
+    const int threads = 256;
+    long long blocks = (n_out_elems + threads - 1) / threads;
     long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
     if (n_out_elems < (1ll << 31))

@@ -170,21 +170,86 @@ class Session:
         return self.out
 
     # ---- CUDA graph ---------------------------------------------------------
-    def capture(self, scalar: complex = 1.0) -> None:
+    def contract_branches(self, scalar: complex, n_streams: int = 8) -> None:
+        """Unsliced plan with independent subtrees issued on different streams
+        (fork after the leaf build, join before the end).  Under stream capture
+        the event waits become graph edges, so the captured graph is the
+        contraction TREE, not a chain: tiny steps of different branches overlap
+        instead of paying one launch latency each."""
+        torch, plan = self.torch, self.plan
+        assert plan.parallel_safe and not plan.sliced
+        origin = torch.cuda.current_stream()
+        if plan.needs_zero_out:
+            rt.check(self.lib.b2_fill_zero(self.out.numel(), self.out.data_ptr(), self.code,
+                                           origin.cuda_stream), "b2_fill_zero")
+        if not hasattr(self, "_pool") or len(self._pool) != n_streams:
+            self._pool = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        pool = self._pool
+        fork = torch.cuda.Event()
+        fork.record(origin)
+        for s in pool:
+            s.wait_event(fork)
+        producer = {}                       # id(layout) -> step index
+        for k, st in enumerate(plan.steps):
+            producer[id(st.c)] = k
+        where = {}                          # step index -> stream index
+        consumers_elsewhere = {}            # step index -> event (recorded after launch)
+        # first pass: stream assignment (inherit the larger operand's stream)
+        rr = 0
+        for k, st in enumerate(plan.steps):
+            pa, pb = producer.get(id(st.a)), producer.get(id(st.b))
+            if pa is not None:
+                where[k] = where[pa]
+            elif pb is not None:
+                where[k] = where[pb]
+            else:
+                where[k] = rr % n_streams
+                rr += 1
+        need_event = set()
+        for k, st in enumerate(plan.steps):
+            for p in (producer.get(id(st.a)), producer.get(id(st.b))):
+                if p is not None and where[p] != where[k]:
+                    need_event.add(p)
+        events = {}
+        zeros = [0] * len(plan.sliced)
+        scalar = complex(scalar)
+        for k, st in enumerate(plan.steps):
+            stream = pool[where[k]]
+            for p in (producer.get(id(st.a)), producer.get(id(st.b))):
+                if p is not None and where[p] != where[k]:
+                    stream.wait_event(events[p])
+            self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream.cuda_stream)
+            if k in need_event:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                events[k] = ev
+        for s in pool:
+            join = torch.cuda.Event()
+            join.record(s)
+            origin.wait_event(join)
+
+    def capture(self, scalar: complex = 1.0, branches: bool = True) -> None:
         """Capture leaf build + all contraction launches into one CUDA graph
         (launch-bound small networks: hundreds of tiny steps per eval)."""
         torch = self.torch
         assert self.desc_dev is not None, "set_leaves first"
+        use_branches = branches and self.plan.parallel_safe and not self.plan.sliced
+
+        def body():
+            self.build_leaves()
+            if use_branches:
+                self.contract_branches(scalar)
+            else:
+                self.contract(scalar)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self.build_leaves()
-            self.contract(scalar)
+            body()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.build_leaves()
-            self.contract(scalar)
+            body()
         self.graph = graph
 
     def replay(self) -> None:
@@ -195,7 +260,7 @@ _PLAN_CACHE: Dict[tuple, Plan] = {}
 
 
 def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None,
-             trials: int = 8, seed: int = 0, gemm_threshold=(16, 16, 4)) -> Plan:
+             trials: int = 8, seed: int = 0, gemm_threshold=(32, 16, 8, 4.0)) -> Plan:
     """Plan cache keyed by network *structure* (the counterpart of cotengra's
     ReusableHyperOptimizer the reference accepts, backends.py:49-56, 436-455)."""
     key = (net.structure_key(), np.dtype(dtype).str, batch, target_size, trials, seed,

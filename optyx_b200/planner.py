@@ -250,6 +250,7 @@ def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
 # layouts and step compilation
 # --------------------------------------------------------------------------
 ARENA, WS, OUT = 0, 1, 2
+PARALLEL_WS_BYTES = 256 << 20
 
 
 @dataclass
@@ -299,6 +300,7 @@ class Plan:
     info: PathInfo
     total_macs: float = 0.0
     total_bytes: float = 0.0
+    parallel_safe: bool = False   # no workspace recycling: branches may overlap
 
 
 class _Allocator:
@@ -353,7 +355,7 @@ def _merge_modes(modes: List[List[int]], fastest_last: bool) -> List[List[int]]:
 
 
 def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int = 1,
-                 gemm_threshold: Tuple[int, int, int] = (16, 16, 4)) -> Plan:
+                 gemm_threshold: Tuple = (32, 16, 8, 4.0)) -> Plan:
     """Turn a pair order into executable steps (layouts, descriptors, memory)."""
     dtype = np.dtype(dtype)
     esize = dtype.itemsize
@@ -476,8 +478,14 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
         def mode(q):
             return [dims[q], la.stride_of(q), lb.stride_of(q), lc.stride_of(q)]
 
+        # tensor-core path only for pairs that really are dense GEMMs: big enough
+        # in every extent AND above the FP64 ridge (~5.7 flop/B on B200: 37 TF/s
+        # over 6.5 TB/s); everything else is bandwidth work for the direct kernel
+        intensity = 8.0 * macs / max(nbytes, 1.0)
+        min_ai = gemm_threshold[3] if len(gemm_threshold) > 3 else 0.0
         use_gemm = (dtype == np.complex128 and Mx >= gemm_threshold[0]
-                    and Nx >= gemm_threshold[1] and Kx >= gemm_threshold[2])
+                    and Nx >= gemm_threshold[1] and Kx >= gemm_threshold[2]
+                    and intensity >= min_ai)
         desc = None
         if not use_gemm:
             # out modes in C *memory* order so that stores are coalesced
@@ -528,13 +536,27 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
     # a slice-invariant buffer must survive all slices: the simple allocator
     # above may have recycled it for a per-slice tensor.  Re-run allocation in
     # two arenas when slicing is on.
+    parallel_safe = False
     if sliced:
         _reallocate_for_slices(steps, batch)
+    else:
+        # small plans: give every intermediate a private buffer so independent
+        # subtrees may run concurrently (parallel branches of one CUDA graph)
+        total = sum(st.c.size * batch for st in steps if st.c.space == WS)
+        if total * esize <= PARALLEL_WS_BYTES:
+            off = 0
+            for st in steps:
+                if st.c.space == WS:
+                    st.c.offset = off
+                    off += st.c.size * batch
+            parallel_safe = True
     ws_elems = max([st.c.offset + st.c.size * batch for st in steps if st.c.space == WS] or [0])
 
-    return Plan(steps, sliced, tuple(dims[q] for q in sliced), info.nslices, leaf_offsets,
+    plan = Plan(steps, sliced, tuple(dims[q] for q in sliced), info.nslices, leaf_offsets,
                 arena_elems, unit_offset, int(ws_elems), out_shape, out_elems,
                 needs_zero or bool(sliced), batch, dtype, info, total_macs, total_bytes)
+    plan.parallel_safe = parallel_safe
+    return plan
 
 
 def _reallocate_for_slices(steps: List[Step], batch: int) -> None:
@@ -559,7 +581,7 @@ def _reallocate_for_slices(steps: List[Step], batch: int) -> None:
 
 def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int = 8,
                  seed: int = 0, target_size: Optional[float] = None,
-                 gemm_threshold: Tuple[int, int, int] = (16, 16, 4)) -> Plan:
+                 gemm_threshold: Tuple = (32, 16, 8, 4.0)) -> Plan:
     """Path search (+ slicing to ``target_size`` elements) + compilation."""
     inputs = [frozenset(l.inds) for l in net.leaves]
     output = frozenset(net.output_inds)

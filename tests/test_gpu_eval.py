@@ -145,3 +145,29 @@ def test_ghz_density_matrix_large_output():
     want[(0,) * (2 * k)] = 0.5
     want[(1,) * (2 * k)] = 0.5
     assert _close(arr, want, TOL128)                                   # discarded qubits decohere
+
+
+@pytest.mark.parametrize("name", ["cfg1_4mode", "ghz8_noisy_measured", "cfg3_small"])
+def test_cuda_graph_with_parallel_branches_matches_plain_run(name):
+    """The captured graph (contraction tree as parallel branches) replays to the
+    same tensor as the stream-ordered run, also after new leaf values arrive."""
+    import torch
+    from optyx_b200 import executor
+    d = CASES[name]()
+    net = compile_channel(d)
+    want = contract_network(net)
+    plan = executor.get_plan(net)
+    sess = executor.Session(plan)
+    sess.set_leaves([net])
+    plain = sess.run([net])[0].cpu().numpy()
+    assert plan.parallel_safe
+    sess.capture(net.scalar)
+    sess.out.zero_()
+    sess.replay()
+    torch.cuda.synchronize()
+    got = sess.out[0].cpu().numpy()
+    assert _close(plain, want, TOL128) and _close(got, want, TOL128)
+    for _ in range(3):
+        sess.replay()
+    torch.cuda.synchronize()
+    assert _close(sess.out[0].cpu().numpy(), want, TOL128)
