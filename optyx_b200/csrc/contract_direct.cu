@@ -22,6 +22,9 @@
 
 namespace b2 {
 
+int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double ar, double ai,
+               int accumulate, int dtype, cudaStream_t s, bool& handled);
+
 constexpr int kMaxRed = 16;
 constexpr int kTileMax = 2048;
 constexpr int kRedTableMax = 512;
@@ -130,17 +133,37 @@ contract_direct_tiled_kernel(const __grid_constant__ b2_modes md, int n_outer, i
         ra[r] = oa; rb[r] = ob;
     }
     __syncthreads();
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        long long oa = 0, ob = 0, oc = 0;
-        long long rem = t;
+    // each CTA owns a CONTIGUOUS range of tiles: one full decode of the outer
+    // modes, then an odometer increment per tile (no divisions in the loop)
+    const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per;
+    const long long t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    if (t0 >= t1) return;
+    int cnt[B2_MAX_MODES];
+    long long oa = 0, ob = 0, oc = 0;
+    {
+        long long rem = t0;
         for (int m = n_outer - 1; m >= 0; --m) {
             const long long d = md.dim[m];
             const long long q = rem / d;
-            const long long i = rem - q * d;
+            const int i = (int)(rem - q * d);
             rem = q;
+            cnt[m] = i;
             oa += i * md.sa[m];
             ob += i * md.sb[m];
             oc += i * md.sc[m];
+        }
+    }
+    for (long long t = t0; t < t1; ++t) {
+        if (t != t0) {
+            for (int m = n_outer - 1; m >= 0; --m) {
+                oa += md.sa[m]; ob += md.sb[m]; oc += md.sc[m];
+                if (++cnt[m] < md.dim[m]) break;
+                oa -= (long long)md.dim[m] * md.sa[m];
+                ob -= (long long)md.dim[m] * md.sb[m];
+                oc -= (long long)md.dim[m] * md.sc[m];
+                cnt[m] = 0;
+            }
         }
         const C* __restrict__ At = A + oa;
         const C* __restrict__ Bt = B + ob;
@@ -229,6 +252,12 @@ int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, dou
     int sms = num_sms();
     if (sms <= 0) return 1;
 
+    {   // primary path: C-tiled, B block in shared memory, A rows in registers
+        bool handled = false;
+        const int dt = sizeof(T) == 8 ? B2_C128 : B2_C64;
+        int st = launch_fma(*md, a, b, c, ar, ai, accumulate, dt, s, handled);
+        if (st != 0 || handled) return st;
+    }
     b2_modes tiled;
     int n_outer = 0, tile = 0;
     if (n_red_elems <= kRedTableMax && make_tiled(*md, n_out_elems, sms, tiled, n_outer, tile)) {

@@ -1,0 +1,285 @@
+// Piece (2a), primary kernel for bandwidth-bound pairs with a short reduction
+// (K <= 16): outer products, "apply a small tensor to a huge one", thin pairs.
+//
+//   C[b, m, n] (+)= alpha * sum_k A[b, m, k] * B[b, k, n]
+//
+// Tiled from the output side like contract_ctile.cu: the CTA tile is TM x TN
+// elements made of the FASTEST C modes, oriented so that the fastest C mode is
+// a row (M) mode.  A work item is (row i, group of U columns): the thread pulls
+// the K values A[i, :] into registers once (16 B loads, lanes = consecutive rows
+// -> consecutive C addresses), reads B[:, j] as shared-memory broadcasts (the
+// TN x K block of B is staged once per tile, or once per CTA when it does not
+// change), does 4*K FMAs per output and stores each output straight from
+// registers: lanes of a warp write consecutive rows = consecutive addresses.
+// No accumulator staging, one barrier per tile, every load independent of every
+// other -> the kernel is limited by HBM, not by latency.
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr int FM_THREADS = 256, FM_TMAX = 16384, FM_MAXM = 512, FM_MAXN = 64, FM_U = 16;
+constexpr int FM_KMAX = 16;
+
+struct fm_desc {
+    int n_outer, n_im, n_in, n_k;       // mode counts, stored in this order
+    int TM, TN, K;
+    int b_static;                       // B's tile does not depend on the outer modes
+    int dim[B2_MAX_MODES];
+    long long sa[B2_MAX_MODES], sb[B2_MAX_MODES], sc[B2_MAX_MODES];
+};
+
+template <typename T, int KP>
+__global__ void __launch_bounds__(FM_THREADS)
+contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
+                    const typename cplx<T>::type* __restrict__ A,
+                    const typename cplx<T>::type* __restrict__ B,
+                    typename cplx<T>::type* __restrict__ Cout, T alpha_re, T alpha_im,
+                    int accumulate) {
+    using C = typename cplx<T>::type;
+    extern __shared__ __align__(16) unsigned char fm_smem[];
+    long long* row_a = reinterpret_cast<long long*>(fm_smem);      // [TM] A offset of row i
+    long long* pos_m = row_a + g.TM;                                // [TM] C offset of row i
+    long long* col_b = pos_m + g.TM;                                // [TN] B offset of col j
+    long long* pos_n = col_b + g.TN;                                // [TN] C offset of col j
+    long long* k_a = pos_n + g.TN;                                  // [KP]
+    long long* k_b = k_a + KP;                                      // [KP]
+    C* Bs = reinterpret_cast<C*>(k_b + KP);                         // [KP][TN]
+
+    const int tid = threadIdx.x;
+    const int f_im = g.n_outer, f_in = f_im + g.n_im, f_k = f_in + g.n_in;
+
+    for (int i = tid; i < g.TM; i += FM_THREADS) {
+        long long oa = 0, oc = 0; int rem = i;
+        for (int m = 0; m < g.n_im; ++m) {
+            const int d = g.dim[f_im + m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            oa += (long long)x * g.sa[f_im + m];
+            oc += (long long)x * g.sc[f_im + m];
+        }
+        row_a[i] = oa; pos_m[i] = oc;
+    }
+    for (int j = tid; j < g.TN; j += FM_THREADS) {
+        long long ob = 0, oc = 0; int rem = j;
+        for (int m = 0; m < g.n_in; ++m) {
+            const int d = g.dim[f_in + m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            ob += (long long)x * g.sb[f_in + m];
+            oc += (long long)x * g.sc[f_in + m];
+        }
+        col_b[j] = ob; pos_n[j] = oc;
+    }
+    if (tid < KP) {
+        long long xa = 0, xb = 0; int rem = tid < g.K ? tid : 0;
+        for (int m = 0; m < g.n_k; ++m) {
+            const int d = g.dim[f_k + m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            xa += (long long)x * g.sa[f_k + m];
+            xb += (long long)x * g.sb[f_k + m];
+        }
+        k_a[tid] = xa; k_b[tid] = xb;
+    }
+
+    // contiguous range of outer tiles + odometer (outer mode 0 = fastest in C)
+    const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per;
+    const long long t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    if (t0 >= t1) return;
+    int cnt[B2_MAX_MODES];
+    long long oa = 0, ob = 0, oc = 0;
+    {
+        long long rem = t0;
+        for (int m = 0; m < g.n_outer; ++m) {
+            const long long d = g.dim[m];
+            const long long q = rem / d;
+            const int x = (int)(rem - q * d);
+            rem = q;
+            cnt[m] = x;
+            oa += x * g.sa[m]; ob += x * g.sb[m]; oc += x * g.sc[m];
+        }
+    }
+    __syncthreads();
+
+    const int n_jg = (g.TN + FM_U - 1) / FM_U;
+    const int n_items = g.TM * n_jg;
+    const bool unit_alpha = (alpha_re == (T)1 && alpha_im == (T)0);
+    const C zero = make_c<T>((T)0, (T)0);
+
+    for (long long t = t0; t < t1; ++t) {
+        if (t != t0) {
+            for (int m = 0; m < g.n_outer; ++m) {
+                oa += g.sa[m]; ob += g.sb[m]; oc += g.sc[m];
+                if (++cnt[m] < g.dim[m]) break;
+                oa -= (long long)g.dim[m] * g.sa[m];
+                ob -= (long long)g.dim[m] * g.sb[m];
+                oc -= (long long)g.dim[m] * g.sc[m];
+                cnt[m] = 0;
+            }
+        }
+        if (t == t0 || !g.b_static) {
+            if (t != t0) __syncthreads();              // everyone done with the old Bs
+            for (int e = tid; e < KP * g.TN; e += FM_THREADS) {
+                const int k = e / g.TN, j = e - k * g.TN;
+                Bs[e] = (k < g.K) ? B[ob + col_b[j] + k_b[k]] : zero;
+            }
+            __syncthreads();
+        }
+        const C* __restrict__ At = A + oa;
+        C* __restrict__ Ct = Cout + oc;
+        for (int w = tid; w < n_items; w += FM_THREADS) {
+            const int jg = w / g.TM, i = w - jg * g.TM;       // lanes = consecutive rows
+            const C* ap = At + row_a[i];
+            C a[KP];
+            #pragma unroll
+            for (int k = 0; k < KP; ++k) a[k] = (k < g.K) ? ap[k_a[k]] : zero;
+            C* cp = Ct + pos_m[i];
+            const int j0 = jg * FM_U;
+            const int j1 = j0 + FM_U < g.TN ? j0 + FM_U : g.TN;
+            #pragma unroll 4
+            for (int j = j0; j < j1; ++j) {
+                C acc = zero;
+                #pragma unroll
+                for (int k = 0; k < KP; ++k) cfma(acc, a[k], Bs[k * g.TN + j]);
+                C res;
+                if (unit_alpha) res = acc;
+                else {
+                    res.x = alpha_re * acc.x - alpha_im * acc.y;
+                    res.y = alpha_re * acc.y + alpha_im * acc.x;
+                }
+                C* dst = cp + pos_n[j];
+                if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
+                *dst = res;
+            }
+        }
+    }
+}
+
+// Classify the modes of the direct-kernel descriptor and build the tile.
+// Returns false when this kernel does not apply (caller falls back).
+static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool& swap_ab) {
+    const int no = md.n_out;
+    long long K = 1;
+    for (int m = 0; m < md.n_red; ++m) K *= md.dim[no + m];
+    if (no == 0 || K > FM_KMAX) return false;
+    // C-stride order of the output modes (they arrive slow -> fast, contiguous or not)
+    int order[B2_MAX_MODES];
+    int cnt = 0;
+    for (int i = 0; i < no; ++i) if (md.dim[i] > 1) order[cnt++] = i;
+    for (int i = 1; i < cnt; ++i) {
+        int x = order[i], j = i - 1;
+        while (j >= 0 && md.sc[order[j]] > md.sc[x]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = x;
+    }
+    if (cnt == 0 || md.sc[order[0]] != 1) return false;
+    const int f = order[0];
+    const bool f_in_a = md.sa[f] != 0, f_in_b = md.sb[f] != 0;
+    if (f_in_a && f_in_b) return false;                 // fastest mode is a batch mode
+    swap_ab = !f_in_a;                                  // rows must own the fastest C mode
+    auto SA = [&](int i) { return swap_ab ? md.sb[i] : md.sa[i]; };
+    auto SB = [&](int i) { return swap_ab ? md.sa[i] : md.sb[i]; };
+    auto is_m = [&](int i) { return SA(i) != 0 && SB(i) == 0; };
+    auto is_n = [&](int i) { return SA(i) == 0 && SB(i) != 0; };
+    bool inner[B2_MAX_MODES] = {false};
+    long long T = 1;
+    int TM = 1, TN = 1;
+    auto fits = [&](int i) {
+        const long long dd = md.dim[i];
+        if (T * dd > FM_TMAX) return false;
+        if (is_m(i)) return (long long)TM * dd <= FM_MAXM;
+        if (is_n(i)) return (long long)TN * dd <= FM_MAXN;
+        return false;
+    };
+    auto take = [&](int i) {
+        if (is_m(i)) TM *= md.dim[i]; else TN *= md.dim[i];
+        T *= md.dim[i];
+        inner[i] = true;
+    };
+    // rows first: M modes in C order until a warp's lanes are all rows
+    bool m_open = true, n_open = true;
+    while (m_open && TM < 64) {
+        int pick = -1;
+        for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (!inner[i] && is_m(i)) { pick = i; break; } }
+        if (pick < 0 || !fits(pick)) { m_open = false; break; }
+        take(pick);
+    }
+    // then columns (operand reuse of the A rows held in registers), then more rows
+    while (m_open || n_open) {
+        const bool want_n = n_open && (TN < FM_U || !m_open || TN < TM);
+        int pick = -1;
+        for (int q = 0; q < cnt; ++q) {
+            const int i = order[q];
+            if (inner[i]) continue;
+            if (want_n ? is_n(i) : is_m(i)) { pick = i; break; }
+        }
+        if (pick < 0 || !fits(pick)) { if (want_n) n_open = false; else m_open = false; continue; }
+        take(pick);
+    }
+    if (TM < 16) return false;
+    int p = 0;
+    auto put = [&](int i) {
+        d.dim[p] = md.dim[i]; d.sa[p] = SA(i); d.sb[p] = SB(i); d.sc[p] = md.sc[i]; ++p;
+    };
+    n_tiles = 1;
+    d.n_outer = 0;
+    d.b_static = 1;
+    for (int q = 0; q < cnt; ++q) {
+        const int i = order[q];
+        if (!inner[i]) { put(i); ++d.n_outer; n_tiles *= md.dim[i]; if (SB(i) != 0) d.b_static = 0; }
+    }
+    d.n_im = 0;
+    for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (inner[i] && is_m(i)) { put(i); ++d.n_im; } }
+    d.n_in = 0;
+    for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (inner[i] && is_n(i)) { put(i); ++d.n_in; } }
+    d.n_k = 0;
+    for (int i = no; i < no + md.n_red; ++i) if (md.dim[i] > 1) { put(i); ++d.n_k; }
+    // (any fixed enumeration of the reduction modes works: A and B offsets are
+    // decoded from the same flat k)
+    d.TM = TM; d.TN = TN; d.K = (int)K;
+    return true;
+}
+
+template <typename T>
+int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void* b, void* c,
+                 double ar, double ai, int accumulate, cudaStream_t s) {
+    using C = typename cplx<T>::type;
+    int sms = num_sms();
+    if (sms <= 0) return 1;
+    int KP = 1;
+    while (KP < d.K) KP <<= 1;
+    const size_t smem = (size_t)(2 * d.TM + 2 * d.TN + 2 * KP) * 8 + (size_t)KP * d.TN * sizeof(C);
+    long long blocks = n_tiles;
+    const long long cap = (long long)sms * 4;
+    if (blocks > cap) blocks = cap;
+    const C* A = (const C*)a; const C* B = (const C*)b; C* Cc = (C*)c;
+#define B2_FMA_LAUNCH(KPV)                                                                   \
+    contract_fma_kernel<T, KPV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(                  \
+        d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate)
+    switch (KP) {
+    case 1: B2_FMA_LAUNCH(1); break;
+    case 2: B2_FMA_LAUNCH(2); break;
+    case 4: B2_FMA_LAUNCH(4); break;
+    case 8: B2_FMA_LAUNCH(8); break;
+    default: B2_FMA_LAUNCH(16); break;
+    }
+#undef B2_FMA_LAUNCH
+    return check_launch("b2_contract_direct(fma)");
+}
+
+int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double ar, double ai,
+               int accumulate, int dtype, cudaStream_t s, bool& handled) {
+    handled = false;
+    fm_desc d;
+    long long n_tiles = 0;
+    bool swap_ab = false;
+    if (!make_fma(md, d, n_tiles, swap_ab)) return 0;
+    const void* pa = swap_ab ? b : a;
+    const void* pb = swap_ab ? a : b;
+    handled = true;
+    if (dtype == B2_C128)
+        return launch_fma_t<double>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);
+    return launch_fma_t<float>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);
+}
+
+}  // namespace b2

@@ -192,6 +192,9 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     }
 }
 
+int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, double ar,
+                 double ai, int accumulate, cudaStream_t s, bool& handled);
+
 }  // namespace b2
 
 extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, const void* b_dev,
@@ -210,6 +213,12 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         return 1;
     }
     if (num_sms() <= 0) return 1;
+    {   // primary path: tile from the output side (coalesced stores, one gather per tile)
+        bool handled = false;
+        int st = launch_ctile(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
+                              (cudaStream_t)stream, handled);
+        if (st != 0 || handled) return st;
+    }
     long long Bt = 1, M = 1, N = 1, K = 1;
     int p = 0;
     for (int i = 0; i < g.n_batch; ++i) Bt *= g.dim[p++];
