@@ -97,6 +97,9 @@ typedef struct {
 /* version / errors */
 int b2_abi_version(void);
 const char* b2_last_error(void);
+/* which kernel variant the last contraction call of this thread launched
+ * ("fma", "tiled", "generic", "ctile", "gemm"): profiling aid */
+const char* b2_last_kernel(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int b2_device_sms(void);
 

@@ -7,6 +7,9 @@ namespace b2 {
 
 static thread_local char g_err[512] = "";
 static int g_sms = 0;
+static thread_local const char* g_last_kernel = "";
+
+void set_last_kernel(const char* name) { g_last_kernel = name; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(256) dmma16816_peak_kernel(int iters, double* 
 extern "C" int b2_abi_version(void) { return B2_ABI_VERSION; }
 extern "C" const char* b2_last_error(void) { return b2::g_err; }
 extern "C" int b2_device_sms(void) { return b2::num_sms(); }
+extern "C" const char* b2_last_kernel(void) { return b2::g_last_kernel; }
 
 extern "C" int b2_fp64_peak_kernel(int32_t kind, int32_t iters, double* sink_dev,
                                    double* flops_out, void* stream) {

@@ -36,5 +36,6 @@ __device__ __forceinline__ C cmul(const C a, const C b) {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
+void set_last_kernel(const char* name);
 
 }  // namespace b2

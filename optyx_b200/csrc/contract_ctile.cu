@@ -299,7 +299,32 @@ contract_ctile_c128_kernel(const __grid_constant__ ct_desc g, long long n_tiles,
 // fastest C modes: first whatever is fastest until the contiguous run is >= 16
 // elements (256 B), then M and N modes alternately so the tile stays as square
 // as the shapes allow (operand reuse), up to 4096 elements and 256 per side.
-static bool make_ctile(const b2_gemm_modes& g, ct_desc& d, long long& n_tiles, size_t& smem) {
+// The planner merges stride-compatible modes; a tile needs finer grain, so the
+// free modes are split back into factors of at most 16 first.
+static void refine_gemm_modes(const b2_gemm_modes& in, b2_gemm_modes& out) {
+    const int counts[4] = {in.n_batch, in.n_m, in.n_n, in.n_k};
+    int newc[4] = {0, 0, 0, 0};
+    int p = 0, src = 0;
+    const int total = in.n_batch + in.n_m + in.n_n + in.n_k;
+    for (int grp = 0; grp < 4; ++grp) {
+        for (int i = 0; i < counts[grp]; ++i, ++src) {
+            long long dd = in.dim[src], sa = in.sa[src], sb = in.sb[src], sc = in.sc[src];
+            while (grp < 3 && dd > 16 && p + (total - src) < B2_MAX_MODES - 1) {
+                int f = 1;
+                for (int c = 16; c >= 2; --c) if (dd % c == 0) { f = c; break; }
+                if (f == 1) break;
+                out.dim[p] = f; out.sa[p] = sa; out.sb[p] = sb; out.sc[p] = sc; ++p; ++newc[grp];
+                sa *= f; sb *= f; sc *= f; dd /= f;
+            }
+            out.dim[p] = (int)dd; out.sa[p] = sa; out.sb[p] = sb; out.sc[p] = sc; ++p; ++newc[grp];
+        }
+    }
+    out.n_batch = newc[0]; out.n_m = newc[1]; out.n_n = newc[2]; out.n_k = newc[3];
+}
+
+static bool make_ctile(const b2_gemm_modes& g_in, ct_desc& d, long long& n_tiles, size_t& smem) {
+    b2_gemm_modes g;
+    refine_gemm_modes(g_in, g);
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const int n_free = g.n_batch + g.n_m + g.n_n;
     int order[B2_MAX_MODES];
@@ -418,6 +443,7 @@ int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, 
     contract_ctile_c128_kernel<<<(unsigned)blocks, CT_THREADS, smem, s>>>(
         d, n_tiles, (const double2*)a, (const double2*)b, (double2*)c, ar, ai, accumulate);
     handled = true;
+    set_last_kernel("ctile");
     return check_launch("b2_contract_gemm(ctile)");
 }
 

@@ -269,9 +269,11 @@ int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, dou
         contract_direct_tiled_kernel<T><<<(unsigned)blocks, kTiledThreads, smem, s>>>(
             tiled, n_outer, tile, (int)n_red_elems, n_tiles, (const C*)a, (const C*)b, (C*)c,
             (T)ar, (T)ai, accumulate);
+        set_last_kernel("tiled");
         return check_launch("b2_contract_direct(tiled)");
     }
 
+    set_last_kernel("generic");
     const int threads = 256;
     long long blocks = (n_out_elems + threads - 1) / threads;
     long long cap = (long long)sms * 16;

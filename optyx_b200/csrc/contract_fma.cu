@@ -1,28 +1,30 @@
 // Piece (2a), primary kernel for bandwidth-bound pairs with a short reduction
-// (K <= 16): outer products, "apply a small tensor to a huge one", thin pairs.
+// (K <= 16): outer products, "apply a small tensor to a huge one", thin pairs,
+// element-wise products over shared (hyper) indices.
 //
 //   C[b, m, n] (+)= alpha * sum_k A[b, m, k] * B[b, k, n]
 //
 // Tiled from the output side like contract_ctile.cu: the CTA tile is TM x TN
 // elements made of the FASTEST C modes, oriented so that the fastest C mode is
-// a row (M) mode.  A work item is (row i, group of U columns): the thread pulls
-// the K values A[i, :] into registers once (16 B loads, lanes = consecutive rows
-// -> consecutive C addresses), reads B[:, j] as shared-memory broadcasts (the
-// TN x K block of B is staged once per tile, or once per CTA when it does not
-// change), does 4*K FMAs per output and stores each output straight from
-// registers: lanes of a warp write consecutive rows = consecutive addresses.
-// No accumulator staging, one barrier per tile, every load independent of every
-// other -> the kernel is limited by HBM, not by latency.
+// a ROW mode (a mode of A: a free M mode or a batch mode shared with B).  A work
+// item is (row i, group of U columns): the thread pulls the K values A[i, :]
+// into registers once (16 B loads, lanes = consecutive rows -> consecutive C
+// addresses), reads B[:, j] from shared memory (the K x TB x TN block of B is
+// staged once per tile, or once per CTA when it does not change; without batch
+// modes in the tile the reads are pure broadcasts), does 4*K FMAs per output
+// and stores each output straight from registers: lanes of a warp write
+// consecutive rows = consecutive addresses.  No accumulator staging, at most
+// one barrier pair per tile, every load independent of every other.
 #include "b2_common.cuh"
 
 namespace b2 {
 
-constexpr int FM_THREADS = 256, FM_TMAX = 16384, FM_MAXM = 512, FM_MAXN = 64, FM_U = 16;
-constexpr int FM_KMAX = 16;
+constexpr int FM_THREADS = 256, FM_TMAX = 16384, FM_MAXM = 1024, FM_MAXN = 64, FM_U = 16;
+constexpr int FM_KMAX = 16, FM_MAXTB = 64, FM_BTILE_BYTES = 32 * 1024;
 
 struct fm_desc {
-    int n_outer, n_im, n_in, n_k;       // mode counts, stored in this order
-    int TM, TN, K;
+    int n_outer, n_ir, n_in, n_k;       // mode counts, stored in this order
+    int TM, TN, TB, K;                  // rows, columns, batch combos inside the rows, reduction
     int b_static;                       // B's tile does not depend on the outer modes
     int dim[B2_MAX_MODES];
     long long sa[B2_MAX_MODES], sb[B2_MAX_MODES], sc[B2_MAX_MODES];
@@ -41,23 +43,37 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
     long long* pos_m = row_a + g.TM;                                // [TM] C offset of row i
     long long* col_b = pos_m + g.TM;                                // [TN] B offset of col j
     long long* pos_n = col_b + g.TN;                                // [TN] C offset of col j
-    long long* k_a = pos_n + g.TN;                                  // [KP]
+    long long* bt_off = pos_n + g.TN;                               // [TB] B offset of batch combo
+    long long* k_a = bt_off + ((g.TB + 1) & ~1);                    // [KP] (keeps Bs 16 B aligned)
     long long* k_b = k_a + KP;                                      // [KP]
-    C* Bs = reinterpret_cast<C*>(k_b + KP);                         // [KP][TN]
+    C* Bs = reinterpret_cast<C*>(k_b + KP);                         // [KP][TB][TN]
+    int* row_bs = reinterpret_cast<int*>(Bs + (size_t)KP * g.TB * g.TN);   // [TM] bt(i) * TN
 
     const int tid = threadIdx.x;
-    const int f_im = g.n_outer, f_in = f_im + g.n_im, f_k = f_in + g.n_in;
+    const int f_ir = g.n_outer, f_in = f_ir + g.n_ir, f_k = f_in + g.n_in;
 
     for (int i = tid; i < g.TM; i += FM_THREADS) {
-        long long oa = 0, oc = 0; int rem = i;
-        for (int m = 0; m < g.n_im; ++m) {
-            const int d = g.dim[f_im + m];
+        long long oa = 0, oc = 0; int rem = i, bt = 0, btm = 1;
+        for (int m = 0; m < g.n_ir; ++m) {
+            const int d = g.dim[f_ir + m];
             const int q = rem / d, x = rem - q * d;
             rem = q;
-            oa += (long long)x * g.sa[f_im + m];
-            oc += (long long)x * g.sc[f_im + m];
+            oa += (long long)x * g.sa[f_ir + m];
+            oc += (long long)x * g.sc[f_ir + m];
+            if (g.sb[f_ir + m] != 0) { bt += x * btm; btm *= d; }
         }
-        row_a[i] = oa; pos_m[i] = oc;
+        row_a[i] = oa; pos_m[i] = oc; row_bs[i] = bt * g.TN;
+    }
+    for (int b = tid; b < g.TB; b += FM_THREADS) {
+        long long ob = 0; int rem = b;
+        for (int m = 0; m < g.n_ir; ++m) {
+            if (g.sb[f_ir + m] == 0) continue;
+            const int d = g.dim[f_ir + m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            ob += (long long)x * g.sb[f_ir + m];
+        }
+        bt_off[b] = ob;
     }
     for (int j = tid; j < g.TN; j += FM_THREADS) {
         long long ob = 0, oc = 0; int rem = j;
@@ -104,6 +120,7 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
 
     const int n_jg = (g.TN + FM_U - 1) / FM_U;
     const int n_items = g.TM * n_jg;
+    const int bplane = g.TB * g.TN;
     const bool unit_alpha = (alpha_re == (T)1 && alpha_im == (T)0);
     const C zero = make_c<T>((T)0, (T)0);
 
@@ -120,9 +137,10 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
         }
         if (t == t0 || !g.b_static) {
             if (t != t0) __syncthreads();              // everyone done with the old Bs
-            for (int e = tid; e < KP * g.TN; e += FM_THREADS) {
-                const int k = e / g.TN, j = e - k * g.TN;
-                Bs[e] = (k < g.K) ? B[ob + col_b[j] + k_b[k]] : zero;
+            for (int e = tid; e < KP * bplane; e += FM_THREADS) {
+                const int k = e / bplane, r = e - k * bplane;
+                const int bt = r / g.TN, j = r - bt * g.TN;
+                Bs[e] = (k < g.K) ? B[ob + bt_off[bt] + col_b[j] + k_b[k]] : zero;
             }
             __syncthreads();
         }
@@ -135,13 +153,14 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             #pragma unroll
             for (int k = 0; k < KP; ++k) a[k] = (k < g.K) ? ap[k_a[k]] : zero;
             C* cp = Ct + pos_m[i];
+            const C* bp = Bs + row_bs[i];
             const int j0 = jg * FM_U;
             const int j1 = j0 + FM_U < g.TN ? j0 + FM_U : g.TN;
             #pragma unroll 4
             for (int j = j0; j < j1; ++j) {
                 C acc = zero;
                 #pragma unroll
-                for (int k = 0; k < KP; ++k) cfma(acc, a[k], Bs[k * g.TN + j]);
+                for (int k = 0; k < KP; ++k) cfma(acc, a[k], bp[k * bplane + j]);
                 C res;
                 if (unit_alpha) res = acc;
                 else {
@@ -158,60 +177,106 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
 
 // Classify the modes of the direct-kernel descriptor and build the tile.
 // Returns false when this kernel does not apply (caller falls back).
-static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool& swap_ab) {
+// The planner merges stride-compatible modes (a contiguous 2^21 run arrives as
+// ONE mode); a tile needs finer grain, so output modes are first split back into
+// factors of at most 4 (the slow part keeps stride * factor).
+static void refine_modes(const b2_modes& in, b2_modes& out) {
+    int p = 0;
+    const int budget = B2_MAX_MODES - in.n_red;
+    for (int i = 0; i < in.n_out; ++i) {
+        long long d = in.dim[i];
+        long long sa = in.sa[i], sb = in.sb[i], sc = in.sc[i];
+        // pieces are emitted slow -> fast, as the surrounding list is
+        long long piece[32], psa[32], psb[32], psc[32];
+        int np = 0;
+        while (d > 4 && np < 30 && p + np + (in.n_out - i) < budget - 1) {
+            int f = 1;
+            for (int c = 4; c >= 2; --c) if (d % c == 0) { f = c; break; }
+            if (f == 1) break;                           // odd prime extent (3, 5, 7): keep whole
+            piece[np] = f; psa[np] = sa; psb[np] = sb; psc[np] = sc; ++np;   // fast part
+            sa *= f; sb *= f; sc *= f; d /= f;
+        }
+        piece[np] = d; psa[np] = sa; psb[np] = sb; psc[np] = sc; ++np;       // slowest part
+        for (int q = np - 1; q >= 0; --q) {
+            out.dim[p] = (int)piece[q]; out.sa[p] = psa[q]; out.sb[p] = psb[q]; out.sc[p] = psc[q];
+            ++p;
+        }
+    }
+    out.n_out = p;
+    out.n_red = in.n_red;
+    for (int m = 0; m < in.n_red; ++m) {
+        out.dim[p + m] = in.dim[in.n_out + m]; out.sa[p + m] = in.sa[in.n_out + m];
+        out.sb[p + m] = in.sb[in.n_out + m]; out.sc[p + m] = in.sc[in.n_out + m];
+    }
+}
+
+static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool swap_ab,
+                     size_t elem_bytes) {
     const int no = md.n_out;
     long long K = 1;
     for (int m = 0; m < md.n_red; ++m) K *= md.dim[no + m];
     if (no == 0 || K > FM_KMAX) return false;
-    // C-stride order of the output modes (they arrive slow -> fast, contiguous or not)
+    int KP = 1;
+    while (KP < K) KP <<= 1;
     int order[B2_MAX_MODES];
     int cnt = 0;
     for (int i = 0; i < no; ++i) if (md.dim[i] > 1) order[cnt++] = i;
-    for (int i = 1; i < cnt; ++i) {
+    for (int i = 1; i < cnt; ++i) {                     // sort by C stride ascending
         int x = order[i], j = i - 1;
         while (j >= 0 && md.sc[order[j]] > md.sc[x]) { order[j + 1] = order[j]; --j; }
         order[j + 1] = x;
     }
     if (cnt == 0 || md.sc[order[0]] != 1) return false;
-    const int f = order[0];
-    const bool f_in_a = md.sa[f] != 0, f_in_b = md.sb[f] != 0;
-    if (f_in_a && f_in_b) return false;                 // fastest mode is a batch mode
-    swap_ab = !f_in_a;                                  // rows must own the fastest C mode
     auto SA = [&](int i) { return swap_ab ? md.sb[i] : md.sa[i]; };
     auto SB = [&](int i) { return swap_ab ? md.sa[i] : md.sb[i]; };
-    auto is_m = [&](int i) { return SA(i) != 0 && SB(i) == 0; };
+    auto is_row = [&](int i) { return SA(i) != 0; };                 // M or batch mode
+    auto is_bat = [&](int i) { return SA(i) != 0 && SB(i) != 0; };
     auto is_n = [&](int i) { return SA(i) == 0 && SB(i) != 0; };
     bool inner[B2_MAX_MODES] = {false};
     long long T = 1;
-    int TM = 1, TN = 1;
+    int TM = 1, TN = 1, TB = 1;
     auto fits = [&](int i) {
         const long long dd = md.dim[i];
         if (T * dd > FM_TMAX) return false;
-        if (is_m(i)) return (long long)TM * dd <= FM_MAXM;
-        if (is_n(i)) return (long long)TN * dd <= FM_MAXN;
-        return false;
+        long long tb = TB, tn = TN;
+        if (is_row(i)) {
+            if ((long long)TM * dd > FM_MAXM) return false;
+            if (is_bat(i)) tb *= dd;
+        } else if (is_n(i)) {
+            tn *= dd;
+            if (tn > FM_MAXN) return false;
+        } else return false;
+        if (tb > FM_MAXTB) return false;
+        return (long long)KP * tb * tn * (long long)elem_bytes <= FM_BTILE_BYTES;
     };
     auto take = [&](int i) {
-        if (is_m(i)) TM *= md.dim[i]; else TN *= md.dim[i];
+        if (is_row(i)) { TM *= md.dim[i]; if (is_bat(i)) TB *= md.dim[i]; } else TN *= md.dim[i];
         T *= md.dim[i];
         inner[i] = true;
     };
-    // rows first: M modes in C order until a warp's lanes are all rows
+    // rows first: row modes in C order until a warp's lanes are all rows
     bool m_open = true, n_open = true;
     while (m_open && TM < 64) {
         int pick = -1;
-        for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (!inner[i] && is_m(i)) { pick = i; break; } }
+        for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (!inner[i] && is_row(i)) { pick = i; break; } }
         if (pick < 0 || !fits(pick)) { m_open = false; break; }
         take(pick);
     }
-    // then columns (operand reuse of the A rows held in registers), then more rows
+    // shared (batch) modes next, wherever they sit in C: with all of them inside
+    // the tile the B block is the same for every tile (loaded once per CTA)
+    for (int q = 0; q < cnt; ++q) {
+        const int i = order[q];
+        if (!inner[i] && is_bat(i) && fits(i)) take(i);
+    }
+    if (TM >= FM_MAXM) m_open = false;
+    // then columns (reuse of the A rows held in registers), then more rows
     while (m_open || n_open) {
         const bool want_n = n_open && (TN < FM_U || !m_open || TN < TM);
         int pick = -1;
         for (int q = 0; q < cnt; ++q) {
             const int i = order[q];
             if (inner[i]) continue;
-            if (want_n ? is_n(i) : is_m(i)) { pick = i; break; }
+            if (want_n ? is_n(i) : is_row(i)) { pick = i; break; }
         }
         if (pick < 0 || !fits(pick)) { if (want_n) n_open = false; else m_open = false; continue; }
         take(pick);
@@ -228,15 +293,15 @@ static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool& s
         const int i = order[q];
         if (!inner[i]) { put(i); ++d.n_outer; n_tiles *= md.dim[i]; if (SB(i) != 0) d.b_static = 0; }
     }
-    d.n_im = 0;
-    for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (inner[i] && is_m(i)) { put(i); ++d.n_im; } }
+    d.n_ir = 0;
+    for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (inner[i] && is_row(i)) { put(i); ++d.n_ir; } }
     d.n_in = 0;
     for (int q = 0; q < cnt; ++q) { const int i = order[q]; if (inner[i] && is_n(i)) { put(i); ++d.n_in; } }
     d.n_k = 0;
     for (int i = no; i < no + md.n_red; ++i) if (md.dim[i] > 1) { put(i); ++d.n_k; }
     // (any fixed enumeration of the reduction modes works: A and B offsets are
     // decoded from the same flat k)
-    d.TM = TM; d.TN = TN; d.K = (int)K;
+    d.TM = TM; d.TN = TN; d.TB = TB; d.K = (int)K;
     return true;
 }
 
@@ -248,7 +313,8 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     if (sms <= 0) return 1;
     int KP = 1;
     while (KP < d.K) KP <<= 1;
-    const size_t smem = (size_t)(2 * d.TM + 2 * d.TN + 2 * KP) * 8 + (size_t)KP * d.TN * sizeof(C);
+    const size_t smem = (size_t)(2 * d.TM + 2 * d.TN + ((d.TB + 1) & ~1) + 2 * KP) * 8 +
+                        (size_t)KP * d.TB * d.TN * sizeof(C) + (size_t)d.TM * 4 + 16;
     long long blocks = n_tiles;
     const long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;
@@ -270,13 +336,34 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
 int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double ar, double ai,
                int accumulate, int dtype, cudaStream_t s, bool& handled) {
     handled = false;
-    fm_desc d;
-    long long n_tiles = 0;
-    bool swap_ab = false;
-    if (!make_fma(md, d, n_tiles, swap_ab)) return 0;
+    if (md.n_out == 0) return 0;
+    b2_modes fine;
+    refine_modes(md, fine);
+    // orientation: rows should own the fastest C mode; if that leaves too few
+    // rows (the fastest mode belongs to a tiny operand), try the other way round
+    int fastest = -1;
+    for (int i = 0; i < fine.n_out; ++i)
+        if (fine.dim[i] > 1 && fine.sc[i] == 1) fastest = i;
+    if (fastest < 0) return 0;
+    const size_t eb = dtype == B2_C128 ? 16 : 8;
+    fm_desc d, d2;
+    long long n_tiles = 0, n_tiles2 = 0;
+    bool swap_ab = fine.sa[fastest] == 0;
+    bool ok = make_fma(fine, d, n_tiles, swap_ab, eb);
+    if (!ok || d.TM < 64) {
+        const bool ok2 = make_fma(fine, d2, n_tiles2, !swap_ab, eb);
+        if (ok2 && (!ok || d2.TM > d.TM)) { d = d2; n_tiles = n_tiles2; swap_ab = !swap_ab; ok = true; }
+    }
+    if (!ok) return 0;
     const void* pa = swap_ab ? b : a;
     const void* pb = swap_ab ? a : b;
     handled = true;
+    {
+        static thread_local char info[96];
+        snprintf(info, sizeof(info), "fma TM=%d TN=%d TB=%d K=%d tiles=%lld bstatic=%d swap=%d",
+                 d.TM, d.TN, d.TB, d.K, n_tiles, d.b_static, (int)swap_ab);
+        set_last_kernel(info);
+    }
     if (dtype == B2_C128)
         return launch_fma_t<double>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);
     return launch_fma_t<float>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);

@@ -213,7 +213,13 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         return 1;
     }
     if (num_sms() <= 0) return 1;
-    {   // primary path: tile from the output side (coalesced stores, one gather per tile)
+    long long k_total = 1, n_total = 1;
+    for (int i = 0; i < g.n_k; ++i) k_total *= g.dim[g.n_batch + g.n_m + g.n_n + i];
+    for (int i = 0; i < g.n_n; ++i) n_total *= g.dim[g.n_batch + g.n_m + i];
+    if (k_total <= 64 || n_total < 64) {
+        // short reductions / skinny pairs: tile from the output side (coalesced
+        // staged stores, one gather per tile).  Long-K square-ish pairs keep the
+        // classic 64x64 tiling below (4x4 register blocking per warp).
         bool handled = false;
         int st = launch_ctile(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
                               (cudaStream_t)stream, handled);
@@ -249,6 +255,7 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
         attr_set = true;
     }
+    set_last_kernel("gemm");
     dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt);
     contract_gemm_c128_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
         g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,

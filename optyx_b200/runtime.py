@@ -18,7 +18,7 @@ MAX_MODES = 64
 MAX_RED_DIRECT = 16
 
 EXPORTS = [
-    "b2_abi_version", "b2_last_error", "b2_device_sms", "b2_build_leaves",
+    "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
     "b2_contract_direct", "b2_contract_gemm", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_fp64_peak_kernel",
 ]
@@ -86,6 +86,7 @@ def load():
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.b2_abi_version.restype = C.c_int
     lib.b2_last_error.restype = C.c_char_p
+    lib.b2_last_kernel.restype = C.c_char_p
     lib.b2_device_sms.restype = C.c_int
     lib.b2_build_leaves.argtypes = [vp, i32, i64, vp, i64, vp, i64, i32, i32, vp]
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
@@ -97,7 +98,7 @@ def load():
     lib.b2_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("b2_abi_version", "b2_last_error", "b2_device_sms"):
+        if name not in ("b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms"):
             fn.restype = C.c_int
     if lib.b2_abi_version() != 1:
         raise B2Error("liboptyx_b200.so ABI version mismatch")

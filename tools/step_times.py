@@ -1,0 +1,55 @@
+"""Per-step CUDA-event timing of one slice of the cfg4 sliced plan: where does the
+time go, and how far is each step from its roofline?"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+from optyx_b200 import executor  # noqa: E402
+
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 41
+tgt = int(sys.argv[2]) if len(sys.argv) > 2 else 26
+net = cases.compile_channel(cases.random_clifford_t(30, depth, seed=0))
+plan = executor.get_plan(net, target_size=float(2 ** tgt), trials=16)
+sess = executor.Session(plan)
+sess.set_leaves([net])
+sess.build_leaves()
+sess.contract(net.scalar, slice_range=(0, 1))
+torch.cuda.synchronize()
+stream = torch.cuda.current_stream().cuda_stream
+vals = [0] * len(plan.sliced)
+rows = []
+for st in plan.steps:
+    if not st.per_slice:
+        continue
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sess._launch(st, vals, 1.0 + 0j, 0, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    ideal = max(st.bytes / 6.556e12, 8 * st.macs / 37e12)
+    rows.append((t, ideal, st, sess.lib.b2_last_kernel().decode()))
+tot = sum(r[0] for r in rows)
+print(f"nslices {plan.nslices} per-slice steps {len(rows)} measured {tot*1e3:.1f} ms "
+      f"ideal {sum(r[1] for r in rows)*1e3:.1f} ms")
+by = {}
+for t, ideal, st, kn in rows:
+    k = kn.split()[0]
+    by.setdefault(k, [0, 0.0, 0.0])
+    by[k][0] += 1; by[k][1] += t; by[k][2] += ideal
+for k, v in by.items():
+    print(f"  {k}: n={v[0]} measured {v[1]*1e3:.1f} ms ideal {v[2]*1e3:.1f} ms")
+print("top 30 by measured time:")
+for t, ideal, st, kn in sorted(rows, key=lambda r: -r[0])[:30]:
+    d = st.desc
+    nm = (d.n_out, d.n_red) if st.kernel == "direct" else (d.n_batch, d.n_m, d.n_n, d.n_k)
+    print(f"  {kn.split()[0]:7s} mnk={st.mnk} t={t*1e3:7.3f} ms ideal={ideal*1e3:6.3f} eff={ideal/t:5.2f} "
+          f"GB/s={st.bytes/t/1e9:7.0f} modes={nm} {' '.join(kn.split()[1:])}")
+small = [r for r in rows if r[1] < 5e-6]
+print(f"steps with ideal < 5us: {len(small)}, measured {sum(r[0] for r in small)*1e3:.2f} ms")
