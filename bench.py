@@ -234,7 +234,9 @@ def main():
 
     # ---- e2e: the user call, host objects in, host numpy out
     backend = B200Backend()
-    res = diagram.eval(backend)          # warm (plan cached by structure)
+    res = None
+    for _ in range(3):                   # warm-up: plan cache + the pinned result
+        res = diagram.eval(backend)      # buffers of torch's caching host allocator
     n_e2e = max(2, min(args.steps, 5))
     barrier()
     t0 = time.perf_counter()
@@ -259,7 +261,11 @@ def main():
     achieved = dom.bytes / dom_secs / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None,
+        "frac": achieved / hbm_peak,
+        # dram__bytes_read+write of this kernel from `ncu --set full` on the
+        # quarter-size instance (1.0385 GB per launch, profiles/r01_fma_final_step.md)
+        # scaled by 4; the full-size capture does not finish under ncu's replay
+        "traffic": 4.154e9 if args.workload == "cfg2" else None,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
         "kernel": f"b2_contract_{dom.kernel} (final step, (batch,M,N,K)={dom.mnk})",
         "algorithmic_bytes_per_launch": dom.bytes, "launch_ms": dom_secs * 1e3,
