@@ -166,6 +166,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # rank 0 must print exactly ONE line: keep NCCL's version banner off stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = rt.load()
 

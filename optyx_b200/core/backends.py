@@ -258,8 +258,53 @@ class B200Backend(AbstractBackend):
         self.last_plan = None
 
     def _nested_eval(self, net: nw.Network) -> np.ndarray:
+        """Contract a sub-network on the device (``BitControlledBox`` slabs,
+        control.py:164-191).  Cached by structure + values: a batch of evals that
+        differ only outside the controlled box pays for it once."""
         from .. import executor
-        return executor.evaluate(net, dtype=np.complex128).cpu().numpy()
+        key = (net.structure_key(), complex(net.scalar),
+               tuple(l.params.tobytes() for l in net.leaves if l.params is not None))
+        cache = self.__dict__.setdefault("_nested_cache", {})
+        if key not in cache:
+            cache[key] = executor.evaluate(net, dtype=np.complex128).cpu().numpy()
+        return cache[key]
+
+    def eval_batch(self, diagrams) -> list:
+        """Evaluate structurally identical diagrams (same boxes and wiring,
+        different parameters) as ONE batched plan: one leaf-arena build and one
+        launch per contraction step for the whole batch."""
+        from .. import executor
+        diagrams = list(diagrams)
+        nets = [self._get_network(d, nested_eval=self._nested_eval) for d in diagrams]
+        key0 = nets[0].structure_key()
+        for net in nets[1:]:
+            if net.structure_key() != key0:
+                raise ValueError("eval_batch needs structurally identical diagrams")
+        # per-eval scalars travel as a rank-0 leaf so the kernels apply them
+        for net in nets:
+            net.leaves.append(nw.Leaf(nw.K_DENSE, (), (), 0,
+                                      np.array([net.scalar], dtype=np.complex128), "scalar"))
+            net.scalar = 1.0 + 0j
+        plan = executor.get_plan(nets[0], dtype=self.dtype, batch=len(nets),
+                                 trials=self.trials, seed=self.seed)
+        self.last_plan = plan
+        sess = executor.Session(plan)
+        if len(plan.steps) > 8 and not plan.sliced:
+            sess.set_leaves(nets)
+            sess.capture(1.0 + 0j)
+            sess.replay()
+            dev = sess.out
+        else:
+            dev = sess.run(nets, scalar=1.0 + 0j)
+        host = self._to_host(dev)
+        n, shape = nets[0].n_dom, nets[0].output_shape
+        results = []
+        for e, d in enumerate(diagrams):
+            state_type = StateType.AMP if d.is_pure else StateType.DM
+            results.append(EvalResult(ResultTensor(shape[:n], shape[n:], host[e]),
+                                      output_types=d.cod, state_type=state_type,
+                                      _device=dev[e] if self.keep_on_device else None))
+        return results
 
     def eval_network(self, net: nw.Network):
         """Device tensor of one network (plan cached by structure)."""

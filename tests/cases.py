@@ -160,3 +160,22 @@ def fusion_i_spider():
             >> qmode ** 2 @ classical.PostselectBit(1) @ bit
             >> qmode @ channel.Swap(qmode, bit) >> channel.Swap(qmode, bit) @ qmode
             >> correction >> photonic.DualRail(1).dagger())
+
+
+def fusion_link(vector, close="bell"):
+    """SURVEY 8(d) cfg5a / README.md:230-280: heralded entanglement link through a
+    type-II fusion of two partially distinguishable dual-rail photons."""
+    bell_state = qubits.Z(0, 2) @ qubits.Scalar(0.5 ** 0.5)
+    enc = photonic.DualRail(1, internal_states=[[1, 0]]) @ \
+        photonic.DualRail(1, internal_states=[list(vector)])
+    post_select = classical.PostselectBit(1) @ classical.PostselectBit(0)
+    experiment = bell_state @ bell_state >> \
+        qubits.Id(1) @ (enc >> photonic.FusionTypeII() >> post_select) @ qubits.Id(1)
+    tail = bell_state.dagger() if close == "bell" else qubits.Discard(2)
+    return (experiment >> tail).inflate(2)
+
+
+def fusion_teleport_input(phi):
+    """fusion-II teleportation with classical feed-forward
+    (test_fusion.py:9-33) applied to the input state Ket('+') >> Z(1, 1, phi)."""
+    return qubits.Ket("+") >> qubits.Z(1, 1, phi) >> fusion_ii_teleportation()

@@ -171,3 +171,40 @@ def test_cuda_graph_with_parallel_branches_matches_plain_run(name):
         sess.replay()
     torch.cuda.synchronize()
     assert _close(sess.out[0].cpu().numpy(), want, TOL128)
+
+
+def test_eval_batch_one_plan_many_parameter_sets():
+    """cfg5: structurally identical diagrams -> one batched plan (leading batch
+    mode on every tensor), per-eval scalars as a rank-0 leaf."""
+    import math
+    from cases import fusion_link, fusion_teleport_input
+    backend = B200Backend()
+    angles = [i * (math.pi / 2) / 7 for i in range(8)]
+    ds = [fusion_link((math.cos(t), math.sin(t)), "bell") for t in angles]
+    res = backend.eval_batch(ds)
+    assert backend.last_plan.batch == 8
+    for d, r in zip(ds, res):
+        want = oracle_eval(d)
+        assert r.tensor.array.shape == want.shape and _close(r.tensor.array, want, TOL128)
+    norm = backend.eval_batch([fusion_link((math.cos(t), math.sin(t)), "discard")
+                               for t in angles])
+    ratios = [(a.tensor.array / b.tensor.array).real for a, b in zip(res, norm)]
+    assert ratios[0] == pytest.approx(1.0, abs=1e-10)
+    assert all(x > y for x, y in zip(ratios, ratios[1:]))
+    phis = [j / 8 for j in range(8)]
+    res = backend.eval_batch([fusion_teleport_input(p) for p in phis])
+    for p, r in zip(phis, res):
+        assert _close(r.tensor.array, oracle_eval(fusion_teleport_input(p)), TOL128)
+
+
+def test_cfg3_standard_size_properties():
+    """cfg3 at a size the oracle cannot reach quickly: 6 modes x inflate 2,
+    2 partially distinguishable photons, loss, 3 measured modes.  Checked through
+    size-independent properties: normalisation, non-negativity, photon number."""
+    from cases import cfg3_interferometer
+    d = cfg3_interferometer(width=6, n_photons=2, measured=3)
+    res = d.eval(B200Backend())
+    p = res.prob_dist()
+    assert sum(p.values()) == pytest.approx(1.0, abs=1e-9)
+    assert all(v >= -1e-12 for v in p.values())
+    assert all(sum(int(i) for i in k) <= 2 for k, v in p.items() if v > 1e-12)

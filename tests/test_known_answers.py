@@ -295,3 +295,21 @@ def test_cfg3_small_distribution_is_normalised():
     p = ev.prob_dist(arr, ["mode", "mode"], ev.DM)
     assert sum(p.values()) == pytest.approx(1.0, abs=1e-9)
     assert all(v >= -1e-12 for v in p.values())
+
+
+# ---- README.md:230-296 (cfg5a) and test_fusion.py + input phases (cfg5b) --------------------
+def test_cfg5_fusion_link_fidelity_and_feed_forward_teleport():
+    import math
+    from cases import fusion_link, fusion_teleport_input
+    ratios = []
+    for i in (0, 7, 14):
+        th = i * (math.pi / 2) / 14
+        v = (math.cos(th), math.sin(th))
+        ratios.append((oracle_eval(fusion_link(v, "bell"))
+                       / oracle_eval(fusion_link(v, "discard"))).real)
+    assert ratios[0] == pytest.approx(1.0, abs=1e-12)          # indistinguishable: perfect link
+    assert ratios[0] > ratios[1] > ratios[2]                   # monotone in the overlap
+    assert ratios[2] == pytest.approx(0.5, abs=1e-12)
+    got = oracle_eval(fusion_teleport_input(0.3))
+    want = dbl(qubits.Ket("+") >> qubits.Z(1, 1, 0.3) @ qubits.Scalar(0.5 ** 0.5))
+    assert np.allclose(got, want)
