@@ -59,7 +59,9 @@ def _emit_z(b, ins, n_out, amplitudes) -> List[int]:
     """``zw.ZBox(n, m, [1, a]).truncation([2] * n)`` (zx.py:382-397).  The
     vector is skipped when it is exactly [1, 1] (identity diagonal)."""
     amps = np.asarray(amplitudes, dtype=complex)
-    trivial = amps[0] == 1 and amps[1] == 1
+    # a 1 -> 1 spider is a phase GATE: keep its vector even at phase 0 so that a
+    # batch of evals over the phase has one network structure (eval_batch)
+    trivial = amps[0] == 1 and amps[1] == 1 and not (len(ins) == 1 and n_out == 1)
     return diagram.emit_spider(b, ins, [2] * len(ins), n_out, 2,
                                amplitudes=None if trivial else amps)
 
