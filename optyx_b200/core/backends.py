@@ -157,8 +157,10 @@ class EvalResult:
         flat = np.flatnonzero(nz_h)
         if flat.size == 0:
             return {}
-        multi = np.vstack(np.unravel_index(flat, self.tensor.array.shape)).T
-        return {tuple(idx): val for idx, val in zip(multi, p_h[flat])}
+        # keys as tuples of Python ints (hash/compare equal to the reference's
+        # tuples of numpy ints); .tolist() makes the dict build ~10x faster
+        multi = np.vstack(np.unravel_index(flat, self.tensor.array.shape)).T.tolist()
+        return dict(zip(map(tuple, multi), p_h[flat].tolist()))
 
     def _prob_dist_mixed(self) -> dict:
         """backends.py:306-356 with the diagonal partial trace on the device."""
@@ -194,9 +196,8 @@ class EvalResult:
         flat = np.flatnonzero(seen_h)
         probs = defaultdict(float)
         if flat.size:
-            multi = np.vstack(np.unravel_index(flat, meas_shape)).T
-            for idx, val in zip(multi, p_h[flat]):
-                probs[tuple(idx)] = float(val)
+            multi = np.vstack(np.unravel_index(flat, meas_shape)).T.tolist()
+            probs.update(zip(map(tuple, multi), p_h[flat].tolist()))
         return probs
 
     def _resident(self):

@@ -623,6 +623,83 @@ def get_max_dim_for_box(left_offset: int, box, right_offset: int, input_dims: Li
     return max(dim_for_box, 2)
 
 
+class ConeTracker:
+    """Forward formulation of the light-cone walk (utils.py:436-510).
+
+    ``get_max_dim_for_box`` walks ALL earlier layers backwards for every box
+    (O(#boxes^2) Python, the dominant host cost of the reference for large or
+    batched circuits, SURVEY.md 8(a) row a3').  The same quantity propagates
+    forwards: every wire carries the set of photon sources in its past cone -- a
+    bitmask over sources, a source being one output of a ``Create`` (weight = its
+    photons) or one open mode input of the diagram (weight = 2 * dim).  A box
+    hands the union of the cones of its mode-typed inputs to each of its
+    outputs; a swap swaps two cones.  The bound of a box is the total weight of
+    the union over its mode inputs, + 1, at least 2 -- identical, by
+    construction, to what the backward walk returns (checked against it in
+    tests/test_known_answers.py::test_forward_cone_equals_backward_walk)."""
+
+    def __init__(self, dom: Ty, input_dims: Sequence[int]):
+        self.weights: List[int] = []
+        self.frontier: List[int] = []
+        for t, dim in zip(dom.inside, input_dims):
+            if t == "mode":
+                self.frontier.append(1 << len(self.weights))
+                self.weights.append(2 * int(dim))
+            else:
+                self.frontier.append(0)
+        self._sums = {0: 0}
+
+    def _weight(self, mask: int) -> int:
+        s = self._sums.get(mask)
+        if s is None:
+            s, m, k = 0, mask, 0
+            while m:
+                if m & 1:
+                    s += self.weights[k]
+                m >>= 1
+                k += 1
+            self._sums[mask] = s
+        return s
+
+    def max_dim(self, left: int, box) -> float:
+        from .zw import Divide, Endo, Multiply
+        if len(box.dom) == 0 or isinstance(box, (Swap, Endo, Divide, Multiply)):
+            return UNCAPPED
+        mask = 0
+        for k, t in enumerate(box.dom.inside):
+            if t == "mode":
+                mask |= self.frontier[left + k]
+        return max(self._weight(mask) + 1, 2)
+
+    def apply(self, left: int, prev_box) -> bool:
+        """Push one recorded (replacement) box; False if its span does not fit
+        the frontier (the backward walk clamps such offsets, utils.py:466-476)."""
+        from .zw import Create
+        n_dom, n_cod = len(prev_box.dom), len(prev_box.cod)
+        if left < 0 or left + n_dom > len(self.frontier):
+            return False
+        if isinstance(prev_box, Swap):
+            f = self.frontier
+            f[left], f[left + 1] = f[left + 1], f[left]
+            return True
+        mask = 0
+        for k, t in enumerate(prev_box.dom.inside):
+            if t == "mode":
+                mask |= self.frontier[left + k]
+        if isinstance(prev_box, Create):
+            new = []
+            for c in range(n_cod):
+                new.append(mask | (1 << len(self.weights)))
+                self.weights.append(int(prev_box.photons[c]))
+        else:
+            new = [mask] * n_cod
+        self.frontier[left:left + n_dom] = new
+        return True
+
+
+FORWARD_CONES = True     # False: the literal backward walk (slow, reference-shaped)
+
+
 def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
                     builder: Optional[nw.NetworkBuilder] = None,
                     in_inds: Optional[List[int]] = None, nested_eval=None):
@@ -642,9 +719,13 @@ def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
     dom_inds = list(wires)
     n_wires = len(d.dom)
     prev_layers: List[Tuple[int, object]] = []
+    cones = ConeTracker(d.dom, input_dims) if FORWARD_CONES else None
     for box, left in zip(d.boxes, d.offsets):
         right = calculate_right_offset(n_wires, left, len(box.dom))
-        max_dim = get_max_dim_for_box(left, box, right, list(input_dims), prev_layers)
+        if cones is not None:
+            max_dim = cones.max_dim(left, box)
+        else:
+            max_dim = get_max_dim_for_box(left, box, right, list(input_dims), prev_layers)
         dims_in = layer_dims[left:left + len(box.dom)]
         dims_out = [int(max_dim) if i > max_dim else int(i)
                     for i in box.determine_output_dimensions(list(dims_in))]
@@ -652,6 +733,13 @@ def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
         if isinstance(repl, Diagram) and not isinstance(repl, Box):
             repl = [_LayerView(l @ bx.dom @ r, l @ bx.cod @ r) for l, bx, r in repl.layers()]
         prev_layers += [(left, rb) for rb in repl]
+        if cones is not None:
+            for rb in repl:
+                if not cones.apply(left, rb):
+                    # an offset the backward walk would clamp: replay everything
+                    # recorded so far through the literal walker from here on
+                    cones = None
+                    break
         outs = box.emit(b, wires[left:left + len(box.dom)], dims_in, dims_out)
         assert len(outs) == len(box.cod), (box, outs)
         for o, dd in zip(outs, dims_out):
