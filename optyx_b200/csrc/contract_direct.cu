@@ -241,6 +241,83 @@ static bool make_tiled(const b2_modes& md, long long n_out_elems, int sms, b2_mo
     return true;
 }
 
+
+// ---- split-K reduction kernel ---------------------------------------------------
+// Few outputs, huge reduction (e.g. the last pair of a photonic network: a 7 x 7
+// result summed over 4 million index values).  Each CTA owns a chunk of the
+// reduction range, decodes its A/B offsets once into shared memory, then every
+// warp sums its outputs over the chunk (lanes stride the chunk, shuffle
+// reduce) and adds the partial into C with two FP64 atomics.
+constexpr int kRedChunk = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+contract_reduce_kernel(const __grid_constant__ b2_modes md, int n_out_elems, long long n_red_elems,
+                       const typename cplx<T>::type* __restrict__ A,
+                       const typename cplx<T>::type* __restrict__ B,
+                       typename cplx<T>::type* __restrict__ Cout, T alpha_re, T alpha_im) {
+    using C = typename cplx<T>::type;
+    __shared__ long long ra[kRedChunk], rb[kRedChunk];
+    const int n_out = md.n_out, n_red = md.n_red;
+    const long long r0 = (long long)blockIdx.x * kRedChunk;
+    const int nr = (int)((n_red_elems - r0) < kRedChunk ? (n_red_elems - r0) : kRedChunk);
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        long long rem = r0 + i, oa = 0, ob = 0;
+        for (int m = n_out + n_red - 1; m >= n_out; --m) {
+            const long long d = md.dim[m];
+            const long long q = rem / d, x = rem - q * d;
+            rem = q;
+            oa += x * md.sa[m];
+            ob += x * md.sb[m];
+        }
+        ra[i] = oa; rb[i] = ob;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int o = warp; o < n_out_elems; o += nwarps) {
+        long long oa = 0, ob = 0, oc = 0;
+        int rem = o;
+        for (int m = n_out - 1; m >= 0; --m) {
+            const int d = md.dim[m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            oa += (long long)x * md.sa[m];
+            ob += (long long)x * md.sb[m];
+            oc += (long long)x * md.sc[m];
+        }
+        C acc = make_c<T>((T)0, (T)0);
+        #pragma unroll 4
+        for (int i = lane; i < nr; i += 32) cfma(acc, A[oa + ra[i]], B[ob + rb[i]]);
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        if (lane == 0) {
+            T* dst = reinterpret_cast<T*>(Cout + oc);
+            atomicAdd(dst, alpha_re * acc.x - alpha_im * acc.y);
+            atomicAdd(dst + 1, alpha_re * acc.y + alpha_im * acc.x);
+        }
+    }
+}
+
+template <typename T>
+__global__ void zero_strided_kernel(const __grid_constant__ b2_modes md, int n_out_elems,
+                                    typename cplx<T>::type* __restrict__ Cout) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_out_elems;
+         o += gridDim.x * blockDim.x) {
+        long long oc = 0;
+        int rem = o;
+        for (int m = md.n_out - 1; m >= 0; --m) {
+            const int d = md.dim[m];
+            const int q = rem / d, x = rem - q * d;
+            rem = q;
+            oc += (long long)x * md.sc[m];
+        }
+        Cout[oc] = make_c<T>((T)0, (T)0);
+    }
+}
+
 template <typename T>
 int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, double ar,
                   double ai, int accumulate, cudaStream_t s) {
@@ -252,6 +329,19 @@ int launch_direct(const b2_modes* md, const void* a, const void* b, void* c, dou
     int sms = num_sms();
     if (sms <= 0) return 1;
 
+    if (n_out_elems <= 4096 && n_red_elems >= 4096 && n_out_elems * 8 <= n_red_elems) {
+        // reduction-dominated pair: parallelise over the reduction range
+        const long long chunks = (n_red_elems + kRedChunk - 1) / kRedChunk;
+        if (chunks <= 2147483647ll) {
+            if (!accumulate)
+                zero_strided_kernel<T><<<(unsigned)((n_out_elems + 255) / 256), 256, 0, s>>>(
+                    *md, (int)n_out_elems, (C*)c);
+            contract_reduce_kernel<T><<<(unsigned)chunks, 256, 0, s>>>(
+                *md, (int)n_out_elems, n_red_elems, (const C*)a, (const C*)b, (C*)c, (T)ar, (T)ai);
+            set_last_kernel("reduce");
+            return check_launch("b2_contract_direct(reduce)");
+        }
+    }
     {   // primary path: C-tiled, B block in shared memory, A rows in registers
         bool handled = false;
         const int dt = sizeof(T) == 8 ? B2_C128 : B2_C64;

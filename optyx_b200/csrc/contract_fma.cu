@@ -20,7 +20,7 @@
 namespace b2 {
 
 constexpr int FM_THREADS = 256, FM_TMAX = 16384, FM_MAXM = 1024, FM_MAXN = 64, FM_U = 16;
-constexpr int FM_KMAX = 16, FM_MAXTB = 64, FM_BTILE_BYTES = 32 * 1024;
+constexpr int FM_KMAX = 16, FM_MAXTB = 64, FM_BTILE_BYTES = 32 * 1024, FM_SMEM_MAX = 64 * 1024;
 
 struct fm_desc {
     int n_outer, n_ir, n_in, n_k;       // mode counts, stored in this order
@@ -315,13 +315,28 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     while (KP < d.K) KP <<= 1;
     const size_t smem = (size_t)(2 * d.TM + 2 * d.TN + ((d.TB + 1) & ~1) + 2 * KP) * 8 +
                         (size_t)KP * d.TB * d.TN * sizeof(C) + (size_t)d.TM * 4 + 16;
+    if (smem > (size_t)FM_SMEM_MAX) { set_error("fma: tile tables need %zu B of shared memory", smem); return 1; }
     long long blocks = n_tiles;
     const long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;
     const C* A = (const C*)a; const C* B = (const C*)b; C* Cc = (C*)c;
+    // tables (<= 21 KB) + the B block (<= 32 KB) can exceed the 48 KB default
 #define B2_FMA_LAUNCH(KPV)                                                                   \
-    contract_fma_kernel<T, KPV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(                  \
-        d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate)
+    do {                                                                                     \
+        static bool attr_done = false;                                                       \
+        if (!attr_done) {                                                                    \
+            cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV>,                \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 FM_SMEM_MAX);                               \
+            if (e != cudaSuccess) {                                                          \
+                set_error("fma smem attr: %s", cudaGetErrorString(e));                       \
+                return 1;                                                                    \
+            }                                                                                \
+            attr_done = true;                                                                \
+        }                                                                                    \
+        contract_fma_kernel<T, KPV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(              \
+            d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate);                                 \
+    } while (0)
     switch (KP) {
     case 1: B2_FMA_LAUNCH(1); break;
     case 2: B2_FMA_LAUNCH(2); break;

@@ -168,6 +168,79 @@ def _gemm_case(rng, mshape, nshape, kshape, bshape=()):
     return dC, want
 
 
+def _direct_case(rng, out_shape, red_shape, dtype, accumulate):
+    """C[out] (+)= alpha * sum_red A[..] B[..] through b2_contract_direct; every mode is
+    given at random to A, B or both, operands stored in random axis orders."""
+    torch = _torch()
+    lib = rt.load()
+    n_out, n_red = len(out_shape), len(red_shape)
+    dims = list(out_shape) + list(red_shape)
+    in_a, in_b = [], []
+    for m in range(len(dims)):
+        w = int(rng.integers(0, 3)) if m < n_out else int(rng.integers(0, 4))
+        (in_a if w in (0, 2, 3) else in_b).append(m)
+        if w in (2, 3) and m not in in_b:
+            in_b.append(m)
+    def operand(modes):
+        order = [modes[i] for i in rng.permutation(len(modes))]
+        shape = [dims[m] for m in order]
+        arr = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        strides, s = {}, 1
+        for m, d in zip(reversed(order), reversed(shape)):
+            strides[m] = s
+            s *= d
+        return arr.astype(dtype), order, strides
+    A, oA, sA = operand(in_a)
+    B, oB, sB = operand(in_b)
+    md = rt.Modes()
+    md.n_out, md.n_red = n_out, n_red
+    s = 1
+    for m in range(len(dims)):
+        md.dim[m] = dims[m]
+        md.sa[m], md.sb[m] = sA.get(m, 0), sB.get(m, 0)
+    for m in reversed(range(n_out)):
+        md.sc[m] = s
+        s *= dims[m]
+    letters = [chr(ord("a") + m) for m in range(len(dims))]
+    spec = "".join(letters[m] for m in oA) + "," + "".join(letters[m] for m in oB) + "->" + \
+        "".join(letters[:n_out])
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    c0 = np.asarray(rng.standard_normal(out_shape) + 1j * rng.standard_normal(out_shape)).astype(dtype)
+    dC = torch.from_numpy(c0.copy()).cuda()
+    alpha = 0.5 - 0.25j
+    stream = torch.cuda.current_stream().cuda_stream
+    dt = rt.B2_C128 if dtype == np.complex128 else rt.B2_C64
+    rt.check(lib.b2_contract_direct(C.byref(md), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(),
+                                    alpha.real, alpha.imag, accumulate, dt, stream))
+    kernel = lib.b2_last_kernel().decode()
+    want = alpha * np.einsum(spec, A.astype(np.complex128), B.astype(np.complex128))
+    if accumulate:
+        want = want + c0
+    return dC.cpu().numpy(), want, kernel
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("accumulate", [0, 1])
+@pytest.mark.parametrize("case", [
+    ((7, 7), (7, 7, 7, 7, 7)),                  # reduction-dominated (split-K kernel)
+    ((), (2,) * 14),                            # scalar output, long reduction
+    ((3,), (5, 1000)),
+    ((2,) * 16, (2, 2)),                        # big x tiny
+    ((7, 7, 7, 7), (7,)),
+    ((4, 4, 4, 4, 4, 4), (4, 4)),
+    ((2,) * 20, ()),                            # outer product
+    ((5, 3), ()),
+    ((128, 64), (48,)),
+])
+def test_direct_kernel_variants(case, accumulate, dtype):
+    for seed in range(3):
+        rng = np.random.default_rng(seed)
+        got, want, kernel = _direct_case(rng, case[0], case[1], dtype, accumulate)
+        tol = 1e-10 if dtype == np.complex128 else 1e-5
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(got - want).max() <= tol * scale, (case, kernel, seed)
+
+
 @pytest.mark.parametrize("case", [
     ((64,), (64,), (8,), ()),
     ((2, 2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2), ()),

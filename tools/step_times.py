@@ -12,14 +12,20 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from optyx_b200 import executor  # noqa: E402
 
-depth = int(sys.argv[1]) if len(sys.argv) > 1 else 41
-tgt = int(sys.argv[2]) if len(sys.argv) > 2 else 26
-net = cases.compile_channel(cases.random_clifford_t(30, depth, seed=0))
-plan = executor.get_plan(net, target_size=float(2 ** tgt), trials=16)
+if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
+    net = cases.compile_channel(cases.cfg3_interferometer(width=6, n_photons=3, measured=2))
+    plan = executor.get_plan(net)
+    for st in plan.steps:
+        st.per_slice = True          # time every step
+else:
+    depth = int(sys.argv[1]) if len(sys.argv) > 1 else 41
+    tgt = int(sys.argv[2]) if len(sys.argv) > 2 else 26
+    net = cases.compile_channel(cases.random_clifford_t(30, depth, seed=0))
+    plan = executor.get_plan(net, target_size=float(2 ** tgt), trials=16)
 sess = executor.Session(plan)
 sess.set_leaves([net])
 sess.build_leaves()
-sess.contract(net.scalar, slice_range=(0, 1))
+sess.contract(net.scalar, slice_range=(0, 1)) if plan.sliced else sess.run([net])
 torch.cuda.synchronize()
 stream = torch.cuda.current_stream().cuda_stream
 vals = [0] * len(plan.sliced)
