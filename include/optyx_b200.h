@@ -120,8 +120,11 @@ int b2_contract_direct(const b2_modes* modes, const void* a_dev,
                        double alpha_im, int32_t accumulate, int32_t dtype,
                        void* stream);
 
-/* (2b) large dense pairs: tiled gather -> shared memory -> FP64 DMMA
- * (complex128) complex GEMM with fused index permutation on load and store.  */
+/* (2b) large dense pairs: complex GEMM with fused index permutation on load
+ * and store.  complex128: gather -> shared memory -> FP64 DMMA (mma.sync, no
+ * tcgen05 kind exists for f64).  complex64: gather + hi/lo split -> shared
+ * memory (UMMA layout) -> tcgen05.mma kind::tf32, 3 split products per k-step,
+ * FP32 accumulators in tensor memory.                                        */
 int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev,
                      const void* b_dev, void* c_dev, double alpha_re,
                      double alpha_im, int32_t accumulate, int32_t dtype,

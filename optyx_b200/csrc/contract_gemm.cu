@@ -194,6 +194,8 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
 
 int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, double ar,
                  double ai, int accumulate, cudaStream_t s, bool& handled);
+int launch_gemm_c64(const b2_gemm_modes& g, const void* a_dev, const void* b_dev, void* c_dev,
+                    double ar, double ai, int accumulate, cudaStream_t s);
 
 }  // namespace b2
 
@@ -202,8 +204,8 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
                                 int32_t accumulate, int32_t dtype, void* stream) {
     using namespace b2;
     if (!modes || !a_dev || !b_dev || !c_dev) { set_error("b2_contract_gemm: null pointer"); return 1; }
-    if (dtype != B2_C128) {
-        set_error("b2_contract_gemm: only complex128 has a tensor-core path in this build");
+    if (dtype != B2_C128 && dtype != B2_C64) {
+        set_error("b2_contract_gemm: bad dtype %d", dtype);
         return 1;
     }
     const b2_gemm_modes& g = *modes;
@@ -213,6 +215,9 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         return 1;
     }
     if (num_sms() <= 0) return 1;
+    if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
+        return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
+                               (cudaStream_t)stream);
     long long k_total = 1, n_total = 1;
     for (int i = 0; i < g.n_k; ++i) k_total *= g.dim[g.n_batch + g.n_m + g.n_n + i];
     for (int i = 0; i < g.n_n; ++i) n_total *= g.dim[g.n_batch + g.n_m + i];

@@ -483,7 +483,8 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
         # over 6.5 TB/s); everything else is bandwidth work for the direct kernel
         intensity = 8.0 * macs / max(nbytes, 1.0)
         min_ai = gemm_threshold[3] if len(gemm_threshold) > 3 else 0.0
-        use_gemm = (dtype == np.complex128 and Mx >= gemm_threshold[0]
+        # (complex128: FP64 DMMA; complex64: tcgen05 kind::tf32 split precision)
+        use_gemm = (Mx >= gemm_threshold[0]
                     and Nx >= gemm_threshold[1] and Kx >= gemm_threshold[2]
                     and intensity >= min_ai)
         desc = None
@@ -494,7 +495,7 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
             redm = sorted([mode(q) for q in red], key=lambda m: (-m[1], -m[2]))
             redm = _merge_modes(redm, fastest_last=True)
             if len(redm) > MAX_RED_DIRECT:
-                use_gemm = dtype == np.complex128
+                use_gemm = True
             if not use_gemm:
                 if len(outm) + len(redm) > MAX_MODES:
                     raise ValueError("contraction step has too many modes for the kernel")

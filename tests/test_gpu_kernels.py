@@ -123,7 +123,7 @@ def test_batched_evals_share_one_plan(batch):
             assert np.abs(got[e] - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
 
 
-def _gemm_case(rng, mshape, nshape, kshape, bshape=()):
+def _gemm_case(rng, mshape, nshape, kshape, bshape=(), dtype=np.complex128):
     """A[b,m,k] x B[b,k,n] with every operand stored in a random axis order."""
     torch = _torch()
     lib = rt.load()
@@ -137,7 +137,7 @@ def _gemm_case(rng, mshape, nshape, kshape, bshape=()):
         perm = list(rng.permutation(len(axes)))
         axes = [axes[p] for p in perm]
         shape = [names[a] for a in axes]
-        arr = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        arr = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dtype)
         strides, s = {}, 1
         for a, d in zip(reversed(axes), reversed(shape)):
             strides[a] = s
@@ -159,13 +159,15 @@ def _gemm_case(rng, mshape, nshape, kshape, bshape=()):
     spec = "".join(letters[a] for a in axA) + "," + "".join(letters[a] for a in axB) + "->" + \
         "".join(letters[a] for a in axC)
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(Bm).cuda()
-    dC = torch.zeros(Cz.shape, dtype=torch.complex128, device="cuda")
+    dC = torch.zeros(Cz.shape, dtype=dA.dtype, device="cuda")
     alpha = 0.5 - 0.25j
     stream = torch.cuda.current_stream().cuda_stream
+    code = rt.B2_C128 if dtype == np.complex128 else rt.B2_C64
     rt.check(lib.b2_contract_gemm(C.byref(desc), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(),
-                                  alpha.real, alpha.imag, 0, rt.B2_C128, stream))
-    want = alpha * torch.einsum(spec, dA, dB)
-    return dC, want
+                                  alpha.real, alpha.imag, 0, code, stream))
+    torch.cuda.synchronize()
+    want = alpha * torch.einsum(spec, dA.to(torch.complex128), dB.to(torch.complex128))
+    return dC.to(torch.complex128), want
 
 
 def _direct_case(rng, out_shape, red_shape, dtype, accumulate):
@@ -184,7 +186,7 @@ def _direct_case(rng, out_shape, red_shape, dtype, accumulate):
     def operand(modes):
         order = [modes[i] for i in rng.permutation(len(modes))]
         shape = [dims[m] for m in order]
-        arr = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        arr = np.asarray(rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
         strides, s = {}, 1
         for m, d in zip(reversed(order), reversed(shape)):
             strides[m] = s
@@ -254,6 +256,27 @@ def test_gemm_kernel_permuted_operands(case):
     got, want = _gemm_case(rng, *case)
     err = (got - want).abs().max().item()
     assert err <= 1e-10 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [
+    ((128,), (64,), (16,), ()),                 # one tile, one chunk
+    ((128,), (32,), (64,), ()),
+    ((256,), (128,), (48,), ()),
+    ((2, 2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2, 2), (2, 2, 2, 2, 2), ()),
+    ((7, 7, 3), (5, 7, 4), (7, 3, 2), (3,)),
+    ((100,), (33,), (17,), (2, 2)),
+    ((130,), (70,), (5,), ()),
+    ((2,) * 10, (2,) * 9, (2,) * 7, ()),
+    ((300,), (200,), (1000,), ()),
+])
+def test_gemm_c64_tcgen05_permuted_operands(case):
+    """complex64 tensor-core path (tcgen05 kind::tf32, 3-product split): FP32-level
+    accuracy, far inside the 1e-5 bar of the north star."""
+    rng = np.random.default_rng(4)
+    got, want = _gemm_case(rng, *case, dtype=np.complex64)
+    assert rt.load().b2_last_kernel().decode() == "gemm_c64_tcgen05"
+    err = (got - want).abs().max().item()
+    assert err <= 5e-6 * max(1.0, want.abs().max().item()), err
 
 
 def test_probs_amp_and_dm_match_oracle():
