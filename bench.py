@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC, UNIT = "eval_diagrams_per_sec", "diagrams/s"
+FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profiles/r01_probe.json)
 
 
 def workload(name: str, small: bool = False):
@@ -274,6 +275,16 @@ def main():
         "macs_per_launch": dom.macs,
     }
 
+    # whole-plan roofline: sum over steps of max(bytes / HBM, flops / FP64 pipe)
+    from optyx_b200.planner import plan_bound_seconds
+    fp64_tf = FP64_PIPE_TFLOPS
+    bound_s = plan_bound_seconds(plan, hbm_peak, fp64_tf)
+    plan_roofline = {"bound_ms": bound_s * 1e3, "measured_ms": secs / args.steps * 1e3,
+                     "frac": bound_s / (secs / args.steps), "hbm_gbs": hbm_peak,
+                     "fp64_pipe_tflops": fp64_tf,
+                     "note": "sum over plan steps of max(algorithmic bytes / HBM peak, 8 MACs / "
+                             "FP64 DMMA peak measured on this pool, profiles/r01_probe.json)"}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
@@ -287,6 +298,7 @@ def main():
                 "d2h_bytes_per_step": d2h, "ms_per_eval": e2e_secs * 1e3},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
+        "plan_roofline": plan_roofline,
         "contraction_tflops": 8.0 * plan.total_macs * world * args.steps / secs / 1e12,
     }
 
@@ -328,9 +340,17 @@ def run_sliced(world: int, rank: int):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         secs = float(tt.item())
     a = complex(amp.cpu().numpy())
+    from optyx_b200.planner import plan_bound_seconds
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except OSError:
+        hbm = 6650.0
+    bound = plan_bound_seconds(plan, hbm, FP64_PIPE_TFLOPS) / world
     return {"workload": desc, "nslices": plan.nslices, "peak_elems": plan.info.peak,
-            "macs": plan.total_macs, "ms": secs * 1e3,
+            "macs": plan.total_macs, "bytes": plan.total_bytes, "ms": secs * 1e3,
             "tflops": 8.0 * plan.total_macs / secs / 1e12,
+            "gbs": plan.total_bytes / secs / 1e9,
+            "roofline_bound_ms": bound * 1e3, "roofline_frac": bound / secs,
             "amplitude": [a.real, a.imag], "n_gpus": world}
 
 

@@ -221,7 +221,7 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     long long k_total = 1, n_total = 1;
     for (int i = 0; i < g.n_k; ++i) k_total *= g.dim[g.n_batch + g.n_m + g.n_n + i];
     for (int i = 0; i < g.n_n; ++i) n_total *= g.dim[g.n_batch + g.n_m + i];
-    if (k_total <= 64 || n_total < 64) {
+    if (k_total <= 32 || n_total < 64) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
         // classic 64x64 tiling below (4x4 register blocking per warp).

@@ -560,6 +560,17 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
     return plan
 
 
+def plan_bound_seconds(plan: Plan, hbm_gbs: float, pipe_tflops: float) -> float:
+    """Roofline lower bound of one evaluation of ``plan``: per
+    step max(algorithmic bytes / HBM bandwidth, 8 * MACs / math-pipe peak),
+    summed over the steps (per-slice steps x nslices)."""
+    total = 0.0
+    for st in plan.steps:
+        t = max(st.bytes / (hbm_gbs * 1e9), 8.0 * st.macs / (pipe_tflops * 1e12))
+        total += t * (plan.nslices if st.per_slice else 1)
+    return total
+
+
 def _reallocate_for_slices(steps: List[Step], batch: int) -> None:
     """Invariant intermediates get a private region (never recycled by
     per-slice tensors); per-slice tensors share a second, recycled region."""
