@@ -35,12 +35,13 @@
 
 namespace b2 {
 
-constexpr int G4_THREADS = 256, G4_BM = 128, G4_KC = 16;
+constexpr int G4_CONV = 256;                      // converter threads (8 warps)
+constexpr int G4_THREADS = G4_CONV + 32;         // + the MMA warp
+constexpr int G4_BM = 128, G4_KC = 16;
 constexpr int G4_RAW = 3;                        // cp.async stages of raw complex64 operands
 constexpr int G4_STAGES = 2;                     // UMMA operand stages (hi/lo split tiles)
 constexpr int G4_KG = G4_KC / 2;                 // 16-byte k-groups (2 complex) per chunk
 constexpr int G4_SEG = 4;                        // chunks per TMEM accumulation segment
-constexpr int G4_RPITCH = G4_KC + 1;             // raw row pitch when K is the contiguous mode
 
 __device__ __forceinline__ uint32_t g4_smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -119,15 +120,15 @@ constexpr int G4_ROWS_A = G4_BM + 1;
 template <int NT>
 struct g4_smem {
     static constexpr int ROWS_B = 2 * NT + 1;
+    static constexpr int LOADS = (G4_BM + NT) * G4_KC / G4_CONV;     // 8 B copies per thread, chunk
     // UMMA operand tiles: [stage][hi/lo][k-group][row][4 floats]
     float4 a[G4_STAGES][2][G4_KG][G4_ROWS_A];
     float4 b[G4_STAGES][2][G4_KG][ROWS_B];
-    // raw complex64 operands as they arrive from global memory
-    float2 raw_a[G4_RAW][G4_BM * G4_RPITCH];
-    float2 raw_b[G4_RAW][NT * G4_RPITCH];
+    // cp.async landing slots, private per thread: [raw stage][copy][thread]
+    float2 raw[G4_RAW][LOADS][G4_CONV];
     long long row_a[G4_BM], row_c[G4_BM], col_b[NT], col_c[NT];
     long long k_a[4][G4_KC], k_b[4][G4_KC];
-    uint64_t bar[G4_STAGES];
+    uint64_t full[G4_STAGES], empty[G4_STAGES];
     uint32_t tmem_base;
 };
 
@@ -139,11 +140,9 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                          float alpha_re, float alpha_im, int accumulate) {
     extern __shared__ __align__(1024) unsigned char g4_raw[];
     g4_smem<NT>& sm = *reinterpret_cast<g4_smem<NT>*>(g4_raw);
-    constexpr int NP = 2 * NT;                       // real columns of D
-    constexpr int A_LOADS = G4_BM * G4_KC / G4_THREADS;      // 8 B copies per thread and chunk
-    constexpr int B_LOADS = NT * G4_KC / G4_THREADS;
-    constexpr int A_ITEMS = G4_BM * G4_KG / G4_THREADS;      // (row, k-pair) items per thread
-    constexpr int B_ITEMS = NT * G4_KG / G4_THREADS;
+    constexpr int NP = 2 * NT;                               // real columns of D
+    constexpr int A_ITEMS = G4_BM * G4_KG / G4_CONV;         // (row, k-pair) items per thread
+    constexpr int B_ITEMS = NT * G4_KG / G4_CONV;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long tile = blockIdx.x;
@@ -168,10 +167,10 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
         sm.col_b[t] = ob; sm.col_c[t] = oc;
     }
     const int nchunks = (int)((K + G4_KC - 1) / G4_KC);
-    // reduction offsets of one chunk (32-bit mixed-radix decode; K < 2^31), done by
-    // 16 lanes of warp 4 -- warp 0 carries the MMA issue
-    auto decode_k = [&](int chunk) {
-        const int t = tid - 4 * 32;
+    // reduction offsets of one chunk (32-bit mixed-radix decode; K < 2^31) by 16
+    // lanes of converter warp `w`
+    auto decode_k = [&](int chunk, int w) {
+        const int t = tid - w * 32;
         if (t >= 0 && t < G4_KC && chunk < nchunks) {
             unsigned k = (unsigned)chunk * G4_KC + (unsigned)t;
             if ((long long)k >= K) k = 0;
@@ -187,9 +186,9 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
             sm.k_b[chunk & 3][t] = ob;
         }
     };
-    decode_k(0);
-    decode_k(1);
-    decode_k(2);
+    decode_k(0, 4);
+    decode_k(1, 5);
+    decode_k(2, 6);
     __syncwarp();
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
@@ -197,7 +196,10 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     if (tid == 32) {
-        for (int s = 0; s < G4_STAGES; ++s) g4_mbar_init(&sm.bar[s], 1);
+        for (int s = 0; s < G4_STAGES; ++s) {
+            g4_mbar_init(&sm.full[s], G4_CONV);              // every converter thread arrives
+            g4_mbar_init(&sm.empty[s], 1);                   // one tcgen05.commit
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -208,155 +210,54 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 2NT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) |
                                ((uint32_t)(G4_BM >> 4) << 24);
-
-    // Two-level accumulation.  The tensor core truncates its FP32 accumulator on
-    // every add (measured: relative error grows ~4e-8 per accumulation), so the
-    // TMEM accumulator only ever sums one SEGMENT of G4_SEG chunks (48 MMAs); the
-    // segments are added in FP32 registers (round-to-nearest).  Two TMEM sets
-    // alternate: segment s+1 accumulates while segment s is drained.
-    const int q = warp & 3, half = warp >> 2;               // TMEM lane quarter, column half
-    constexpr int COLS_PER_WARP = NP / 2;
-    float acc[COLS_PER_WARP];
-    #pragma unroll
-    for (int j = 0; j < COLS_PER_WARP; ++j) acc[j] = 0.f;
-    int next_drain = 0;                                     // first segment not yet drained
-
-    // raw layouts: K contiguous in the operand -> [row][k] (pitch 17), else [k][row];
-    // either way the copies are coalesced in global memory and conflict-free here
-    const int a_pr = a_kfast ? G4_RPITCH : 1, a_pk = a_kfast ? 1 : G4_BM;
-    const int b_pr = b_kfast ? G4_RPITCH : 1, b_pk = b_kfast ? 1 : NT;
-    // copy p of this thread moves element (row r0 + p * rstep, k index k0 + p * kstep)
-    const int a_r0 = a_kfast ? tid / G4_KC : tid % G4_BM, a_rstep = a_kfast ? G4_THREADS / G4_KC : 0;
-    const int a_k0 = a_kfast ? tid % G4_KC : tid / G4_BM, a_kstep = a_kfast ? 0 : G4_THREADS / G4_BM;
-    const int b_r0 = b_kfast ? tid / G4_KC : tid % NT, b_rstep = b_kfast ? G4_THREADS / G4_KC : 0;
-    const int b_k0 = b_kfast ? tid % G4_KC : tid / NT, b_kstep = b_kfast ? 0 : G4_THREADS / NT;
-    const int mrem = (int)(M - m0 < G4_BM ? M - m0 : G4_BM), nrem = (int)(N - n0 < NT ? N - n0 : NT);
-    const uint32_t raw_a0 = g4_smem_u32(&sm.raw_a[0][0]) + 8u * (uint32_t)(a_r0 * a_pr + a_k0 * a_pk);
-    const uint32_t raw_b0 = g4_smem_u32(&sm.raw_b[0][0]) + 8u * (uint32_t)(b_r0 * b_pr + b_k0 * b_pk);
-    const uint32_t a_dstep = 8u * (uint32_t)(a_rstep * a_pr + a_kstep * a_pk);
-    const uint32_t b_dstep = 8u * (uint32_t)(b_rstep * b_pr + b_kstep * b_pk);
-    constexpr uint32_t RAW_A_STAGE = G4_BM * G4_RPITCH * 8, RAW_B_STAGE = NT * G4_RPITCH * 8;
-    // asynchronous gather of chunk c through the per-mode strides
-    auto issue = [&](int c) {
-        if (c < nchunks) {
-            const int kt = c & 3, rs = c % G4_RAW;
-            const long long kleft = K - (long long)c * G4_KC;
-            const int krem = (int)(kleft < G4_KC ? kleft : G4_KC);
-            #pragma unroll
-            for (int p = 0; p < A_LOADS; ++p) {
-                const int r = a_r0 + p * a_rstep, k = a_k0 + p * a_kstep;
-                const int bytes = (r < mrem && k < krem) ? 8 : 0;
-                const float2* src = A + (sm.row_a[r] + sm.k_a[kt][k]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                 raw_a0 + (uint32_t)rs * RAW_A_STAGE + (uint32_t)p * a_dstep),
-                             "l"(src), "r"(bytes));
-            }
-            #pragma unroll
-            for (int p = 0; p < B_LOADS; ++p) {
-                const int n = b_r0 + p * b_rstep, k = b_k0 + p * b_kstep;
-                const int bytes = (n < nrem && k < krem) ? 8 : 0;
-                const float2* src = B + (sm.col_b[n] + sm.k_b[kt][k]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                 raw_b0 + (uint32_t)rs * RAW_B_STAGE + (uint32_t)p * b_dstep),
-                             "l"(src), "r"(bytes));
-            }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    issue(0);
-    issue(1);
-    // shared-memory matrix descriptors of stage 0 (hi tiles); lo tiles, later stages
-    // and k-steps are constant offsets of the 14-bit (address >> 4) field
     constexpr uint32_t a_lbo = G4_ROWS_A * 16, b_lbo = g4_smem<NT>::ROWS_B * 16, sbo = 128;
     constexpr uint32_t A_HALF_BYTES = G4_KG * G4_ROWS_A * 16, A_STAGE_BYTES = 2 * A_HALF_BYTES;
     constexpr uint32_t B_HALF_BYTES = G4_KG * g4_smem<NT>::ROWS_B * 16, B_STAGE_BYTES = 2 * B_HALF_BYTES;
-    const uint64_t desc_a_hi = g4_desc(g4_smem_u32(&sm.a[0][0][0][0]), a_lbo, sbo);
-    const uint64_t desc_b_hi = g4_desc(g4_smem_u32(&sm.b[0][0][0][0]), b_lbo, sbo);
 
-    #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-        const int st = c % G4_STAGES, rs = c % G4_RAW;
-        issue(c + 2);                         // raw slot of chunk c - 1: consumed before the last barrier
-        decode_k(c + 3);
-        asm volatile("cp.async.wait_group 2;\n" ::: "memory");
-        __syncthreads();                      // chunk c has landed for every thread
-        // the UMMA stage is free once the MMAs of chunk c - 2 have completed; if
-        // that chunk closed a segment, its TMEM set is complete: drain it
-        if (c >= G4_STAGES) {
-            g4_mbar_wait(&sm.bar[st], (uint32_t)((c / G4_STAGES - 1) & 1));
-            if ((c - G4_STAGES) % G4_SEG == G4_SEG - 1) {
+    if (warp == G4_CONV / 32) {
+        // =================== MMA warp: one thread issues ===================
+        if (lane == 0) {
+            // descriptors of stage 0 (hi tiles); lo tiles, the other stage and the
+            // k-steps are constant offsets of the 14-bit (address >> 4) field
+            const uint64_t desc_a_hi = g4_desc(g4_smem_u32(&sm.a[0][0][0][0]), a_lbo, sbo);
+            const uint64_t desc_b_hi = g4_desc(g4_smem_u32(&sm.b[0][0][0][0]), b_lbo, sbo);
+            #pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % G4_STAGES;
+                g4_mbar_wait(&sm.full[st], (uint32_t)((c / G4_STAGES) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t base = tmem_d + (uint32_t)((next_drain & 1) * NP) +
-                                      ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP);
+                const uint32_t d = tmem_d + (uint32_t)(((c / G4_SEG) & 1) * NP);
+                const bool first = (c % G4_SEG) == 0;
+                const uint64_t sa = (uint64_t)((uint32_t)st * (A_STAGE_BYTES >> 4));
+                const uint64_t sb = (uint64_t)((uint32_t)st * (B_STAGE_BYTES >> 4));
                 #pragma unroll
-                for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
-                    uint32_t v[16];
-                    g4_ld16(base + (uint32_t)c0, v);
-                    #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+                for (int ks = 0; ks < G4_KG / 2; ++ks) {      // UMMA K = 8 tf32 = 2 k-groups
+                    const uint64_t dah = desc_a_hi + sa + (uint64_t)(ks * 2 * a_lbo >> 4);
+                    const uint64_t dal = dah + (A_HALF_BYTES >> 4);
+                    const uint64_t dbh = desc_b_hi + sb + (uint64_t)(ks * 2 * b_lbo >> 4);
+                    const uint64_t dbl = dbh + (B_HALF_BYTES >> 4);
+                    g4_mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+                    g4_mma_tf32(d, dah, dbl, idesc, 1u);
+                    g4_mma_tf32(d, dal, dbh, idesc, 1u);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                ++next_drain;
+                g4_commit(&sm.empty[st]);     // frees the stage; also "chunk c is in TMEM"
             }
         }
-        // ---- split hi/lo and store in the UMMA K-major layout (lanes = rows)
+    } else {
+        // =================== converter warps (256 threads) ===================
+        // Two-level accumulation.  The tensor core truncates its FP32 accumulator
+        // on every add (measured: relative error grows ~4e-8 per accumulation), so
+        // the TMEM accumulator only ever sums one SEGMENT of G4_SEG chunks (48
+        // MMAs); the segments are added in FP32 registers (round-to-nearest).  Two
+        // TMEM sets alternate: segment s+1 accumulates while segment s is drained.
+        const int q = warp & 3, half = warp >> 2;           // TMEM lane quarter, column half
+        constexpr int COLS_PER_WARP = NP / 2;
+        float acc[COLS_PER_WARP];
         #pragma unroll
-        for (int p = 0; p < A_ITEMS; ++p) {
-            const int e = tid + p * G4_THREADS;
-            const int r = e % G4_BM, kp = e / G4_BM;
-            const float2 v0 = sm.raw_a[rs][r * a_pr + (2 * kp) * a_pk];
-            const float2 v1 = sm.raw_a[rs][r * a_pr + (2 * kp + 1) * a_pk];
-            const float4 x = make_float4(v0.x, v0.y, v1.x, v1.y);
-            const float4 h = make_float4(g4_hi(x.x), g4_hi(x.y), g4_hi(x.z), g4_hi(x.w));
-            sm.a[st][0][kp][r] = h;
-            sm.a[st][1][kp][r] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-        }
-        #pragma unroll
-        for (int p = 0; p < B_ITEMS; ++p) {
-            const int e = tid + p * G4_THREADS;
-            const int n = e % NT, kp = e / NT;
-            const float2 v0 = sm.raw_b[rs][n * b_pr + (2 * kp) * b_pk];
-            const float2 v1 = sm.raw_b[rs][n * b_pr + (2 * kp + 1) * b_pk];
-            const float4 xr = make_float4(v0.x, -v0.y, v1.x, -v1.y);      // row of C_re
-            const float4 xi = make_float4(v0.y, v0.x, v1.y, v1.x);        // row of C_im
-            const float4 hr = make_float4(g4_hi(xr.x), g4_hi(xr.y), g4_hi(xr.z), g4_hi(xr.w));
-            const float4 hi = make_float4(g4_hi(xi.x), g4_hi(xi.y), g4_hi(xi.z), g4_hi(xi.w));
-            sm.b[st][0][kp][2 * n] = hr;
-            sm.b[st][0][kp][2 * n + 1] = hi;
-            sm.b[st][1][kp][2 * n] = make_float4(xr.x - hr.x, xr.y - hr.y, xr.z - hr.z, xr.w - hr.w);
-            sm.b[st][1][kp][2 * n + 1] = make_float4(xi.x - hi.x, xi.y - hi.y, xi.z - hi.z, xi.w - hi.w);
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
+        for (int j = 0; j < COLS_PER_WARP; ++j) acc[j] = 0.f;
+        int next_drain = 0;                                 // first segment not yet drained
+        auto drain = [&]() {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const int seg = c / G4_SEG;
-            const uint32_t d = tmem_d + (uint32_t)((seg & 1) * NP);
-            const bool first = (c % G4_SEG) == 0;
-            const uint64_t sa = (uint64_t)((uint32_t)st * (A_STAGE_BYTES >> 4));
-            const uint64_t sb = (uint64_t)((uint32_t)st * (B_STAGE_BYTES >> 4));
-            #pragma unroll
-            for (int ks = 0; ks < G4_KG / 2; ++ks) {          // UMMA K = 8 tf32 = 2 k-groups
-                const uint64_t dah = desc_a_hi + sa + (uint64_t)(ks * 2 * a_lbo >> 4);
-                const uint64_t dal = dah + (A_HALF_BYTES >> 4);
-                const uint64_t dbh = desc_b_hi + sb + (uint64_t)(ks * 2 * b_lbo >> 4);
-                const uint64_t dbl = dbh + (B_HALF_BYTES >> 4);
-                g4_mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
-                g4_mma_tf32(d, dah, dbl, idesc, 1u);
-                g4_mma_tf32(d, dal, dbh, idesc, 1u);
-            }
-            g4_commit(&sm.bar[st]);
-        }
-    }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    // ---- all MMAs done (a commit tracks every earlier MMA of the issuing thread):
-    //      drain the segments still in TMEM (at most two)
-    {
-        const int last = nchunks - 1;
-        g4_mbar_wait(&sm.bar[last % G4_STAGES], (uint32_t)((last / G4_STAGES) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int nseg = (nchunks + G4_SEG - 1) / G4_SEG;
-        for (; next_drain < nseg; ++next_drain) {
             const uint32_t base = tmem_d + (uint32_t)((next_drain & 1) * NP) +
                                   ((uint32_t)(q * 32) << 16) + (uint32_t)(half * COLS_PER_WARP);
             #pragma unroll
@@ -366,25 +267,128 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            ++next_drain;
+        };
+
+        // Work items (row, k-pair) of this thread, the same for every chunk.  Each
+        // thread converts exactly the elements it copied itself, so the copies need
+        // no block-wide barrier: K contiguous in the operand -> 8 lanes cover the 8
+        // k-pairs of a row (128 B contiguous), else lanes = consecutive rows.
+        const int a_r0 = a_kfast ? tid / G4_KG : tid % G4_BM, a_rstep = a_kfast ? G4_CONV / G4_KG : 0;
+        const int a_p0 = a_kfast ? tid % G4_KG : (tid / G4_BM) * A_ITEMS, a_pstep = a_kfast ? 0 : 1;
+        const int b_r0 = b_kfast ? tid / G4_KG : tid % NT, b_rstep = b_kfast ? G4_CONV / G4_KG : 0;
+        const int b_p0 = b_kfast ? tid % G4_KG : (tid / NT) * B_ITEMS, b_pstep = b_kfast ? 0 : 1;
+        const int mrem = (int)(M - m0 < G4_BM ? M - m0 : G4_BM), nrem = (int)(N - n0 < NT ? N - n0 : NT);
+        const uint32_t raw0 = g4_smem_u32(&sm.raw[0][0][tid]);
+        constexpr uint32_t RAW_SLOT = G4_CONV * 8, RAW_STAGE = g4_smem<NT>::LOADS * RAW_SLOT;
+
+        // asynchronous gather of chunk c through the per-mode strides
+        auto issue = [&](int c) {
+            if (c < nchunks) {
+                const int kt = c & 3;
+                const uint32_t dst = raw0 + (uint32_t)(c % G4_RAW) * RAW_STAGE;
+                const long long kleft = K - (long long)c * G4_KC;
+                const int krem = (int)(kleft < G4_KC ? kleft : G4_KC);
+                #pragma unroll
+                for (int p = 0; p < A_ITEMS; ++p) {
+                    const int r = a_r0 + p * a_rstep, kp = a_p0 + p * a_pstep;
+                    const long long ro = sm.row_a[r];
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int bytes = (r < mrem && 2 * kp + h < krem) ? 8 : 0;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                         dst + (uint32_t)(2 * p + h) * RAW_SLOT),
+                                     "l"(A + (ro + sm.k_a[kt][2 * kp + h])), "r"(bytes));
+                    }
+                }
+                #pragma unroll
+                for (int p = 0; p < B_ITEMS; ++p) {
+                    const int n = b_r0 + p * b_rstep, kp = b_p0 + p * b_pstep;
+                    const long long co = sm.col_b[n];
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int bytes = (n < nrem && 2 * kp + h < krem) ? 8 : 0;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                         dst + (uint32_t)(2 * A_ITEMS + 2 * p + h) * RAW_SLOT),
+                                     "l"(B + (co + sm.k_b[kt][2 * kp + h])), "r"(bytes));
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+        issue(0);
+        issue(1);
+
+        #pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+            const int st = c % G4_STAGES, rs = c % G4_RAW;
+            issue(c + 2);
+            asm volatile("cp.async.wait_group 2;\n" ::: "memory");     // own copies of chunk c landed
+            // the UMMA stage is free once the MMAs of chunk c - 2 have completed; if
+            // that chunk closed a segment, its TMEM set is complete: drain it
+            if (c >= G4_STAGES) {
+                g4_mbar_wait(&sm.empty[st], (uint32_t)((c / G4_STAGES - 1) & 1));
+                if ((c - G4_STAGES) % G4_SEG == G4_SEG - 1) drain();
+            }
+            // ---- split hi/lo and store in the UMMA K-major layout
+            #pragma unroll
+            for (int p = 0; p < A_ITEMS; ++p) {
+                const int r = a_r0 + p * a_rstep, kp = a_p0 + p * a_pstep;
+                const float2 v0 = sm.raw[rs][2 * p][tid], v1 = sm.raw[rs][2 * p + 1][tid];
+                const float4 x = make_float4(v0.x, v0.y, v1.x, v1.y);
+                const float4 h = make_float4(g4_hi(x.x), g4_hi(x.y), g4_hi(x.z), g4_hi(x.w));
+                sm.a[st][0][kp][r] = h;
+                sm.a[st][1][kp][r] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+            #pragma unroll
+            for (int p = 0; p < B_ITEMS; ++p) {
+                const int n = b_r0 + p * b_rstep, kp = b_p0 + p * b_pstep;
+                const float2 v0 = sm.raw[rs][2 * A_ITEMS + 2 * p][tid];
+                const float2 v1 = sm.raw[rs][2 * A_ITEMS + 2 * p + 1][tid];
+                const float4 xr = make_float4(v0.x, -v0.y, v1.x, -v1.y);      // row of C_re
+                const float4 xi = make_float4(v0.y, v0.x, v1.y, v1.x);        // row of C_im
+                const float4 hr = make_float4(g4_hi(xr.x), g4_hi(xr.y), g4_hi(xr.z), g4_hi(xr.w));
+                const float4 hi = make_float4(g4_hi(xi.x), g4_hi(xi.y), g4_hi(xi.z), g4_hi(xi.w));
+                sm.b[st][0][kp][2 * n] = hr;
+                sm.b[st][0][kp][2 * n + 1] = hi;
+                sm.b[st][1][kp][2 * n] = make_float4(xr.x - hr.x, xr.y - hr.y, xr.z - hr.z, xr.w - hr.w);
+                sm.b[st][1][kp][2 * n + 1] = make_float4(xi.x - hi.x, xi.y - hi.y, xi.z - hi.z, xi.w - hi.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(g4_smem_u32(&sm.full[st]))
+                         : "memory");
+            // reduction offsets of chunk c + 3, visible to everyone after the barrier
+            // (converter warps only; the MMA warp never touches the tables)
+            decode_k(c + 3, c & 7);
+            asm volatile("bar.sync 1, %0;\n" ::"n"(G4_CONV) : "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    }
-    // ---- epilogue: thread = row q*32 + lane, columns = (re, im) pairs of its half
-    {
-        const int row = q * 32 + lane;
-        const bool okm = m0 + row < M;
-        float2* crow = Cout + sm.row_c[row];
-        #pragma unroll
-        for (int j = 0; j < COLS_PER_WARP / 2; ++j) {
-            const int n = half * (COLS_PER_WARP / 2) + j;
-            if (okm && n0 + n < N) {
-                const float re = acc[2 * j], im = acc[2 * j + 1];
-                float2 r;
-                r.x = alpha_re * re - alpha_im * im;
-                r.y = alpha_re * im + alpha_im * re;
-                float2* dst = crow + sm.col_c[n];
-                if (accumulate) { const float2 o = *dst; r.x += o.x; r.y += o.y; }
-                *dst = r;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        // ---- all MMAs done (a commit tracks every earlier MMA of the issuing
+        //      thread): drain the segments still in TMEM (at most two)
+        {
+            const int last = nchunks - 1;
+            g4_mbar_wait(&sm.empty[last % G4_STAGES], (uint32_t)((last / G4_STAGES) & 1));
+            const int nseg = (nchunks + G4_SEG - 1) / G4_SEG;
+            while (next_drain < nseg) drain();
+        }
+        // ---- epilogue: thread = row q*32 + lane, columns = (re, im) pairs of its half
+        {
+            const int row = q * 32 + lane;
+            const bool okm = m0 + row < M;
+            float2* crow = Cout + sm.row_c[row];
+            #pragma unroll
+            for (int j = 0; j < COLS_PER_WARP / 2; ++j) {
+                const int n = half * (COLS_PER_WARP / 2) + j;
+                if (okm && n0 + n < N) {
+                    const float re = acc[2 * j], im = acc[2 * j + 1];
+                    float2 r;
+                    r.x = alpha_re * re - alpha_im * im;
+                    r.y = alpha_re * im + alpha_im * re;
+                    float2* dst = crow + sm.col_c[n];
+                    if (accumulate) { const float2 o = *dst; r.x += o.x; r.y += o.y; }
+                    *dst = r;
+                }
             }
         }
     }
