@@ -217,6 +217,35 @@ def _torch():
     return torch
 
 
+_BATCH_JOB = None        # (backend, make) inherited by the fork pool of compile_batch
+_BATCH_KEY = None        # structure key of make(0)
+
+
+class _NeedsDevice(Exception):
+    pass
+
+
+def _compile_job(j: int):
+    """Runs in a forked worker: pure host work, no CUDA."""
+    backend, make = _BATCH_JOB
+
+    def cached_only(net):
+        key = (net.structure_key(), complex(net.scalar),
+               tuple(l.params.tobytes() for l in net.leaves if l.params is not None))
+        hit = backend.__dict__.get("_nested_cache", {}).get(key)
+        if hit is None:
+            raise _NeedsDevice()
+        return hit
+    try:
+        net = backend._get_network(make(j), nested_eval=cached_only)
+    except _NeedsDevice:
+        return j, None
+    # same structure as make(0) (checked): only the values travel back
+    if net.structure_key() != _BATCH_KEY:
+        return j, net
+    return j, ([l.params for l in net.leaves if l.params is not None], net.scalar)
+
+
 def _np_dtype(dev):
     return np.complex64 if dev.dtype == _torch().complex64 else np.complex128
 
@@ -270,13 +299,57 @@ class B200Backend(AbstractBackend):
             cache[key] = executor.evaluate(net, dtype=np.complex128).cpu().numpy()
         return cache[key]
 
-    def eval_batch(self, diagrams) -> list:
+    def compile_batch(self, make, count: int, workers: Optional[int] = None):
+        """Host compile (CP doubling + light-cone dims + leaf descriptors) of the
+        ``count`` structurally identical diagrams ``make(j)`` on a fork pool: the
+        per-diagram Python work (channel.py:600-641, diagram.py:301-375,
+        utils.py:436-510 in the reference) is the whole cost of a batched eval once
+        the kernels run.  Workers never touch the device:
+        nested contractions (``BitControlledBox``) must hit the cache the parent
+        warmed on ``make(0)``; a diagram that misses is compiled serially here.
+        Returns ``(networks, first_diagram)``."""
+        import multiprocessing as mp
+        import os
+        first = make(0)
+        net0 = self._get_network(first, nested_eval=self._nested_eval)
+        if workers is None:
+            workers = min(32, os.cpu_count() or 1, max(1, count // 16))
+        nets = [net0] + [None] * (count - 1)
+        if workers > 1 and count > 1:
+            global _BATCH_JOB, _BATCH_KEY
+            _BATCH_JOB, _BATCH_KEY = (self, make), net0.structure_key()
+            import dataclasses
+            try:
+                with mp.get_context("fork").Pool(workers) as pool:
+                    chunk = max(1, (count - 1) // (workers * 4))
+                    for j, res in pool.imap_unordered(_compile_job, range(1, count), chunksize=chunk):
+                        if isinstance(res, tuple):       # (params of the value leaves, scalar)
+                            it = iter(res[0])
+                            leaves = [l if l.params is None else dataclasses.replace(l, params=next(it))
+                                      for l in net0.leaves]
+                            res = dataclasses.replace(net0, leaves=leaves, scalar=res[1])
+                        nets[j] = res
+            finally:
+                _BATCH_JOB = _BATCH_KEY = None
+        for j in range(1, count):
+            if nets[j] is None:
+                nets[j] = self._get_network(make(j), nested_eval=self._nested_eval)
+        return nets, first
+
+    def eval_batch(self, diagrams=None, make=None, count: Optional[int] = None,
+                   workers: Optional[int] = None) -> list:
         """Evaluate structurally identical diagrams (same boxes and wiring,
         different parameters) as ONE batched plan: one leaf-arena build and one
-        launch per contraction step for the whole batch."""
+        launch per contraction step for the whole batch.
+        Either a list of ``diagrams``, or a factory ``make(j)`` with ``count``:
+        the latter also spreads the host compile over ``workers`` processes."""
         from .. import executor
-        diagrams = list(diagrams)
-        nets = [self._get_network(d, nested_eval=self._nested_eval) for d in diagrams]
+        if diagrams is not None:
+            diagrams = list(diagrams)
+            nets = [self._get_network(d, nested_eval=self._nested_eval) for d in diagrams]
+        else:
+            nets, first = self.compile_batch(make, count, workers)
+            diagrams = [first] * len(nets)           # same structure: same cod / purity
         key0 = nets[0].structure_key()
         for net in nets[1:]:
             if net.structure_key() != key0:

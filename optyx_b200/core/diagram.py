@@ -103,6 +103,10 @@ bit = Bit(1)
 mode = Mode(1)
 
 
+_SWAP_CACHE: dict = {}
+_PERM_CACHE: dict = {}
+
+
 class Diagram:
     """A list of ``(box, offset)`` layers between ``dom`` and ``cod``."""
 
@@ -210,7 +214,20 @@ class Diagram:
     # ---- symmetric / frobenius structure -------------------------------------
     @classmethod
     def swap(cls, left: Ty, right: Ty) -> "Diagram":
-        """Block swap ``left @ right -> right @ left`` out of adjacent ``Swap``s."""
+        """Block swap ``left @ right -> right @ left`` out of adjacent ``Swap``s.
+        Memoised: diagrams are immutable values and CP doubling / inflation ask for
+        the same few swaps thousands of times per compile."""
+        key = (cls, type(left), left.inside, right.inside)
+        hit = _SWAP_CACHE.get(key)
+        if hit is not None:
+            return hit
+        res = cls._swap_uncached(left, right)
+        if len(_SWAP_CACHE) < 4096:
+            _SWAP_CACHE[key] = res
+        return res
+
+    @classmethod
+    def _swap_uncached(cls, left: Ty, right: Ty) -> "Diagram":
         mk = type(left)._make
         res = cls.id(left @ right)
         wires = list(left.inside) + list(right.inside)
@@ -229,6 +246,17 @@ class Diagram:
         """``cod[j] = dom[xs[j]]`` (DisCoPy's ``symmetric.Diagram.permutation``,
         used at channel.py:623-625, 635-637 and utils.py:77-78)."""
         xs = list(xs)
+        key = (cls, type(dom), tuple(xs), dom.inside)
+        hit = _PERM_CACHE.get(key)
+        if hit is not None:
+            return hit
+        res = cls._permutation_uncached(xs, dom)
+        if len(_PERM_CACHE) < 4096:
+            _PERM_CACHE[key] = res
+        return res
+
+    @classmethod
+    def _permutation_uncached(cls, xs, dom: Ty) -> "Diagram":
         assert sorted(xs) == list(range(len(dom))), "not a permutation"
         if len(dom) <= 1:
             return cls.id(dom)

@@ -87,13 +87,18 @@ def batched(name, make, batch=1024, reps=10):
     t_leaf = timed(sess.build_leaves, reps)
     t0 = time.perf_counter()
     res = backend.eval_batch(ds)
+    t_e2e_serial = time.perf_counter() - t0
+    backend.eval_batch(make=make, count=batch)               # warm (plan cache, pinned buffers)
+    t0 = time.perf_counter()
+    res = backend.eval_batch(make=make, count=batch)         # host compile on a fork pool
     t_e2e = time.perf_counter() - t0
     out[name] = {"batch": batch, "leaves": len(nets[0].leaves), "steps": len(plan.steps),
                  "device_ms_per_batch": dt * 1e3, "device_evals_per_s": batch / dt,
                  "leaf_build_ms": t_leaf * 1e3, "leaf_build_gbs": arena_bytes / t_leaf / 1e9,
                  "arena_bytes": arena_bytes, "plan_bytes": plan.total_bytes, "gbs": plan.total_bytes / dt / 1e9,
                  "host_compile_s": t_compile, "params_upload_ms": t_upload * 1e3,
-                 "e2e_evals_per_s": batch / t_e2e, "first": complex(res[0].tensor.array.reshape(-1)[0]).real}
+                 "e2e_evals_per_s": batch / t_e2e, "e2e_evals_per_s_serial_compile": batch / t_e2e_serial,
+                 "host_cores": os.cpu_count(), "first": complex(res[0].tensor.array.reshape(-1)[0]).real}
     print(name, out[name], flush=True)
 
 
