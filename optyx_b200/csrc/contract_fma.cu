@@ -124,16 +124,31 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
     const bool unit_alpha = (alpha_re == (T)1 && alpha_im == (T)0);
     const C zero = make_c<T>((T)0, (T)0);
 
-    for (long long t = t0; t < t1; ++t) {
-        if (t != t0) {
-            for (int m = 0; m < g.n_outer; ++m) {
-                oa += g.sa[m]; ob += g.sb[m]; oc += g.sc[m];
-                if (++cnt[m] < g.dim[m]) break;
-                oa -= (long long)g.dim[m] * g.sa[m];
-                ob -= (long long)g.dim[m] * g.sb[m];
-                oc -= (long long)g.dim[m] * g.sc[m];
-                cnt[m] = 0;
-            }
+    // R consecutive tiles are processed together (same work item, R tile offsets):
+    // with K = 1 or 2 one item is one or two 16 B loads per thread, far too little
+    // in flight to cover the HBM latency; R tiles at once give R times as much and
+    // amortise the per-item table look-ups.  Needs a tile-invariant B block.
+    constexpr int RMAX = KP <= 2 ? 4 : (KP == 4 ? 2 : 1);
+    const int R = g.b_static ? RMAX : 1;
+    auto advance = [&]() {
+        for (int m = 0; m < g.n_outer; ++m) {
+            oa += g.sa[m]; ob += g.sb[m]; oc += g.sc[m];
+            if (++cnt[m] < g.dim[m]) break;
+            oa -= (long long)g.dim[m] * g.sa[m];
+            ob -= (long long)g.dim[m] * g.sb[m];
+            oc -= (long long)g.dim[m] * g.sc[m];
+            cnt[m] = 0;
+        }
+    };
+    for (long long t = t0; t < t1; t += R) {
+        const int nt = (int)(t1 - t < R ? t1 - t : R);
+        long long oa_r[RMAX], oc_r[RMAX];
+        #pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            if (r < nt) {
+                if (t + r != t0) advance();
+                oa_r[r] = oa; oc_r[r] = oc;
+            } else { oa_r[r] = oa; oc_r[r] = oc; }
         }
         if (t == t0 || !g.b_static) {
             if (t != t0) __syncthreads();              // everyone done with the old Bs
@@ -144,32 +159,38 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             }
             __syncthreads();
         }
-        const C* __restrict__ At = A + oa;
-        C* __restrict__ Ct = Cout + oc;
         for (int w = tid; w < n_items; w += FM_THREADS) {
             const int jg = w / g.TM, i = w - jg * g.TM;       // lanes = consecutive rows
-            const C* ap = At + row_a[i];
-            C a[KP];
-            #pragma unroll
-            for (int k = 0; k < KP; ++k) a[k] = (k < g.K) ? ap[k_a[k]] : zero;
-            C* cp = Ct + pos_m[i];
+            const long long ra = row_a[i], pm = pos_m[i];
             const C* bp = Bs + row_bs[i];
+            C a[RMAX][KP];
+            #pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const C* ap = A + oa_r[r] + ra;
+                #pragma unroll
+                for (int k = 0; k < KP; ++k) a[r][k] = (r < nt && k < g.K) ? ap[k_a[k]] : zero;
+            }
             const int j0 = jg * FM_U;
             const int j1 = j0 + FM_U < g.TN ? j0 + FM_U : g.TN;
-            #pragma unroll 4
-            for (int j = j0; j < j1; ++j) {
-                C acc = zero;
-                #pragma unroll
-                for (int k = 0; k < KP; ++k) cfma(acc, a[k], bp[k * bplane + j]);
-                C res;
-                if (unit_alpha) res = acc;
-                else {
-                    res.x = alpha_re * acc.x - alpha_im * acc.y;
-                    res.y = alpha_re * acc.y + alpha_im * acc.x;
+            #pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r >= nt) break;
+                C* cp = Cout + oc_r[r] + pm;
+                #pragma unroll 4
+                for (int j = j0; j < j1; ++j) {
+                    C acc = zero;
+                    #pragma unroll
+                    for (int k = 0; k < KP; ++k) cfma(acc, a[r][k], bp[k * bplane + j]);
+                    C res;
+                    if (unit_alpha) res = acc;
+                    else {
+                        res.x = alpha_re * acc.x - alpha_im * acc.y;
+                        res.y = alpha_re * acc.y + alpha_im * acc.x;
+                    }
+                    C* dst = cp + pos_n[j];
+                    if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
+                    *dst = res;
                 }
-                C* dst = cp + pos_n[j];
-                if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
-                *dst = res;
             }
         }
     }
@@ -316,9 +337,6 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     const size_t smem = (size_t)(2 * d.TM + 2 * d.TN + ((d.TB + 1) & ~1) + 2 * KP) * 8 +
                         (size_t)KP * d.TB * d.TN * sizeof(C) + (size_t)d.TM * 4 + 16;
     if (smem > (size_t)FM_SMEM_MAX) { set_error("fma: tile tables need %zu B of shared memory", smem); return 1; }
-    long long blocks = n_tiles;
-    const long long cap = (long long)sms * 4;
-    if (blocks > cap) blocks = cap;
     const C* A = (const C*)a; const C* B = (const C*)b; C* Cc = (C*)c;
     // tables (<= 21 KB) + the B block (<= 32 KB) can exceed the 48 KB default
 #define B2_FMA_LAUNCH(KPV)                                                                   \
@@ -334,6 +352,16 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
             }                                                                                \
             attr_done = true;                                                                \
         }                                                                                    \
+        /* persistent grid = exactly one resident wave (every CTA gets an equal share   \
+           of the tiles; a partial second wave would idle most of the GPU) */           \
+        int occ = 0;                                                                         \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
+                &occ, contract_fma_kernel<T, KPV>, FM_THREADS, smem) != cudaSuccess ||       \
+            occ < 1)                                                                         \
+            occ = 1;                                                                         \
+        long long blocks = n_tiles;                                                          \
+        const long long cap = (long long)sms * occ;                                          \
+        if (blocks > cap) blocks = cap;                                                      \
         contract_fma_kernel<T, KPV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(              \
             d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate);                                 \
     } while (0)

@@ -448,6 +448,16 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
         red = [q for q in la.inds if q not in keep_set and q not in sl] + \
               [q for q in lb.inds if q not in keep_set and q not in sl and q not in sa_set]
 
+        # ---- kernel class (decides the output layout): tensor-core GEMM only for
+        # pairs that really are dense (see below), everything else is "thin"
+        Mx0, Nx0, Kx0 = _prod(dims, m_m), _prod(dims, n_m), _prod(dims, red)
+        Bx0 = _prod(dims, batch_m) * batch
+        size_abc = (_prod(dims, [q for q in la.inds if q not in sl]) +
+                    _prod(dims, [q for q in lb.inds if q not in sl]) + _prod(dims, keep)) * batch
+        ai0 = 8.0 * Bx0 * Mx0 * Nx0 * Kx0 / max(esize * size_abc, 1.0)
+        min_ai0 = gemm_threshold[3] if len(gemm_threshold) > 3 else 0.0
+        thin = not (Mx0 >= gemm_threshold[0] and Nx0 >= gemm_threshold[1]
+                    and Kx0 >= gemm_threshold[2] and ai0 >= min_ai0)
         # ---- output layout
         if final:
             assert set(keep) == set(out_unique), (keep, out_unique)
@@ -456,6 +466,13 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
             lc = Layout(c_inds, c_strides, OUT, 0, out_elems)
         else:
             c_inds = tuple(batch_m + m_m + n_m)
+            if thin:
+                # bandwidth-bound pair (big A x tiny B): C keeps A's own mode order
+                # (minus the reduced modes) so A streams in and C streams out in
+                # the same sequence, and the few new modes B brings are the
+                # SLOWEST ones -- one contiguous output stream per column instead
+                # of 16 B stores strided by N
+                c_inds = tuple(n_m + by_stride(la, batch_m + m_m))
             c_strides, s = [], 1
             for q in reversed(c_inds):
                 c_strides.append(s)

@@ -197,6 +197,35 @@ def test_eval_batch_one_plan_many_parameter_sets():
         assert _close(r.tensor.array, oracle_eval(fusion_teleport_input(p)), TOL128)
 
 
+def test_eval_batch_pooled_host_compile_matches_serial():
+    """eval_batch(make, count): host compile on a fork pool (workers never touch
+    the device; the BitControlledGate slab comes from the cache warmed on
+    make(0)) gives the same tensors as the serial path, bit for bit."""
+    from cases import fusion_teleport_input
+    backend = B200Backend()
+    make = lambda j: fusion_teleport_input(j / 16)          # noqa: E731
+    serial = backend.eval_batch([make(j) for j in range(16)])
+    pooled = backend.eval_batch(make=make, count=16, workers=4)
+    assert len(pooled) == 16
+    for a, b in zip(serial, pooled):
+        assert np.array_equal(a.tensor.array, b.tensor.array)
+        assert a.state_type == b.state_type
+
+
+def test_complex64_eval_uses_tensor_core_gemm_and_meets_tolerance():
+    """complex64 mode: dense pairs go to the tcgen05 split-precision GEMM; the
+    result matches the complex128 oracle within the north star's 1e-5."""
+    from cases import cfg1_interferometer
+    d = cfg1_interferometer(5, (1, 1, 1, 0, 0), depth=5)
+    backend = B200Backend(dtype="complex64")
+    res = d.eval(backend)
+    want = oracle_eval(d)
+    assert res.tensor.array.dtype == np.complex64
+    assert np.abs(res.tensor.array - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    kinds = {st.kernel for st in backend.last_plan.steps}
+    assert "gemm" in kinds, kinds
+
+
 def test_cfg3_standard_size_properties():
     """cfg3 at a size the oracle cannot reach quickly: 6 modes x inflate 2,
     2 partially distinguishable photons, loss, 3 measured modes.  Checked through

@@ -30,9 +30,22 @@ torch.cuda.synchronize()
 stream = torch.cuda.current_stream().cuda_stream
 vals = [0] * len(plan.sliced)
 rows = []
+prof = os.environ.get("B2_PROFILE_MNK")          # e.g. "2,16777216,1,1": ncu --profile-from-start off
+prof = tuple(int(x) for x in prof.split(",")) if prof else None
 for st in plan.steps:
     if not st.per_slice:
         continue
+    if prof is not None and tuple(st.mnk) == prof:
+        d = st.desc
+        n = d.n_out + d.n_red
+        print("profile step", st.mnk, "n_out", d.n_out, "n_red", d.n_red, "dims", list(d.dim[:n]),
+              "sa", list(d.sa[:n]), "sb", list(d.sb[:n]), "sc", list(d.sc[:n]), flush=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        sess._launch(st, vals, 1.0 + 0j, 0, stream)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        prof = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     sess._launch(st, vals, 1.0 + 0j, 0, stream)
