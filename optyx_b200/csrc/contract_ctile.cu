@@ -155,14 +155,14 @@ contract_ctile_c128_kernel(const __grid_constant__ ct_desc g, long long n_tiles,
     auto decode_k = [&](int chunk) {
         if (tid < CT_BK) {
             long long xa = 0, xb = 0;
-            long long k = (long long)chunk * CT_BK + tid;
-            if (k >= g.K) k = 0;
+            unsigned k = (unsigned)chunk * CT_BK + (unsigned)tid;     // K < 2^31: 32-bit divisions
+            if ((long long)k >= g.K) k = 0;
             for (int m = 0; m < g.n_k; ++m) {
-                const long long d = g.dim[f_k + m];
-                const long long q = k / d, x = k - q * d;
+                const unsigned d = (unsigned)g.dim[f_k + m];
+                const unsigned q = k / d, x = k - q * d;
                 k = q;
-                xa += x * g.sa[f_k + m];
-                xb += x * g.sb[f_k + m];
+                xa += (long long)x * g.sa[f_k + m];
+                xb += (long long)x * g.sb[f_k + m];
             }
             k_a[(chunk % S) * CT_BK + tid] = xa;
             k_b[(chunk % S) * CT_BK + tid] = xb;

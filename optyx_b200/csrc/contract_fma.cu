@@ -30,7 +30,7 @@ struct fm_desc {
     long long sa[B2_MAX_MODES], sb[B2_MAX_MODES], sc[B2_MAX_MODES];
 };
 
-template <typename T, int KP>
+template <typename T, int KP, int RMAX>
 __global__ void __launch_bounds__(FM_THREADS)
 contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                     const typename cplx<T>::type* __restrict__ A,
@@ -128,8 +128,8 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
     // with K = 1 or 2 one item is one or two 16 B loads per thread, far too little
     // in flight to cover the HBM latency; R tiles at once give R times as much and
     // amortise the per-item table look-ups.  Needs a tile-invariant B block.
-    constexpr int RMAX = KP <= 2 ? 4 : (KP == 4 ? 2 : 1);
-    const int R = g.b_static ? RMAX : 1;
+    // (RMAX > 1 is instantiated for narrow tiles only: TN <= 8 and a static B)
+    const int R = RMAX;
     auto advance = [&]() {
         for (int m = 0; m < g.n_outer; ++m) {
             oa += g.sa[m]; ob += g.sb[m]; oc += g.sc[m];
@@ -339,11 +339,11 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     if (smem > (size_t)FM_SMEM_MAX) { set_error("fma: tile tables need %zu B of shared memory", smem); return 1; }
     const C* A = (const C*)a; const C* B = (const C*)b; C* Cc = (C*)c;
     // tables (<= 21 KB) + the B block (<= 32 KB) can exceed the 48 KB default
-#define B2_FMA_LAUNCH(KPV)                                                                   \
+#define B2_FMA_LAUNCH_R(KPV, RV)                                                             \
     do {                                                                                     \
         static bool attr_done = false;                                                       \
         if (!attr_done) {                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV>,                \
+            cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV, RV>,            \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  FM_SMEM_MAX);                               \
             if (e != cudaSuccess) {                                                          \
@@ -356,22 +356,29 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
            of the tiles; a partial second wave would idle most of the GPU) */           \
         int occ = 0;                                                                         \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
-                &occ, contract_fma_kernel<T, KPV>, FM_THREADS, smem) != cudaSuccess ||       \
+                &occ, contract_fma_kernel<T, KPV, RV>, FM_THREADS, smem) != cudaSuccess ||   \
             occ < 1)                                                                         \
             occ = 1;                                                                         \
         long long blocks = n_tiles;                                                          \
         const long long cap = (long long)sms * occ;                                          \
         if (blocks > cap) blocks = cap;                                                      \
-        contract_fma_kernel<T, KPV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(              \
+        contract_fma_kernel<T, KPV, RV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(          \
             d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate);                                 \
     } while (0)
+    // several tiles in flight per thread only where one item is little work
+    const bool narrow = d.b_static && d.TN <= 8;
+#define B2_FMA_LAUNCH(KPV, RV)                                                               \
+    do {                                                                                     \
+        if (narrow) B2_FMA_LAUNCH_R(KPV, RV); else B2_FMA_LAUNCH_R(KPV, 1);                  \
+    } while (0)
     switch (KP) {
-    case 1: B2_FMA_LAUNCH(1); break;
-    case 2: B2_FMA_LAUNCH(2); break;
-    case 4: B2_FMA_LAUNCH(4); break;
-    case 8: B2_FMA_LAUNCH(8); break;
-    default: B2_FMA_LAUNCH(16); break;
+    case 1: B2_FMA_LAUNCH(1, 4); break;
+    case 2: B2_FMA_LAUNCH(2, 4); break;
+    case 4: B2_FMA_LAUNCH(4, 2); break;
+    case 8: B2_FMA_LAUNCH_R(8, 1); break;
+    default: B2_FMA_LAUNCH_R(16, 1); break;
     }
+#undef B2_FMA_LAUNCH_R
 #undef B2_FMA_LAUNCH
     return check_launch("b2_contract_direct(fma)");
 }

@@ -93,13 +93,24 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     }
     const int nchunks = (int)((K + BK - 1) / BK);
 
+    // reduction offsets of one chunk: 32-bit mixed-radix decode (K < 2^31) by the
+    // last warp, so the 64-bit divisions of a many-mode K never sit on the critical
+    // path of the warps that issue the copies first
     auto decode_k = [&](int chunk) {
-        if (tid < BK) {
-            long long oa, ob, oc;
-            const long long k = (long long)chunk * BK + tid;
-            decode3(k < K ? k : 0, g, f_k, g.n_k, oa, ob, oc);
-            sm.k_a[chunk % STAGES][tid] = oa;
-            sm.k_b[chunk % STAGES][tid] = ob;
+        const int t = tid - (GEMM_THREADS - 32);
+        if (t >= 0 && t < BK) {
+            unsigned k = (unsigned)chunk * BK + (unsigned)t;
+            if ((long long)k >= K) k = 0;
+            long long oa = 0, ob = 0;
+            for (int m = 0; m < g.n_k; ++m) {
+                const unsigned d = (unsigned)g.dim[f_k + m];
+                const unsigned q = k / d, i = k - q * d;
+                k = q;
+                oa += (long long)i * g.sa[f_k + m];
+                ob += (long long)i * g.sb[f_k + m];
+            }
+            sm.k_a[chunk % STAGES][t] = oa;
+            sm.k_b[chunk % STAGES][t] = ob;
         }
     };
     auto issue = [&](int chunk) {
@@ -215,12 +226,16 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         return 1;
     }
     if (num_sms() <= 0) return 1;
-    if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
-        return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
-                               (cudaStream_t)stream);
     long long k_total = 1, n_total = 1;
     for (int i = 0; i < g.n_k; ++i) k_total *= g.dim[g.n_batch + g.n_m + g.n_n + i];
     for (int i = 0; i < g.n_n; ++i) n_total *= g.dim[g.n_batch + g.n_m + i];
+    if (k_total >= (1ll << 31)) {
+        set_error("b2_contract_gemm: reduction extent %lld too large (slice the network)", k_total);
+        return 1;
+    }
+    if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
+        return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
+                               (cudaStream_t)stream);
     if (k_total <= 32 || n_total < 64) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
