@@ -147,9 +147,17 @@ class Session:
             rt.check(self.lib.b2_fill_zero(self.out.numel(), self.out.data_ptr(), self.code,
                                            stream), "b2_fill_zero")
         zeros = [0] * len(plan.sliced)
-        for st in plan.steps:
-            if not st.per_slice:
-                self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream)
+        n_inv = sum(1 for st in plan.steps if not st.per_slice)
+        if plan.sliced and n_inv > 32 and not self.torch.cuda.is_current_stream_capturing():
+            # the slice-invariant subtrees of a sliced circuit are thousands of tiny
+            # steps: one CUDA graph (captured on first use) instead of one launch each
+            if getattr(self, "inv_graph", None) is None:
+                self._capture_invariant()
+            self.inv_graph.replay()
+        else:
+            for st in plan.steps:
+                if not st.per_slice:
+                    self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream)
         if not plan.sliced:
             return
         for sid in range(s0, s1):
@@ -161,6 +169,30 @@ class Session:
                 if st.per_slice:
                     self._launch(st, vals, scalar if st.final else 1.0 + 0j,
                                  1 if st.final else 0, stream)
+
+    def _capture_invariant(self) -> None:
+        """CUDA graph of the slice-invariant steps (none of them is final: alpha = 1;
+        their buffers are private, ``planner._reallocate_for_slices``)."""
+        torch, plan = self.torch, self.plan
+        zeros = [0] * len(plan.sliced)
+
+        def body():
+            stream = torch.cuda.current_stream().cuda_stream
+            for st in plan.steps:
+                if not st.per_slice:
+                    self._launch(st, zeros, 1.0 + 0j, 0, stream)
+        launches = self.launches
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()                                   # warm-up outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            body()
+        self.launches = launches
+        self.inv_graph = graph
 
     def run(self, nets: Sequence[Network], scalar: Optional[complex] = None):
         """Full device path for a batch of structurally identical networks."""

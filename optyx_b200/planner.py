@@ -124,6 +124,11 @@ def greedy_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: froze
     return path
 
 
+# cost model of the path search: a step costs max(bytes / HBM, flops / FP64 pipe)
+# (complex128 on B200: 16 B per element, 6.5 TB/s, 37 TFLOP/s)
+_COST_BW, _COST_PIPE, _COST_ESIZE = 6.5e12, 37e12, 16.0
+
+
 @dataclass
 class PathInfo:
     path: List[Tuple[int, int]]
@@ -132,6 +137,7 @@ class PathInfo:
     peak: float                 # largest intermediate (elements) per slice
     nslices: int
     step_inds: List[frozenset] = field(default_factory=list)   # result inds per step
+    time_est: float = 0.0       # roofline estimate of the whole (sliced) contraction, s
 
 
 def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: frozenset,
@@ -147,6 +153,9 @@ def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: froz
     macs, peak = 0.0, 0.0
     step_inds = []
     nxt = len(inputs)
+    nslices = int(_prod(dims, sl)) if sl else 1
+    dep = {k: bool(s & sl) for k, s in tens.items()}      # depends on a sliced index
+    t_inv = t_dep = 0.0
     for a, b in path:
         sa, sb = tens.pop(a), tens.pop(b)
         union = sa | sb
@@ -157,19 +166,35 @@ def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: froz
             count[q] -= 1
         for q in new:
             count[q] += 1
-        macs += _prod(dims, [q for q in union if q not in sl])
-        peak = max(peak, _prod(dims, [q for q in new if q not in sl]))
+        m = _prod(dims, [q for q in union if q not in sl])
+        size_c = _prod(dims, [q for q in new if q not in sl])
+        nbytes = _COST_ESIZE * (_prod(dims, [q for q in sa if q not in sl]) +
+                                _prod(dims, [q for q in sb if q not in sl]) + size_c)
+        t = max(nbytes / _COST_BW, 8.0 * m / _COST_PIPE) + 2e-6      # + launch floor
+        d = dep.pop(a) | dep.pop(b)
+        dep[nxt] = d
+        if d:
+            t_dep += t
+        else:
+            t_inv += t
+        macs += m
+        peak = max(peak, size_c)
         tens[nxt] = new
         step_inds.append(new)
         nxt += 1
-    nslices = int(_prod(dims, sl)) if sl else 1
-    return PathInfo(list(path), tuple(sliced), macs, peak, nslices, step_inds)
+    return PathInfo(list(path), tuple(sliced), macs, peak, nslices, step_inds,
+                    t_inv + nslices * t_dep)
 
 
 def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
-              minimize: str = "flops") -> PathInfo:
-    """Best of a deterministic greedy plus ``trials-1`` noisy ones."""
-    best = None
+              minimize: str = "flops", target_size: Optional[float] = None,
+              slice_candidates: int = 4) -> PathInfo:
+    """Best of a deterministic greedy plus ``trials-1`` noisy ones.  With a
+    ``target_size`` the candidates are compared AFTER slicing, by the roofline
+    estimate of the whole sliced contraction (a tree that is cheapest unsliced can
+    be far from the cheapest once its widest tensors must be cut): the
+    ``slice_candidates`` cheapest trees are sliced and the best sliced one wins."""
+    cands = []
     rng = random.Random(seed)
     for t in range(max(1, trials)):
         if t == 0:
@@ -180,9 +205,16 @@ def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
                             costmod=rng.choice([0.5, 1.0, 1.0, 2.0]))
         info = analyse_path(inputs, dims, output, p)
         key = (info.macs, info.peak) if minimize == "flops" else (info.peak, info.macs)
-        if best is None or key < best[0]:
-            best = (key, info)
-    return best[1]
+        cands.append((key, t, info))
+    cands.sort(key=lambda c: (c[0], c[1]))
+    if target_size is None or cands[0][2].peak <= target_size:
+        return cands[0][2]
+    best = None
+    for _, _, info in cands[:max(1, slice_candidates)]:
+        sl = slice_path(inputs, dims, output, info, target_size) if info.peak > target_size else info
+        if best is None or sl.time_est < best.time_est:
+            best = sl
+    return best
 
 
 def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
@@ -615,9 +647,8 @@ def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int 
     inputs = [frozenset(l.inds) for l in net.leaves]
     output = frozenset(net.output_inds)
     if len(inputs) >= 2:
-        info = find_path(inputs, net.dims, output, trials=trials, seed=seed)
-        if target_size is not None and info.peak > target_size:
-            info = slice_path(inputs, net.dims, output, info, target_size)
+        info = find_path(inputs, net.dims, output, trials=trials, seed=seed,
+                         target_size=target_size)
     else:
         info = PathInfo([], (), 0.0, 0.0, 1, [])
     return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)
