@@ -166,9 +166,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # rank 0 must print exactly ONE line on stdout: libraries (NCCL's version
+    # banner, ...) write to the C-level fd 1, so fd 1 is pointed at stderr for the
+    # whole run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # rank 0 must print exactly ONE line: keep NCCL's version banner off stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("B2_NCCL_DEBUG", "WARN")
+        if "B2_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["B2_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = rt.load()
 
@@ -306,10 +314,14 @@ def main():
         out["sliced"] = run_sliced(world, rank)
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"], _ = cpu_reference(args.workload, 2, 0)
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    os.close(real_stdout)
 
 
 def run_sliced(world: int, rank: int):

@@ -179,8 +179,20 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                 #pragma unroll 4
                 for (int j = j0; j < j1; ++j) {
                     C acc = zero;
-                    #pragma unroll
-                    for (int k = 0; k < KP; ++k) cfma(acc, a[r][k], bp[k * bplane + j]);
+                    if constexpr (KP >= 4) {
+                        // two independent accumulation chains halve the dependent
+                        // FMA latency per output
+                        C acc2 = zero;
+                        #pragma unroll
+                        for (int k = 0; k < KP; k += 2) {
+                            cfma(acc, a[r][k], bp[k * bplane + j]);
+                            cfma(acc2, a[r][k + 1], bp[(k + 1) * bplane + j]);
+                        }
+                        acc.x += acc2.x; acc.y += acc2.y;
+                    } else {
+                        #pragma unroll
+                        for (int k = 0; k < KP; ++k) cfma(acc, a[r][k], bp[k * bplane + j]);
+                    }
                     C res;
                     if (unit_alpha) res = acc;
                     else {
