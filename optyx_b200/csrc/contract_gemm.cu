@@ -165,16 +165,20 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
             for (int r = 0; r < 4; ++r) af[r] = sm.a[st][k4 + fk][wm * 32 + r * 8 + frow];
             #pragma unroll
             for (int q = 0; q < 4; ++q) bf[q] = sm.b[st][k4 + fk][wn * 32 + q * 8 + frow];
+            // the asm statements are volatile (kept in source order): issue the 8
+            // independent accumulators of a row before coming back to any of them,
+            // so that a dependent DMMA is 8 instructions behind its producer
             #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const double nai = -af[r].y;
                 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    dmma884(cre[r][q][0], cre[r][q][1], af[r].x, bf[q].x);
-                    dmma884(cre[r][q][0], cre[r][q][1], nai, bf[q].y);
-                    dmma884(cim[r][q][0], cim[r][q][1], af[r].x, bf[q].y);
-                    dmma884(cim[r][q][0], cim[r][q][1], af[r].y, bf[q].x);
-                }
+                for (int q = 0; q < 4; ++q) dmma884(cre[r][q][0], cre[r][q][1], af[r].x, bf[q].x);
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) dmma884(cim[r][q][0], cim[r][q][1], af[r].x, bf[q].y);
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) dmma884(cre[r][q][0], cre[r][q][1], nai, bf[q].y);
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) dmma884(cim[r][q][0], cim[r][q][1], af[r].y, bf[q].x);
             }
         }
     }

@@ -53,3 +53,29 @@ def test_slices_partition_across_ranks():
         emulate_plan(net, plan, slice_range=(half, plan.nslices))[0]
     # invariant steps do not depend on the slice range; only the accumulated output adds
     assert np.allclose(part, want, rtol=1e-9, atol=1e-9)
+
+
+def test_path_candidates_are_compared_after_slicing():
+    """With a target size the search keeps the tree whose SLICED contraction has the
+    best roofline estimate, which is never worse than slicing the unsliced winner."""
+    import random as _random
+    from optyx_b200 import planner
+    rnd = _random.Random(5)
+    n_t, n_i = 40, 60
+    dims = {i: 2 for i in range(n_i)}
+    inputs = []
+    for _ in range(n_t):
+        inputs.append(frozenset(rnd.sample(range(n_i), 4)))
+    used = set().union(*inputs)
+    # close every index that appears once by giving it a partner tensor
+    count = {q: sum(q in s for s in inputs) for q in used}
+    inputs += [frozenset([q]) for q, c in count.items() if c == 1]
+    output = frozenset()
+    base = planner.find_path(inputs, dims, output, trials=12, seed=3)
+    target = max(4.0, base.peak / 16)
+    old_way = planner.slice_path(inputs, dims, output, base, target)
+    new_way = planner.find_path(inputs, dims, output, trials=12, seed=3, target_size=target,
+                                slice_candidates=6)
+    assert new_way.peak <= target + 1e-9
+    assert new_way.time_est <= old_way.time_est * (1 + 1e-12)
+    assert new_way.nslices >= 1 and new_way.time_est > 0

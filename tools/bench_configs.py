@@ -17,6 +17,7 @@ from optyx_b200 import executor  # noqa: E402
 from optyx_b200.core.backends import B200Backend  # noqa: E402
 
 out = {}
+results = {}
 backend = B200Backend()
 
 
@@ -32,13 +33,15 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) * 1e-3 / reps
 
 
-def single(name, factory, reps=50):
+def single(name, factory, reps=50, dtype=np.complex128, check_against=None):
+    global backend
+    backend = B200Backend(dtype=dtype)
     d = factory()
     t0 = time.perf_counter()
     net = backend._get_network(d, nested_eval=backend._nested_eval)
     t_compile = time.perf_counter() - t0
     t0 = time.perf_counter()
-    plan = executor.get_plan(net)
+    plan = executor.get_plan(net, dtype=dtype)
     t_plan = time.perf_counter() - t0
     sess = executor.Session(plan)
     sess.set_leaves([net])
@@ -62,7 +65,14 @@ def single(name, factory, reps=50):
                  "e2e_ms_per_eval": t_e2e * 1e3, "host_compile_ms": t_compile * 1e3,
                  "host_plan_ms": t_plan * 1e3, "prob_dist_ms": t_prob * 1e3,
                  "prob_total": float(sum(p.values())) if p else None,
-                 "tflops": 8 * plan.total_macs / dt / 1e12, "gbs": plan.total_bytes / dt / 1e9}
+                 "tflops": 8 * plan.total_macs / dt / 1e12, "gbs": plan.total_bytes / dt / 1e9,
+                 "dtype": np.dtype(dtype).name,
+                 "kernels": {k: sum(1 for st in plan.steps if st.kernel == k) for k in ("direct", "gemm")}}
+    results[name] = res.tensor.array
+    if check_against is not None:
+        ref = results[check_against]
+        out[name]["max_rel_err_vs_" + check_against] = float(
+            np.abs(res.tensor.array - ref).max() / max(1e-300, np.abs(ref).max()))
     print(name, out[name], flush=True)
 
 
@@ -105,7 +115,10 @@ def batched(name, make, batch=1024, reps=10):
 single("cfg1_hom_lossy", lambda: cases.lossy_hom(0.8))
 single("cfg1_6mode_3photon", lambda: cases.cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)))
 single("cfg3_6mode_3photon_k2", lambda: cases.cfg3_interferometer(width=6, n_photons=3, measured=2), reps=3)
+single("cfg3_6mode_3photon_k2_complex64", lambda: cases.cfg3_interferometer(width=6, n_photons=3, measured=2),
+       reps=3, dtype=np.complex64, check_against="cfg3_6mode_3photon_k2")
 single("cfg2_ghz20_measured", lambda: cases.ghz(20, noise=0.95, measure=True))
+backend = B200Backend()
 batched("cfg5a_fusion_link_x1024",
         lambda j: cases.fusion_link((math.cos(j * (math.pi / 2) / 1023), math.sin(j * (math.pi / 2) / 1023)), "bell"))
 batched("cfg5b_fusion_teleport_x1024", lambda j: cases.fusion_teleport_input(j / 1024))

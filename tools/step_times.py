@@ -37,8 +37,9 @@ for st in plan.steps:
         continue
     if prof is not None and tuple(st.mnk) == prof:
         d = st.desc
-        n = d.n_out + d.n_red
-        print("profile step", st.mnk, "n_out", d.n_out, "n_red", d.n_red, "dims", list(d.dim[:n]),
+        counts = (d.n_out, d.n_red) if st.kernel == "direct" else (d.n_batch, d.n_m, d.n_n, d.n_k)
+        n = sum(counts)
+        print("profile step", st.kernel, st.mnk, "mode counts", counts, "dims", list(d.dim[:n]),
               "sa", list(d.sa[:n]), "sb", list(d.sb[:n]), "sc", list(d.sc[:n]), flush=True)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
