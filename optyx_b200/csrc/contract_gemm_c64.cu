@@ -19,18 +19,25 @@
 // FP32).  a*b ~= ahi*bhi + ahi*blo + alo*bhi, accumulated in FP32 in tensor
 // memory: 3 tcgen05.mma.kind::tf32 per k-step, relative error ~2^-21.
 //
-// Data flow per CTA (tile 128 x NT complex, K chunk 16 complex = 32 real):
-//   all 8 warps : gather the chunk's A rows / B columns through the per-mode
-//                 strides (the index permutation; no transposes in HBM), split
-//                 hi/lo in registers, st.shared into the canonical K-major
-//                 no-swizzle UMMA layout [k-group][row][16 B], fence.proxy.async
-//   one thread  : 12 tcgen05.mma (4 k-steps x 3 split products) per chunk, D in
-//                 TMEM (128 lanes x 2NT fp32 columns, two sets), tcgen05.commit
-//                 -> mbarrier frees the stage; the next gather overlaps the MMAs
-//   all 8 warps : every 4 chunks the finished TMEM set is drained with
-//                 tcgen05.ld 32x32b (lane = row, columns = (re, im) pairs) into
-//                 FP32 register accumulators (two-level accumulation, see below)
-//   epilogue    : alpha scaling, scatter through the C permutation.
+// Data flow per CTA (tile 128 x NT complex, K chunk 16 complex = 32 real), warp
+// specialised, no block-wide barrier in the loop:
+//   8 converter warps : gather the chunk's A rows / B columns through the per-mode
+//                 strides (the index permutation; no transposes in HBM) with 8-byte
+//                 cp.async, 3 stages deep; split hi/lo in registers;
+//                 A -> TENSOR MEMORY with tcgen05.st.32x32b (lane = row, 16 columns
+//                 = the thread's 8 complex k values), B -> shared memory in the
+//                 canonical K-major no-swizzle UMMA layout [k-group][row][16 B];
+//                 fence, arrive on the stage's `full` mbarrier
+//   MMA warp    : one thread issues 12 tcgen05.mma.kind::tf32 per chunk (4 k-steps x
+//                 3 split products; A operand from TMEM, B from a shared-memory
+//                 descriptor), D in TMEM (128 lanes x 2NT fp32 columns, two sets),
+//                 tcgen05.commit -> the stage's `empty` mbarrier
+//   converters  : every 4 chunks the finished TMEM set is drained with
+//                 tcgen05.ld.32x32b into FP32 register accumulators (two-level
+//                 accumulation, see below); epilogue = alpha scaling + scatter
+//                 through the C permutation.
+// Tensor memory map (512 or 256 columns): [D set 0 | D set 1 | A hi/lo stage 0 | A
+// hi/lo stage 1].
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -73,6 +80,23 @@ __device__ __forceinline__ void g4_mma_tf32(uint32_t tmem_d, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (128 lanes x 8 columns of 32-bit), B from shared memory
+__device__ __forceinline__ void g4_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void g4_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+          "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+          "r"(v[14]), "r"(v[15]) : "memory");
+}
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor: 8 x 16 B core matrices,
 // `lbo` bytes between core matrices along K, `sbo` bytes along M/N.
 __device__ __forceinline__ uint64_t g4_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -113,18 +137,19 @@ __device__ __forceinline__ float g4_hi(float x) {
     return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
-// rows per k-group are padded by one 16 B slot (the descriptor's leading byte
-// offset is then 16 B off a multiple of 128 B)
-constexpr int G4_ROWS_A = G4_BM + 1;
+// B rows per k-group are padded by one 16 B slot (the descriptor's leading byte
+// offset is then 16 B off a multiple of 128 B: conflict-free tile stores)
 
 template <int NT>
 struct g4_smem {
     static constexpr int ROWS_B = 2 * NT + 1;
-    static constexpr int LOADS = (G4_BM + NT) * G4_KC / G4_CONV;     // 8 B copies per thread, chunk
-    // UMMA operand tiles: [stage][hi/lo][k-group][row][4 floats]
-    float4 a[G4_STAGES][2][G4_KG][G4_ROWS_A];
+    static constexpr int LOADS = NT * G4_KC / G4_CONV;               // 8 B copies of B per thread, chunk
+    // UMMA B operand tiles: [stage][hi/lo][k-group][row][4 floats]  (A lives in TMEM)
     float4 b[G4_STAGES][2][G4_KG][ROWS_B];
-    // cp.async landing slots, private per thread: [raw stage][copy][thread]
+    // cp.async landing zone of A: one 128 x 16 complex tile per raw stage, [row][k]
+    // (pitch 17) when K is contiguous in the operand, else [k][row]
+    float2 raw_a[G4_RAW][G4_BM * (G4_KC + 1)];
+    // cp.async landing slots of B, private per thread: [raw stage][copy][thread]
     float2 raw[G4_RAW][LOADS][G4_CONV];
     long long row_a[G4_BM], row_c[G4_BM], col_b[NT], col_c[NT];
     long long k_a[4][G4_KC], k_b[4][G4_KC];
@@ -141,7 +166,11 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     extern __shared__ __align__(1024) unsigned char g4_raw[];
     g4_smem<NT>& sm = *reinterpret_cast<g4_smem<NT>*>(g4_raw);
     constexpr int NP = 2 * NT;                               // real columns of D
-    constexpr int A_ITEMS = G4_BM * G4_KG / G4_CONV;         // (row, k-pair) items per thread
+    // tensor memory columns: [D set 0 | D set 1 | A stage 0 hi, lo | A stage 1 hi, lo]
+    constexpr int KR = 2 * G4_KC;                            // real K columns of a chunk (32)
+    constexpr int TM_A0 = 2 * NP;
+    constexpr int TM_COLS = (2 * NP + 2 * G4_STAGES * KR) <= 256 ? 256 : 512;
+    constexpr int A_LOADS = G4_BM * G4_KC / G4_CONV;         // complex A elements per thread, chunk (8)
     constexpr int B_ITEMS = NT * G4_KG / G4_CONV;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -192,7 +221,7 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     __syncwarp();
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
-                     ::"r"(g4_smem_u32(&sm.tmem_base)), "r"(2 * NP));
+                     ::"r"(g4_smem_u32(&sm.tmem_base)), "r"(TM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     if (tid == 32) {
@@ -210,16 +239,15 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 2NT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) |
                                ((uint32_t)(G4_BM >> 4) << 24);
-    constexpr uint32_t a_lbo = G4_ROWS_A * 16, b_lbo = g4_smem<NT>::ROWS_B * 16, sbo = 128;
-    constexpr uint32_t A_HALF_BYTES = G4_KG * G4_ROWS_A * 16, A_STAGE_BYTES = 2 * A_HALF_BYTES;
+    constexpr uint32_t b_lbo = g4_smem<NT>::ROWS_B * 16, sbo = 128;
     constexpr uint32_t B_HALF_BYTES = G4_KG * g4_smem<NT>::ROWS_B * 16, B_STAGE_BYTES = 2 * B_HALF_BYTES;
 
     if (warp == G4_CONV / 32) {
         // =================== MMA warp: one thread issues ===================
         if (lane == 0) {
-            // descriptors of stage 0 (hi tiles); lo tiles, the other stage and the
-            // k-steps are constant offsets of the 14-bit (address >> 4) field
-            const uint64_t desc_a_hi = g4_desc(g4_smem_u32(&sm.a[0][0][0][0]), a_lbo, sbo);
+            // B descriptor of stage 0 (hi tile); the lo tile, the other stage and the
+            // k-steps are constant offsets of the 14-bit (address >> 4) field.  A is
+            // read from tensor memory: 128 lanes x 8 columns per MMA.
             const uint64_t desc_b_hi = g4_desc(g4_smem_u32(&sm.b[0][0][0][0]), b_lbo, sbo);
             #pragma unroll 1
             for (int c = 0; c < nchunks; ++c) {
@@ -228,17 +256,15 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t d = tmem_d + (uint32_t)(((c / G4_SEG) & 1) * NP);
                 const bool first = (c % G4_SEG) == 0;
-                const uint64_t sa = (uint64_t)((uint32_t)st * (A_STAGE_BYTES >> 4));
+                const uint32_t a_hi = tmem_d + (uint32_t)(TM_A0 + st * 2 * KR), a_lo = a_hi + KR;
                 const uint64_t sb = (uint64_t)((uint32_t)st * (B_STAGE_BYTES >> 4));
                 #pragma unroll
                 for (int ks = 0; ks < G4_KG / 2; ++ks) {      // UMMA K = 8 tf32 = 2 k-groups
-                    const uint64_t dah = desc_a_hi + sa + (uint64_t)(ks * 2 * a_lbo >> 4);
-                    const uint64_t dal = dah + (A_HALF_BYTES >> 4);
                     const uint64_t dbh = desc_b_hi + sb + (uint64_t)(ks * 2 * b_lbo >> 4);
                     const uint64_t dbl = dbh + (B_HALF_BYTES >> 4);
-                    g4_mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
-                    g4_mma_tf32(d, dah, dbl, idesc, 1u);
-                    g4_mma_tf32(d, dal, dbh, idesc, 1u);
+                    g4_mma_tf32_ts(d, a_hi + 8 * ks, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+                    g4_mma_tf32_ts(d, a_hi + 8 * ks, dbl, idesc, 1u);
+                    g4_mma_tf32_ts(d, a_lo + 8 * ks, dbh, idesc, 1u);
                 }
                 g4_commit(&sm.empty[st]);     // frees the stage; also "chunk c is in TMEM"
             }
@@ -271,12 +297,22 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
             ++next_drain;
         };
 
-        // Work items (row, k-pair) of this thread, the same for every chunk.  Each
-        // thread converts exactly the elements it copied itself, so the copies need
-        // no block-wide barrier: K contiguous in the operand -> 8 lanes cover the 8
-        // k-pairs of a row (128 B contiguous), else lanes = consecutive rows.
-        const int a_r0 = a_kfast ? tid / G4_KG : tid % G4_BM, a_rstep = a_kfast ? G4_CONV / G4_KG : 0;
-        const int a_p0 = a_kfast ? tid % G4_KG : (tid / G4_BM) * A_ITEMS, a_pstep = a_kfast ? 0 : 1;
+        // Work items of this thread, the same for every chunk.  Each thread converts
+        // exactly the elements it copied itself, so the copies need no block-wide
+        // barrier.  A: thread = (row q*32 + lane, K half): a warp may only write its
+        // own quarter of the TMEM lanes, so the row is fixed by (warp % 4, lane) and
+        // the two warps of a quarter split the chunk's 16 k values.  B: K contiguous
+        // in the operand -> 8 lanes cover the 8 k-pairs of a row, else lanes = rows.
+        const int a_row = q * 32 + lane, a_k0 = half * (G4_KC / 2);
+        // A is copied with a coalesced mapping (16 lanes cover a row's 16 k values,
+        // or lanes = consecutive rows) into the shared raw tile and read back by the
+        // row's owner after the per-chunk converter barrier
+        const int a_pr = a_kfast ? G4_KC + 1 : 1, a_pk = a_kfast ? 1 : G4_BM;
+        const int c_r0 = a_kfast ? tid / G4_KC : tid % G4_BM, c_rstep = a_kfast ? G4_CONV / G4_KC : 0;
+        const int c_k0 = a_kfast ? tid % G4_KC : tid / G4_BM, c_kstep = a_kfast ? 0 : G4_CONV / G4_BM;
+        const uint32_t raw_a0 = g4_smem_u32(&sm.raw_a[0][0]) + 8u * (uint32_t)(c_r0 * a_pr + c_k0 * a_pk);
+        const uint32_t a_dstep = 8u * (uint32_t)(c_rstep * a_pr + c_kstep * a_pk);
+        constexpr uint32_t RAW_A_STAGE = G4_BM * (G4_KC + 1) * 8;
         const int b_r0 = b_kfast ? tid / G4_KG : tid % NT, b_rstep = b_kfast ? G4_CONV / G4_KG : 0;
         const int b_p0 = b_kfast ? tid % G4_KG : (tid / NT) * B_ITEMS, b_pstep = b_kfast ? 0 : 1;
         const int mrem = (int)(M - m0 < G4_BM ? M - m0 : G4_BM), nrem = (int)(N - n0 < NT ? N - n0 : NT);
@@ -291,16 +327,12 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                 const long long kleft = K - (long long)c * G4_KC;
                 const int krem = (int)(kleft < G4_KC ? kleft : G4_KC);
                 #pragma unroll
-                for (int p = 0; p < A_ITEMS; ++p) {
-                    const int r = a_r0 + p * a_rstep, kp = a_p0 + p * a_pstep;
-                    const long long ro = sm.row_a[r];
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int bytes = (r < mrem && 2 * kp + h < krem) ? 8 : 0;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                         dst + (uint32_t)(2 * p + h) * RAW_SLOT),
-                                     "l"(A + (ro + sm.k_a[kt][2 * kp + h])), "r"(bytes));
-                    }
+                for (int p = 0; p < A_LOADS; ++p) {
+                    const int r = c_r0 + p * c_rstep, k = c_k0 + p * c_kstep;
+                    const int bytes = (r < mrem && k < krem) ? 8 : 0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                     raw_a0 + (uint32_t)(c % G4_RAW) * RAW_A_STAGE + (uint32_t)p * a_dstep),
+                                 "l"(A + (sm.row_a[r] + sm.k_a[kt][k])), "r"(bytes));
                 }
                 #pragma unroll
                 for (int p = 0; p < B_ITEMS; ++p) {
@@ -310,7 +342,7 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                     for (int h = 0; h < 2; ++h) {
                         const int bytes = (n < nrem && 2 * kp + h < krem) ? 8 : 0;
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                         dst + (uint32_t)(2 * A_ITEMS + 2 * p + h) * RAW_SLOT),
+                                         dst + (uint32_t)(2 * p + h) * RAW_SLOT),
                                      "l"(B + (co + sm.k_b[kt][2 * kp + h])), "r"(bytes));
                     }
                 }
@@ -323,29 +355,40 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
         #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             const int st = c % G4_STAGES, rs = c % G4_RAW;
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");     // own copies of chunk c landed
+            // converter barrier: everyone's copies of chunk c are visible (the A tile is
+            // read by the rows' owners), the reduction offsets of chunk c + 2 are
+            // written, and the raw stage of chunk c - 1 is free for chunk c + 2
+            asm volatile("bar.sync 1, %0;\n" ::"n"(G4_CONV) : "memory");
             issue(c + 2);
-            asm volatile("cp.async.wait_group 2;\n" ::: "memory");     // own copies of chunk c landed
             // the UMMA stage is free once the MMAs of chunk c - 2 have completed; if
             // that chunk closed a segment, its TMEM set is complete: drain it
             if (c >= G4_STAGES) {
                 g4_mbar_wait(&sm.empty[st], (uint32_t)((c / G4_STAGES - 1) & 1));
                 if ((c - G4_STAGES) % G4_SEG == G4_SEG - 1) drain();
             }
-            // ---- split hi/lo and store in the UMMA K-major layout
-            #pragma unroll
-            for (int p = 0; p < A_ITEMS; ++p) {
-                const int r = a_r0 + p * a_rstep, kp = a_p0 + p * a_pstep;
-                const float2 v0 = sm.raw[rs][2 * p][tid], v1 = sm.raw[rs][2 * p + 1][tid];
-                const float4 x = make_float4(v0.x, v0.y, v1.x, v1.y);
-                const float4 h = make_float4(g4_hi(x.x), g4_hi(x.y), g4_hi(x.z), g4_hi(x.w));
-                sm.a[st][0][kp][r] = h;
-                sm.a[st][1][kp][r] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            // ---- A: split hi/lo in registers and store straight into tensor memory
+            //      (lane = row, 16 columns = this thread's 8 complex k values)
+            {
+                uint32_t hi[16], lo[16];
+                #pragma unroll
+                for (int j = 0; j < A_LOADS; ++j) {
+                    const float2 v = sm.raw_a[rs][a_row * a_pr + (a_k0 + j) * a_pk];
+                    const float hx = g4_hi(v.x), hy = g4_hi(v.y);
+                    hi[2 * j] = __float_as_uint(hx); hi[2 * j + 1] = __float_as_uint(hy);
+                    lo[2 * j] = __float_as_uint(v.x - hx); lo[2 * j + 1] = __float_as_uint(v.y - hy);
+                }
+                const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) +
+                                    (uint32_t)(TM_A0 + st * 2 * KR + half * (KR / 2));
+                g4_st16(ta, hi);
+                g4_st16(ta + KR, lo);
             }
+            // ---- B: split hi/lo and store in the UMMA K-major shared-memory layout
             #pragma unroll
             for (int p = 0; p < B_ITEMS; ++p) {
                 const int n = b_r0 + p * b_rstep, kp = b_p0 + p * b_pstep;
-                const float2 v0 = sm.raw[rs][2 * A_ITEMS + 2 * p][tid];
-                const float2 v1 = sm.raw[rs][2 * A_ITEMS + 2 * p + 1][tid];
+                const float2 v0 = sm.raw[rs][2 * p][tid];
+                const float2 v1 = sm.raw[rs][2 * p + 1][tid];
                 const float4 xr = make_float4(v0.x, -v0.y, v1.x, -v1.y);      // row of C_re
                 const float4 xi = make_float4(v0.y, v0.x, v1.y, v1.x);        // row of C_im
                 const float4 hr = make_float4(g4_hi(xr.x), g4_hi(xr.y), g4_hi(xr.z), g4_hi(xr.w));
@@ -355,13 +398,14 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
                 sm.b[st][1][kp][2 * n] = make_float4(xr.x - hr.x, xr.y - hr.y, xr.z - hr.z, xr.w - hr.w);
                 sm.b[st][1][kp][2 * n + 1] = make_float4(xi.x - hi.x, xi.y - hi.y, xi.z - hi.z, xi.w - hi.w);
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(g4_smem_u32(&sm.full[st]))
                          : "memory");
-            // reduction offsets of chunk c + 3, visible to everyone after the barrier
-            // (converter warps only; the MMA warp never touches the tables)
+            // reduction offsets of chunk c + 3, visible to everyone after the next
+            // converter barrier (the MMA warp never touches the tables)
             decode_k(c + 3, c & 7);
-            asm volatile("bar.sync 1, %0;\n" ::"n"(G4_CONV) : "memory");
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         // ---- all MMAs done (a commit tracks every earlier MMA of the issuing
@@ -394,7 +438,7 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     }
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(2 * NP));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(TM_COLS));
     }
 }
 
