@@ -191,7 +191,9 @@ class EvalResult:
         p_h, seen_h, mx_h = p.cpu().numpy(), seen.cpu().numpy(), float(mx.cpu().numpy()[0])
         # float(np.real_if_close(amp)) raises for a genuinely complex diagonal
         # entry (backends.py:348); tol = 100 machine epsilons
-        if mx_h >= 100 * np.finfo(np.float64).eps:
+        # (machine epsilon of the tensor's own precision, as numpy does)
+        real_dtype = np.float32 if _np_dtype(dev) == np.complex64 else np.float64
+        if mx_h >= 100 * np.finfo(real_dtype).eps:
             raise TypeError("can't convert complex to float")
         flat = np.flatnonzero(seen_h)
         probs = defaultdict(float)
