@@ -226,6 +226,25 @@ def test_complex64_eval_uses_tensor_core_gemm_and_meets_tolerance():
     assert "gemm" in kinds, kinds
 
 
+def test_quimb_adapter_path_on_device():
+    """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
+    ``term.to_quimb()`` yields) contracted by the CUDA kernels."""
+    from types import SimpleNamespace
+    from optyx_b200 import executor
+    from optyx_b200.adapters import network_from_quimb
+    rng = np.random.default_rng(11)
+    shapes = {"a": 3, "b": 4, "c": 2, "d": 5, "e": 3, "h": 4}
+    specs = [("a", "b", "h"), ("h", "c", "d"), ("d", "e", "h"), ("b", "c")]
+    tensors = [SimpleNamespace(data=rng.standard_normal([shapes[i] for i in ix]) +
+                               1j * rng.standard_normal([shapes[i] for i in ix]), inds=ix)
+               for ix in specs]
+    tn = SimpleNamespace(tensors=tensors, outer_inds=lambda: ("a", "e"))
+    net = network_from_quimb(tn)
+    got = executor.evaluate(net).cpu().numpy()
+    want = np.einsum("abh,hcd,deh,bc->ae", *[t.data for t in tensors])
+    assert _close(got, want, TOL128)
+
+
 def test_cfg3_standard_size_properties():
     """cfg3 at a size the oracle cannot reach quickly: 6 modes x inflate 2,
     2 partially distinguishable photons, loss, 3 measured modes.  Checked through

@@ -79,3 +79,26 @@ def test_path_candidates_are_compared_after_slicing():
     assert new_way.peak <= target + 1e-9
     assert new_way.time_est <= old_way.time_est * (1 + 1e-12)
     assert new_way.nslices >= 1 and new_way.time_est > 0
+
+
+def test_quimb_adapter_on_stand_in_objects():
+    """INTEGRATION.md adapter path: quimb-like tensors (data + index names, a hyper
+    index shared by three tensors, an integer-valued tensor) -> Network -> oracle."""
+    from types import SimpleNamespace
+    from optyx_b200.adapters import network_from_quimb
+    from oracle.contract import contract_network
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((2, 3, 4)) + 1j * rng.standard_normal((2, 3, 4))
+    b = rng.standard_normal((4, 3, 5)) + 1j * rng.standard_normal((4, 3, 5))
+    c = np.arange(6).reshape(3, 2)                   # int dtype, shares the hyper index "h"
+    tn = SimpleNamespace(
+        tensors=[SimpleNamespace(data=a, inds=("i", "h", "k")),
+                 SimpleNamespace(data=b, inds=("k", "h", "o")),
+                 SimpleNamespace(data=c, inds=("h", "p"))],
+        outer_inds=lambda: ("i", "o", "p"))
+    net = network_from_quimb(tn)
+    assert net.output_shape == (2, 5, 2) and all(l.params.dtype == np.complex128 for l in net.leaves)
+    want = np.einsum("ihk,kho,hp->iop", a, b, c)
+    assert np.allclose(contract_network(net), want, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        network_from_quimb(tn, output_inds=("i", "zzz"))
