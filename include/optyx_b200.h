@@ -130,6 +130,47 @@ int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev,
                      double alpha_im, int32_t accumulate, int32_t dtype,
                      void* stream);
 
+/* (2c) launch-bound small networks (hundreds of leaves of <= 343 elements): whole
+ * SUBTREES of tiny pairwise contractions in ONE launch, intermediates in SHARED
+ * MEMORY.  One CTA per group (an independent subtree): it first copies the
+ * group's leaf operands (`preload_dev[pre_start[g] .. pre_start[g+1])`) from the
+ * arena into its shared-memory scratch, then runs the group's steps
+ * (`steps_dev[group_start[g] .. group_start[g+1])`) back to back with a block
+ * barrier between them.  An operand / result with `*_smem != 0` lives in the
+ * scratch at byte offset `*_off`, otherwise at the absolute device address
+ * `*_ptr` (+ `*_off` bytes).  Same contraction form as b2_modes, at most
+ * B2_SMALL_MODES modes, alpha = 1, no accumulation.                          */
+#define B2_SMALL_MODES 16
+
+typedef struct {
+    int32_t n_out;
+    int32_t n_red;
+    int32_t n_out_elems;
+    int32_t n_red_elems;
+    int32_t dim[B2_SMALL_MODES];
+    uint32_t magic[B2_SMALL_MODES];     /* ceil(2^32 / dim): exact division of indices < 2^16 */
+    int64_t sa[B2_SMALL_MODES];
+    int64_t sb[B2_SMALL_MODES];
+    int64_t sc[B2_SMALL_MODES];
+    const void* a_ptr;
+    const void* b_ptr;
+    void* c_ptr;
+    int32_t a_off, b_off, c_off;        /* bytes */
+    int32_t a_smem, b_smem, c_smem;     /* 1 = in the CTA's shared-memory scratch */
+} b2_small_step;
+
+typedef struct {
+    const void* src;                    /* device address of a leaf (contiguous) */
+    int32_t dst_off;                    /* byte offset in the scratch           */
+    int32_t nbytes;
+} b2_small_preload;
+
+int b2_contract_small_groups(const b2_small_step* steps_dev,
+                             const int32_t* group_start_dev,
+                             const b2_small_preload* preload_dev,
+                             const int32_t* pre_start_dev, int32_t n_groups,
+                             int32_t scratch_bytes, int32_t dtype, void* stream);
+
 /* (3) slice / Sum-term accumulation: y += alpha * x over n complex elements  */
 int b2_axpy(int64_t n, double alpha_re, double alpha_im, const void* x_dev,
             void* y_dev, int32_t dtype, void* stream);

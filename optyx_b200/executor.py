@@ -82,6 +82,71 @@ class Session:
         self.params_stride = 0
         self.graph = None
         self.launches = 0
+        self._init_small_groups()
+
+    # ---- small-subtree launch -------------------------------------------------
+    def _init_small_groups(self) -> None:
+        """Device tables of the single small-subtree launch (``plan.small_groups``):
+        compact mode descriptors, leaf preload lists, scratch offsets."""
+        plan, torch = self.plan, self.torch
+        groups = plan.small_groups
+        self.small_n = len(groups)
+        if not self.small_n:
+            return
+        zeros = [0] * len(plan.sliced)
+        n_steps = sum(len(g.steps) for g in groups)
+        n_pre = sum(len(g.preload) for g in groups)
+        table = (rt.SmallStep * n_steps)()
+        pre = (rt.SmallPreload * max(1, n_pre))()
+        starts, pstarts, i, j = [0], [0], 0, 0
+        for g in groups:
+            for k in g.steps:
+                st, row = plan.steps[k], table[i]
+                d = st.desc
+                n = d.n_out + d.n_red
+                row.n_out, row.n_red = d.n_out, d.n_red
+                n_out = n_red = 1
+                for m in range(n):
+                    row.dim[m], row.sa[m], row.sb[m], row.sc[m] = d.dim[m], d.sa[m], d.sb[m], d.sc[m]
+                    assert d.dim[m] >= 2, "unit modes are merged away by the planner"
+                    row.magic[m] = ((1 << 32) + d.dim[m] - 1) // d.dim[m]
+                    if m < d.n_out:
+                        n_out *= d.dim[m]
+                    else:
+                        n_red *= d.dim[m]
+                row.n_out_elems, row.n_red_elems = n_out, n_red
+                a_off, b_off, c_off = g.place[k]
+                for name, lay, off in (("a", st.a, a_off), ("b", st.b, b_off), ("c", st.c, c_off)):
+                    if off is None:
+                        setattr(row, name + "_ptr", self._ptr(lay, zeros, ()))
+                        setattr(row, name + "_off", 0)
+                        setattr(row, name + "_smem", 0)
+                    else:
+                        setattr(row, name + "_ptr", None)
+                        setattr(row, name + "_off", off)
+                        setattr(row, name + "_smem", 1)
+                i += 1
+            for lay, off in g.preload:
+                pre[j].src = self._ptr(lay, zeros, ())
+                pre[j].dst_off, pre[j].nbytes = off, lay.size * self.esize
+                j += 1
+            starts.append(i)
+            pstarts.append(j)
+        self.small_scratch = max(g.scratch_bytes for g in groups)
+        self.small_steps_dev = torch.from_numpy(
+            np.frombuffer(bytes(table), dtype=np.uint8).copy()).to(self.device)
+        self.small_pre_dev = torch.from_numpy(
+            np.frombuffer(bytes(pre), dtype=np.uint8).copy()).to(self.device)
+        self.small_start_dev = torch.tensor(starts, dtype=torch.int32, device=self.device)
+        self.small_pstart_dev = torch.tensor(pstarts, dtype=torch.int32, device=self.device)
+
+    def _launch_small_groups(self, stream) -> None:
+        if self.small_n:
+            rt.check(self.lib.b2_contract_small_groups(
+                self.small_steps_dev.data_ptr(), self.small_start_dev.data_ptr(),
+                self.small_pre_dev.data_ptr(), self.small_pstart_dev.data_ptr(), self.small_n,
+                self.small_scratch, self.code, stream), "b2_contract_small_groups")
+            self.launches += 1
 
     # ---- leaves -------------------------------------------------------------
     def set_leaves(self, nets: Sequence[Network]) -> None:
@@ -155,8 +220,9 @@ class Session:
                 self._capture_invariant()
             self.inv_graph.replay()
         else:
+            self._launch_small_groups(stream)
             for st in plan.steps:
-                if not st.per_slice:
+                if not st.per_slice and not st.grouped:
                     self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream)
         if not plan.sliced:
             return
@@ -178,8 +244,9 @@ class Session:
 
         def body():
             stream = torch.cuda.current_stream().cuda_stream
+            self._launch_small_groups(stream)
             for st in plan.steps:
-                if not st.per_slice:
+                if not st.per_slice and not st.grouped:
                     self._launch(st, zeros, 1.0 + 0j, 0, stream)
         launches = self.launches
         side = torch.cuda.Stream(device=self.device)
@@ -217,18 +284,22 @@ class Session:
         if not hasattr(self, "_pool") or len(self._pool) != n_streams:
             self._pool = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         pool = self._pool
+        self._launch_small_groups(origin.cuda_stream)        # tiny subtrees: one launch, before the fork
         fork = torch.cuda.Event()
         fork.record(origin)
         for s in pool:
             s.wait_event(fork)
         producer = {}                       # id(layout) -> step index
         for k, st in enumerate(plan.steps):
-            producer[id(st.c)] = k
+            if not st.grouped:
+                producer[id(st.c)] = k
         where = {}                          # step index -> stream index
         consumers_elsewhere = {}            # step index -> event (recorded after launch)
         # first pass: stream assignment (inherit the larger operand's stream)
         rr = 0
         for k, st in enumerate(plan.steps):
+            if st.grouped:
+                continue
             pa, pb = producer.get(id(st.a)), producer.get(id(st.b))
             if pa is not None:
                 where[k] = where[pa]
@@ -239,6 +310,8 @@ class Session:
                 rr += 1
         need_event = set()
         for k, st in enumerate(plan.steps):
+            if st.grouped:
+                continue
             for p in (producer.get(id(st.a)), producer.get(id(st.b))):
                 if p is not None and where[p] != where[k]:
                     need_event.add(p)
@@ -246,6 +319,8 @@ class Session:
         zeros = [0] * len(plan.sliced)
         scalar = complex(scalar)
         for k, st in enumerate(plan.steps):
+            if st.grouped:
+                continue
             stream = pool[where[k]]
             for p in (producer.get(id(st.a)), producer.get(id(st.b))):
                 if p is not None and where[p] != where[k]:

@@ -312,6 +312,7 @@ class Step:
     macs: float                  # complex MACs (incl. eval batch)
     bytes: float                 # algorithmic bytes: s * (|A| + |B| + |C|)
     mnk: Tuple[int, int, int, int]   # (batch, M, N, K) extents
+    grouped: bool = False        # runs inside the small-subtree launch (plan.small_groups)
 
 
 @dataclass
@@ -333,6 +334,7 @@ class Plan:
     total_macs: float = 0.0
     total_bytes: float = 0.0
     parallel_safe: bool = False   # no workspace recycling: branches may overlap
+    small_groups: list = field(default_factory=list)      # SmallGroup per tiny subtree
 
 
 class _Allocator:
@@ -602,11 +604,130 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
             parallel_safe = True
     ws_elems = max([st.c.offset + st.c.size * batch for st in steps if st.c.space == WS] or [0])
 
+    small_groups = _group_small_steps(steps, esize, batch)
+    for group in small_groups:          # private, never recycled outputs (they run first)
+        for k in group.steps:
+            st = steps[k]
+            st.grouped = True
+            st.c.offset = int(ws_elems)
+            ws_elems += st.c.size * batch
+
     plan = Plan(steps, sliced, tuple(dims[q] for q in sliced), info.nslices, leaf_offsets,
                 arena_elems, unit_offset, int(ws_elems), out_shape, out_elems,
                 needs_zero or bool(sliced), batch, dtype, info, total_macs, total_bytes)
     plan.parallel_safe = parallel_safe
+    plan.small_groups = small_groups
     return plan
+
+
+SMALL_MODES, SMALL_OUT, SMALL_WORK = 16, 4096, 1 << 16
+SMALL_SCRATCH = 144 * 1024          # shared-memory scratch of one subtree CTA (bytes)
+SMALL_MAX_STEPS = 32                # longest subtree that runs inside one CTA
+
+
+@dataclass
+class SmallGroup:
+    """One leaf-rooted subtree of tiny steps, executed by one CTA with its leaves
+    and intermediates in shared memory (csrc/contract_small.cu)."""
+    steps: List[int]                                  # indices into plan.steps, in order
+    preload: List[Tuple[Layout, int]]                 # (leaf layout, scratch byte offset)
+    place: Dict[int, Tuple[Optional[int], Optional[int], Optional[int]]]
+    # step index -> scratch byte offsets of (a, b, c); None = global memory
+    scratch_bytes: int = 0
+
+
+def _group_small_steps(steps: List[Step], esize: int, batch: int) -> List[SmallGroup]:
+    """Leaf-rooted subtrees of tiny steps (each at most SMALL_OUT outputs and
+    SMALL_WORK multiply-adds, all operands leaves or tiny steps of the same
+    subtree).  Returns the subtrees with their shared-memory layout."""
+    if batch != 1:
+        return []
+    producer = {id(st.c): k for k, st in enumerate(steps)}
+    consumer: Dict[int, int] = {}
+    for k, st in enumerate(steps):
+        for lay in (st.a, st.b):
+            p = producer.get(id(lay))
+            if p is not None:
+                consumer[p] = k
+    early = [False] * len(steps)
+    parent = list(range(len(steps)))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    for k, st in enumerate(steps):
+        if st.kernel != "direct" or st.final or st.per_slice or st.a_slice or st.b_slice:
+            continue
+        d = st.desc
+        if d.n_out + d.n_red > SMALL_MODES:
+            continue
+        n_out = n_red = 1
+        for m in range(d.n_out):
+            n_out *= d.dim[m]
+        for m in range(d.n_red):
+            n_red *= d.dim[d.n_out + m]
+        if n_out > SMALL_OUT or n_red >= (1 << 16) or n_out * n_red > SMALL_WORK:
+            continue
+        prods = [producer.get(id(lay)) for lay in (st.a, st.b)]
+        if any(p is not None and not early[p] for p in prods):
+            continue
+        if any(p is None and lay.space != ARENA for p, lay in zip(prods, (st.a, st.b))):
+            continue
+        early[k] = True
+        for p in prods:
+            if p is not None:
+                parent[find(p)] = find(k)
+    members: Dict[int, List[int]] = {}
+    for k in range(len(steps)):
+        if early[k]:
+            members.setdefault(find(k), []).append(k)
+
+    def align(x):
+        return (x + 15) & ~15
+    groups: List[SmallGroup] = []
+    for ks in members.values():
+        inside = set(ks)
+        top = 0
+        leaf_off: Dict[int, int] = {}
+        preload: List[Tuple[Layout, int]] = []
+        for k in ks:                                  # leaves first, back to back
+            for lay in (steps[k].a, steps[k].b):
+                if id(lay) not in producer and id(lay) not in leaf_off:
+                    leaf_off[id(lay)] = top
+                    preload.append((lay, top))
+                    top += align(lay.size * esize)
+        alloc = _Allocator()                          # intermediates, recycled (units of 16 B)
+        inter_off: Dict[int, int] = {}
+        place = {}
+        for k in ks:
+            st = steps[k]
+            offs = []
+            for lay in (st.a, st.b):
+                p = producer.get(id(lay))
+                offs.append(leaf_off[id(lay)] if p is None else inter_off[p])
+            if consumer.get(k) in inside:
+                units = align(st.c.size * esize) // 16
+                inter_off[k] = top + 16 * alloc.alloc(units)     # provisional: leaves end at `top`
+                c_off = inter_off[k]
+            else:
+                c_off = None                          # root of the subtree -> global memory
+            for lay in (st.a, st.b):                  # operands die here (single consumer)
+                p = producer.get(id(lay))
+                if p is not None:
+                    alloc.release((inter_off[p] - top) // 16, align(steps[p].c.size * esize) // 16)
+            place[k] = (offs[0], offs[1], c_off)
+        scratch = top + 16 * alloc.top
+        # measured (tools/small_nets.py): a CTA walks its steps at ~1.5 us per step,
+        # about what a dependent kernel node of a CUDA graph costs, so the launch pays
+        # for many short PARALLEL subtrees (cfg1: 21 subtrees, -9 %; HOM: -15 %), not
+        # for one long chain (cfg2: 170-step subtrees, +40 %): long subtrees keep
+        # their own launches
+        if scratch <= SMALL_SCRATCH and len(ks) <= SMALL_MAX_STEPS:
+            groups.append(SmallGroup(list(ks), preload, place, scratch))
+    # the extra launch only pays when it replaces a fair number of tiny launches
+    return groups if sum(len(g.steps) for g in groups) >= 8 else []
 
 
 def plan_bound_seconds(plan: Plan, hbm_gbs: float, pipe_tflops: float) -> float:

@@ -19,7 +19,7 @@ MAX_RED_DIRECT = 16
 
 EXPORTS = [
     "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
-    "b2_contract_direct", "b2_contract_gemm", "b2_axpy", "b2_fill_zero",
+    "b2_contract_direct", "b2_contract_gemm", "b2_contract_small_groups", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_fp64_peak_kernel",
 ]
 
@@ -62,6 +62,28 @@ class GemmModes(C.Structure):
     ]
 
 
+SMALL_MODES = 16
+
+
+class SmallStep(C.Structure):
+    _fields_ = [
+        ("n_out", C.c_int32), ("n_red", C.c_int32),
+        ("n_out_elems", C.c_int32), ("n_red_elems", C.c_int32),
+        ("dim", C.c_int32 * SMALL_MODES),
+        ("magic", C.c_uint32 * SMALL_MODES),
+        ("sa", C.c_int64 * SMALL_MODES),
+        ("sb", C.c_int64 * SMALL_MODES),
+        ("sc", C.c_int64 * SMALL_MODES),
+        ("a_ptr", C.c_void_p), ("b_ptr", C.c_void_p), ("c_ptr", C.c_void_p),
+        ("a_off", C.c_int32), ("b_off", C.c_int32), ("c_off", C.c_int32),
+        ("a_smem", C.c_int32), ("b_smem", C.c_int32), ("c_smem", C.c_int32),
+    ]
+
+
+class SmallPreload(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_off", C.c_int32), ("nbytes", C.c_int32)]
+
+
 class B2Error(RuntimeError):
     pass
 
@@ -91,6 +113,7 @@ def load():
     lib.b2_build_leaves.argtypes = [vp, i32, i64, vp, i64, vp, i64, i32, i32, vp]
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_contract_gemm.argtypes = [C.POINTER(GemmModes), vp, vp, vp, dbl, dbl, i32, i32, vp]
+    lib.b2_contract_small_groups.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.b2_axpy.argtypes = [i64, dbl, dbl, vp, vp, i32, vp]
     lib.b2_fill_zero.argtypes = [i64, vp, i32, vp]
     lib.b2_probs_amp.argtypes = [i64, vp, vp, vp, i32, vp]
