@@ -226,6 +226,36 @@ def test_complex64_eval_uses_tensor_core_gemm_and_meets_tolerance():
     assert "gemm" in kinds, kinds
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_small_subtree_launch_matches_oracle(dtype):
+    """cfg1-like networks: the short leaf-rooted subtrees run in ONE launch with
+    shared-memory intermediates (b2_contract_small_groups); same tensor as the
+    oracle, and the same as the plan executed one launch per step."""
+    from cases import cfg1_interferometer, compile_channel
+    from optyx_b200 import executor, planner
+    d = cfg1_interferometer(4, (1, 1, 0, 0), depth=4)
+    net = compile_channel(d)
+    plan = planner.plan_network(net, dtype=dtype)
+    assert plan.small_groups and all(len(g.steps) <= planner.SMALL_MAX_STEPS for g in plan.small_groups)
+    sess = executor.Session(plan)
+    got = sess.run([net])[0].cpu().numpy()
+    assert sess.lib.b2_last_kernel().decode() != "" and sess.small_n == len(plan.small_groups)
+    want = oracle_eval(d)
+    tol = TOL128 if dtype == np.complex128 else 1e-5
+    assert _close(got, want, tol)
+    plain = planner.plan_network(net, dtype=dtype)
+    for g in plain.small_groups:
+        for k in g.steps:
+            plain.steps[k].grouped = False
+    plain.small_groups = []
+    ref = executor.Session(plain).run([net])[0].cpu().numpy()
+    assert _close(got, ref, tol)
+    # and through the captured graph (tree branches after the subtree launch)
+    sess.capture(net.scalar)
+    sess.replay()
+    assert _close(sess.out[0].cpu().numpy(), want, tol)
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""
