@@ -256,6 +256,48 @@ def test_small_subtree_launch_matches_oracle(dtype):
     assert _close(sess.out[0].cpu().numpy(), want, tol)
 
 
+def test_cfg2_full_size_closed_form_on_device():
+    """BASELINE cfg2 at the bench size: 20-qubit GHZ, DephasingError(0.95) on every
+    qubit, 14 open / 6 discarded -> 2^28-entry density tensor (4.3 GB, checked on
+    the device).  Closed form: the discarded qubits kill the coherences, and by the
+    reference's zx.ZBox.conjugate quirk each noise box multiplies
+    the diagonal by (2p - 1): exactly two non-zero entries 0.5 * 0.9^20."""
+    import torch
+    from cases import compile_channel
+    from optyx_b200 import executor
+    n, k, p = 20, 14, 0.95
+    net = compile_channel(ghz(n, open_qubits=k, noise=p))
+    dev = executor.evaluate(net)
+    assert tuple(dev.shape) == (2,) * (2 * k)
+    flat = dev.reshape(-1)
+    want = 0.5 * (2 * p - 1) ** n
+    first, last = complex(flat[0].item()), complex(flat[-1].item())
+    assert abs(first - want) <= 1e-10 * want and abs(last - want) <= 1e-10 * want
+    mag = flat.abs()
+    assert int((mag > 1e-12 * want).sum().item()) == 2          # nothing else survives
+    assert abs(float(mag.sum().item()) - 2 * want) <= 1e-9 * want
+    del dev, flat, mag
+    torch.cuda.empty_cache()
+
+
+def test_cfg4_full_size_two_slicings_agree():
+    """BASELINE cfg4 at the bench size (30 qubits, depth 41): the amplitude summed
+    over 2^26-element slices equals the one summed over 2^25-element slices (two
+    different plans, different slice sets), and |amplitude| <= 1."""
+    from cases import compile_channel
+    from optyx_b200 import executor
+    net = compile_channel(random_clifford_t(30, 41, seed=0))
+    vals = []
+    for tgt in (26, 25):
+        plan = executor.get_plan(net, target_size=float(2 ** tgt), trials=8)
+        assert plan.nslices > 1 and plan.info.peak <= 2 ** tgt
+        sess = executor.Session(plan)
+        vals.append(complex(sess.run([net])[0].cpu().numpy()))
+        del sess
+    a, b = vals
+    assert abs(a) <= 1.0 and abs(a - b) <= 1e-9 * abs(a), (a, b)
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""
