@@ -60,11 +60,13 @@ struct gemm_smem {
     long long k_a[STAGES][BK], k_b[STAGES][BK];
 };
 
+template <bool SPLITK>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
                           const double2* __restrict__ B, double2* __restrict__ Cout,
                           long long M, long long N, long long K, int tiles_m, int a_kfast,
-                          int b_kfast, double alpha_re, double alpha_im, int accumulate) {
+                          int b_kfast, double alpha_re, double alpha_im, int accumulate,
+                          int ksplit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     gemm_smem& sm = *reinterpret_cast<gemm_smem*>(smem_raw);
 
@@ -91,7 +93,15 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
         decode3(n < N ? n : 0, g, f_n, g.n_n, oa, ob, oc);
         sm.col_b[t] = ob; sm.col_c[t] = oc;
     }
-    const int nchunks = (int)((K + BK - 1) / BK);
+    // split-K (grid z): this CTA reduces chunks [c_begin, c_begin + nchunks) and adds
+    // its partial tile into the zero-filled C with FP64 atomics
+    // (the unsplit instantiation is the plain kernel: c_begin folds to 0)
+    const int all_chunks = (int)((K + BK - 1) / BK);
+    const int per_split = SPLITK ? (all_chunks + ksplit - 1) / ksplit : all_chunks;
+    const int c_begin = SPLITK ? (int)blockIdx.z * per_split : 0;
+    const int nchunks = !SPLITK ? all_chunks
+                        : (all_chunks - c_begin < per_split
+                               ? (all_chunks - c_begin > 0 ? all_chunks - c_begin : 0) : per_split);
 
     // reduction offsets of one chunk: 32-bit mixed-radix decode (K < 2^31) by the
     // last warp, so the 64-bit divisions of a many-mode K never sit on the critical
@@ -99,7 +109,7 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     auto decode_k = [&](int chunk) {
         const int t = tid - (GEMM_THREADS - 32);
         if (t >= 0 && t < BK) {
-            unsigned k = (unsigned)chunk * BK + (unsigned)t;
+            unsigned k = (unsigned)(c_begin + chunk) * BK + (unsigned)t;
             if ((long long)k >= K) k = 0;
             long long oa = 0, ob = 0;
             for (int m = 0; m < g.n_k; ++m) {
@@ -115,7 +125,7 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     };
     auto issue = [&](int chunk) {
         const int st = chunk % STAGES;
-        const long long kbase = (long long)chunk * BK;
+        const long long kbase = (long long)(c_begin + chunk) * BK;
         #pragma unroll
         for (int p = 0; p < (BM * BK) / GEMM_THREADS; ++p) {
             const int e = tid + p * GEMM_THREADS;
@@ -200,8 +210,13 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
                 v.x = alpha_re * cre[r][q][h] - alpha_im * cim[r][q][h];
                 v.y = alpha_re * cim[r][q][h] + alpha_im * cre[r][q][h];
                 double2* dst = Cout + ro + sm.col_c[j];
-                if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-                *dst = v;
+                if (SPLITK) {
+                    atomicAdd(&dst->x, v.x);
+                    atomicAdd(&dst->y, v.y);
+                } else {
+                    if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
             }
         }
     }
@@ -240,7 +255,12 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
         return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
                                (cudaStream_t)stream);
-    if (k_total <= 32 || n_total < 64) {
+    long long m_total = 1, b_total = 1;
+    for (int i = 0; i < g.n_m; ++i) m_total *= g.dim[g.n_batch + i];
+    for (int i = 0; i < g.n_batch; ++i) b_total *= g.dim[i];
+    const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
+                                 2ll * num_sms() && k_total >= 256;
+    if ((k_total <= 32 || n_total < 64) && !underfilled) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
         // classic 64x64 tiling below (4x4 register blocking per warp).
@@ -274,15 +294,45 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     static bool attr_set = false;
     const int smem = (int)sizeof(gemm_smem);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_gemm_c128_kernel,
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_c128_kernel<false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(contract_gemm_c128_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
         attr_set = true;
     }
-    set_last_kernel("gemm");
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt);
-    contract_gemm_c128_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-        g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
-        a_kfast, b_kfast, alpha_re, alpha_im, accumulate);
+    // split-K when the tiles alone leave most SMs idle (small M x N, long K: the
+    // reduction-heavy pairs of photonic networks).  C must be one dense block so
+    // that it can be zero-filled first (the partial tiles are added atomically).
+    int ksplit = 1;
+    {
+        const long long tiles = tiles_m * tiles_n * Bt, slots = 2ll * num_sms();
+        const long long chunks = (K + BK - 1) / BK;
+        long long span = 0;
+        for (int i = 0; i < f_k; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
+        const bool dense_c = span + 1 == Bt * M * N;
+        if (tiles * 2 <= slots && chunks >= 32 && (dense_c || accumulate)) {
+            long long want = slots / tiles;              // one resident wave
+            if (want > chunks / 8) want = chunks / 8;
+            if (want > 64) want = 64;
+            if (want > 1) ksplit = (int)want;
+        }
+        if (ksplit > 1 && !accumulate) {
+            cudaError_t e = cudaMemsetAsync(c_dev, 0, (size_t)(Bt * M * N) * sizeof(double2),
+                                            (cudaStream_t)stream);
+            if (e != cudaSuccess) { set_error("b2_contract_gemm: memset: %s", cudaGetErrorString(e)); return 1; }
+        }
+    }
+    set_last_kernel(ksplit > 1 ? "gemm_splitk" : "gemm");
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt, (unsigned)ksplit);
+    if (ksplit > 1)
+        contract_gemm_c128_kernel<true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
+            g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
+            a_kfast, b_kfast, alpha_re, alpha_im, accumulate, ksplit);
+    else
+        contract_gemm_c128_kernel<false><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
+            g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
+            a_kfast, b_kfast, alpha_re, alpha_im, accumulate, 1);
     return check_launch("b2_contract_gemm");
 }

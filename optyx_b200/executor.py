@@ -57,6 +57,10 @@ def params_vector(net: Network) -> np.ndarray:
     return np.concatenate(ps) if ps else np.zeros(1, dtype=np.complex128)
 
 
+BRANCH_STREAMS = 32      # capture streams = concurrent branches of the contraction tree
+                         # (cfg2's 394 small steps: 0.23 ms with 8, 0.16 with 16, 0.13-0.17 with 32)
+
+
 class Session:
     """Device buffers for one plan (arena, workspace, output) and its launcher."""
 
@@ -269,7 +273,7 @@ class Session:
         return self.out
 
     # ---- CUDA graph ---------------------------------------------------------
-    def contract_branches(self, scalar: complex, n_streams: int = 8) -> None:
+    def contract_branches(self, scalar: complex, n_streams: Optional[int] = None) -> None:
         """Unsliced plan with independent subtrees issued on different streams
         (fork after the leaf build, join before the end).  Under stream capture
         the event waits become graph edges, so the captured graph is the
@@ -277,6 +281,7 @@ class Session:
         instead of paying one launch latency each."""
         torch, plan = self.torch, self.plan
         assert plan.parallel_safe and not plan.sliced
+        n_streams = BRANCH_STREAMS if n_streams is None else n_streams
         origin = torch.cuda.current_stream()
         if plan.needs_zero_out:
             rt.check(self.lib.b2_fill_zero(self.out.numel(), self.out.data_ptr(), self.code,

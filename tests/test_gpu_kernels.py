@@ -250,6 +250,8 @@ def test_direct_kernel_variants(case, accumulate, dtype):
     ((100,), (33,), (17,), (2, 2)),
     ((130,), (70,), (5,), ()),
     ((2,) * 10, (2,) * 9, (2,) * 7, ()),
+    ((64,), (48,), (4096,), ()),                # few tiles, long K: split-K with FP64 atomics
+    ((8, 8), (4, 4), (7, 7, 7, 7), (2, 2)),
 ])
 def test_gemm_kernel_permuted_operands(case):
     rng = np.random.default_rng(3)

@@ -15,7 +15,8 @@ def timed(fn, reps=50):
 for name, d in (("cfg2_k10", cases.ghz(20, open_qubits=10, noise=0.95)), ("cfg2_measured", cases.ghz(20, noise=0.95, measure=True)),
                 ("cfg1", cases.cfg1_interferometer(6, (1, 1, 1, 0, 0, 0))), ("hom", cases.lossy_hom(0.8))):
     net = cases.compile_channel(d)
-    for grouping in (True, False):
+    for grouping, n_streams in ((True, 8), (False, 8), (True, 16), (True, 32)):
+        executor.BRANCH_STREAMS = n_streams
         plan = planner.plan_network(net)
         if not grouping:
             for g in plan.small_groups:
@@ -24,4 +25,4 @@ for name, d in (("cfg2_k10", cases.ghz(20, open_qubits=10, noise=0.95)), ("cfg2_
         sess = executor.Session(plan)
         sess.set_leaves([net]); sess.run([net])
         sess.capture(net.scalar)
-        print(name, "grouping", grouping, "groups", len(plan.small_groups), "steps", len(plan.steps), "ms %.4f" % timed(sess.replay), flush=True)
+        print(name, "streams", n_streams, "grouping", grouping, "groups", len(plan.small_groups), "steps", len(plan.steps), "ms %.4f" % timed(sess.replay), flush=True)

@@ -12,9 +12,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from optyx_b200 import executor  # noqa: E402
 
-if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
-    net = cases.compile_channel(cases.cfg3_interferometer(width=6, n_photons=3, measured=2))
+if len(sys.argv) > 1 and sys.argv[1] in ("cfg3", "cfg1"):
+    net = cases.compile_channel(cases.cfg3_interferometer(width=6, n_photons=3, measured=2)
+                                if sys.argv[1] == "cfg3" else
+                                cases.cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)))
     plan = executor.get_plan(net)
+    for g in plan.small_groups:                      # time every step on its own
+        for k in g.steps:
+            plan.steps[k].grouped = False
+    plan.small_groups = []
     for st in plan.steps:
         st.per_slice = True          # time every step
 else:
