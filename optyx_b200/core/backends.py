@@ -405,7 +405,35 @@ class B200Backend(AbstractBackend):
         torch.cuda.current_stream().synchronize()
         return host.numpy()
 
+    def _eval_sum(self, diagram) -> EvalResult:
+        """Formal sums (backends.py:473-476): every term is contracted on the device
+        and added with ``b2_axpy``; ``Sum.to_tensor`` padding (diagram.py:739-757)
+        makes the shapes agree."""
+        from .. import runtime as rt
+        pure = diagram.is_pure
+        td = diagram.get_kraus() if pure else diagram.double()
+        nets = td.to_networks(nested_eval=self._nested_eval) if hasattr(td, "terms") else \
+            [td.to_network(nested_eval=self._nested_eval)]
+        torch = _torch()
+        lib = rt.load()
+        total = None
+        for net in nets:
+            dev = self.eval_network(net)
+            if total is None:
+                total = dev.clone()
+            else:
+                stream = torch.cuda.current_stream().cuda_stream
+                rt.check(lib.b2_axpy(total.numel(), 1.0, 0.0, dev.data_ptr(), total.data_ptr(),
+                                     rt.dtype_code(_np_dtype(total)), stream), "b2_axpy")
+        n, shape = nets[0].n_dom, nets[0].output_shape
+        array = self._to_host(total)
+        return EvalResult(ResultTensor(shape[:n], shape[n:], array), output_types=diagram.cod,
+                          state_type=StateType.AMP if pure else StateType.DM,
+                          _device=total if self.keep_on_device else None)
+
     def eval(self, diagram: channel.Diagram, **extra: Any) -> EvalResult:
+        if hasattr(diagram, "terms"):
+            return self._eval_sum(diagram)
         net = self._get_network(diagram, nested_eval=self._nested_eval)
         dev = self.eval_network(net)
         array = self._to_host(dev)

@@ -139,6 +139,31 @@ class Diagram(diagram.Diagram):
 Diagram.diagram_factory = Diagram
 
 
+class Sum(diagram.Sum):
+    """Formal sum of channel diagrams (channel.py:697-722)."""
+
+    def double(self) -> diagram.Sum:
+        return diagram.Sum([t.double() for t in self.terms])            # channel.py:706-707
+
+    def get_kraus(self):
+        if not self.terms:
+            return diagram.Scalar(0)
+        return diagram.Sum([t.get_kraus() for t in self.terms])         # channel.py:715-722
+
+    @property
+    def is_pure(self) -> bool:
+        return all(t.is_pure for t in self.terms)
+
+    def eval(self, backend=None, **kwargs):
+        from .backends import B200Backend
+        if backend is None:
+            backend = B200Backend()
+        return backend.eval(self, **kwargs)
+
+
+Diagram.sum_factory = Sum
+
+
 class _CBox(Diagram):
     """Common base of channel-level generators."""
 

@@ -140,6 +140,8 @@ class Diagram:
         return res
 
     def __rshift__(self, other: "Diagram") -> "Diagram":
+        if isinstance(other, Sum):
+            return NotImplemented               # -> Sum.__rrshift__ (distributes)
         if isinstance(other, Ty):
             other = self.id(other)
         if self.cod != other.dom:
@@ -151,6 +153,8 @@ class Diagram:
         return other >> self
 
     def __matmul__(self, other) -> "Diagram":
+        if isinstance(other, Sum):
+            return NotImplemented               # -> Sum.__rmatmul__
         if isinstance(other, Ty):
             other = self.id(other)
         # f @ g = f @ g.dom >> f.cod @ g   (monoidal whiskering order)
@@ -306,6 +310,91 @@ class Diagram:
 
 
 Diagram.diagram_factory = Diagram
+
+
+class Sum:
+    """Formal sum of diagrams with one ``dom`` / ``cod`` (diagram.py:710-765).
+    ``>>`` / ``@`` distribute over the terms, as DisCoPy's ``symmetric.Sum`` does;
+    evaluation contracts every term and adds the results after padding each
+    output wire to the per-wire maximum dimension (``Sum.to_tensor``, 737-765)."""
+
+    def __init__(self, terms: Sequence[Diagram], dom: Optional[Ty] = None, cod: Optional[Ty] = None):
+        self.terms: List[Diagram] = list(terms)
+        if self.terms:
+            dom = self.terms[0].dom if dom is None else dom
+            cod = self.terms[0].cod if cod is None else cod
+        if dom is None or cod is None:
+            raise ValueError("an empty sum needs explicit dom and cod")
+        for t in self.terms:
+            if t.dom != dom or t.cod != cod:
+                raise ValueError(f"cannot add diagrams of types {t.dom} -> {t.cod} and {dom} -> {cod}")
+        self.dom, self.cod = dom, cod
+
+    def _make(self, terms, dom=None, cod=None):
+        return type(self)(terms, dom, cod)
+
+    def __iter__(self):
+        return iter(self.terms)
+
+    def __len__(self):
+        return len(self.terms)
+
+    def __add__(self, other):
+        if isinstance(other, int) and other == 0:
+            return self
+        others = other.terms if isinstance(other, Sum) else [other]
+        return self._make(self.terms + list(others), self.dom, self.cod)
+
+    __radd__ = __add__
+
+    def __rshift__(self, other):
+        others = other.terms if isinstance(other, Sum) else [other]
+        out = [a >> b for a in self.terms for b in others]
+        cod = others[0].cod if others else self.cod
+        return self._make(out, self.dom, cod)
+
+    def __rrshift__(self, other):           # diagram >> sum
+        return self._make([other >> t for t in self.terms], other.dom, self.cod)
+
+    def __matmul__(self, other):
+        others = other.terms if isinstance(other, Sum) else [other]
+        out = [a @ b for a in self.terms for b in others]
+        return self._make(out, self.dom @ others[0].dom, self.cod @ others[0].cod)
+
+    def __rmatmul__(self, other):
+        return self._make([other @ t for t in self.terms], other.dom @ self.dom, other.cod @ self.cod)
+
+    def conjugate(self):
+        return self._make([t.conjugate() for t in self.terms], self.dom, self.cod)
+
+    def dagger(self):
+        return self._make([t.dagger() for t in self.terms], self.cod, self.dom)
+
+    def inflate(self, d: int):
+        terms = [t.inflate(d) for t in self.terms]
+        return self._make(terms, terms[0].dom, terms[0].cod) if terms else self
+
+    def to_networks(self, input_dims: Optional[List[int]] = None, nested_eval=None) -> List[nw.Network]:
+        """One network per term, output wires padded to the per-wire maximum
+        with ``EmbeddingTensor`` leaves (diagram.py:739-757)."""
+        nets = [t.to_network(input_dims, nested_eval=nested_eval) for t in self.terms]
+        return nw.pad_outputs_to_common_shape(nets)
+
+    def to_tensor(self, input_dims: Optional[List[int]] = None, nested_eval=None):
+        return self.to_networks(input_dims, nested_eval=nested_eval)
+
+
+def _diagram_add(self, other):
+    if isinstance(other, int) and other == 0:          # sum([...]) starts from 0
+        return self
+    if isinstance(other, Sum):
+        return other._make([self] + other.terms, self.dom, self.cod)
+    return self.sum_factory([self, other], self.dom, self.cod)
+
+
+Diagram.sum_factory = Sum
+Diagram.__add__ = _diagram_add
+Diagram.__radd__ = _diagram_add
 
 
 def is_identity(d: Diagram) -> bool:

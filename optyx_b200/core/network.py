@@ -193,3 +193,36 @@ class NetworkBuilder:
         )
         net.validate()
         return net
+
+
+def pad_outputs_to_common_shape(nets: Sequence[Network]) -> List[Network]:
+    """Terms of a formal sum: every output (cod) wire is embedded into the per-wire
+    maximum dimension over the terms with an ``EmbeddingTensor`` leaf
+    (optyx/core/diagram.py:739-757, 1005-1027), so that the results can be added.
+    Domain axes are fixed by ``input_dims`` and must already agree."""
+    nets = list(nets)
+    if not nets:
+        return nets
+    shapes = [n.output_shape for n in nets]
+    rank = len(shapes[0])
+    if any(len(s) != rank for s in shapes):
+        raise ValueError("terms of a sum have different numbers of open wires")
+    target = tuple(max(s[p] for s in shapes) for p in range(rank))
+    out = []
+    for net in nets:
+        n_dom = net.n_dom
+        if any(net.output_shape[p] != target[p] for p in range(n_dom)):
+            raise ValueError("terms of a sum disagree on the input dimensions")
+        leaves, dims = list(net.leaves), dict(net.dims)
+        outs = list(net.output_inds)
+        nxt = max(dims, default=-1) + 1
+        for p in range(n_dom, rank):
+            d = net.output_shape[p]
+            if d == target[p]:
+                continue
+            dims[nxt] = target[p]
+            leaves.append(Leaf(K_EMBED, (d, target[p]), (outs[p], nxt), 0, None, "embed"))
+            outs[p] = nxt
+            nxt += 1
+        out.append(Network(leaves, dims, tuple(outs), net.scalar, n_dom))
+    return out

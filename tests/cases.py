@@ -25,7 +25,19 @@ def compile_channel(d: channel.Diagram):
     return d.double().to_network(nested_eval=oracle_nested)
 
 
+def _pad_to(arr: np.ndarray, shape) -> np.ndarray:
+    out = np.zeros(shape, dtype=arr.dtype)
+    out[tuple(slice(0, s) for s in arr.shape)] = arr
+    return out
+
+
 def oracle_eval(d) -> np.ndarray:
+    if hasattr(d, "terms"):
+        # formal sum (backends.py:473-476 + diagram.py:737-765): every term on its
+        # own, zero-padded to the largest extent of each axis, then added
+        arrs = [oracle_eval(t) for t in d.terms]
+        shape = tuple(max(a.shape[k] for a in arrs) for k in range(arrs[0].ndim))
+        return sum(_pad_to(a, shape) for a in arrs)
     if isinstance(d, channel.Diagram):
         net = compile_channel(d)
     else:

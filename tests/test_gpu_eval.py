@@ -298,6 +298,25 @@ def test_cfg4_full_size_two_slicings_agree():
     assert abs(a) <= 1.0 and abs(a - b) <= 1e-9 * abs(a), (a, b)
 
 
+def test_formal_sums_on_device():
+    """backends.py:473-476: a Sum is evaluated term by term and added (b2_axpy);
+    pure sum = test_zw.py:284-292 (branching), mixed sum: two loss channels."""
+    from optyx_b200 import photonic
+    from optyx_b200.core import zw
+    branching = photonic.Create(1) @ photonic.Create(0) + photonic.Create(0) @ photonic.Create(1)
+    res = branching.eval(B200Backend())
+    assert res.state_type is StateType.AMP
+    assert _close(res.tensor.array, oracle_eval(branching), TOL128)
+    amps = res.amplitudes()
+    assert set(amps) == {(1, 0), (0, 1)} and abs(amps[(1, 0)] - 2 ** -0.5) < 1e-12
+    mixed = photonic.Create(1) >> (photonic.PhotonLoss(0.3) + photonic.PhotonLoss(0.9)) \
+        >> photonic.NumberResolvingMeasurement(1)
+    r = mixed.eval(B200Backend())
+    assert r.state_type is StateType.DM and _close(r.tensor.array, oracle_eval(mixed), TOL128)
+    p = r.prob_dist()
+    assert p[(1,)] == pytest.approx(0.6, abs=1e-12) and p[(0,)] == pytest.approx(0.4, abs=1e-12)
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""

@@ -336,3 +336,32 @@ def test_forward_cone_equals_backward_walk():
             finally:
                 dg.FORWARD_CONES = True
         assert keys[0] == keys[1]
+
+
+def test_branching_sum_equals_w():
+    """test_zw.py:284-292: Create(1) >> W(2) == Create(1) @ Create(0) + Create(0) @ Create(1)
+    (formal sums: diagram.py:710-765, terms padded to a common shape and added)."""
+    from optyx_b200.core import zw
+    lhs = oracle_eval(zw.Create(1) >> zw.W(2))
+    rhs_diagram = zw.Create(1) @ zw.Create(0) + zw.Create(0) @ zw.Create(1)
+    assert len(rhs_diagram.terms) == 2
+    rhs = oracle_eval(rhs_diagram)
+    shape = tuple(max(a, b) for a, b in zip(lhs.shape, rhs.shape))
+    pad = lambda a: np.pad(a, [(0, s - d) for s, d in zip(shape, a.shape)])      # noqa: E731
+    assert np.allclose(pad(lhs), pad(rhs))
+    # the product's own padding (EmbeddingTensor leaves) gives the same tensor
+    nets = rhs_diagram.to_networks()
+    from oracle.contract import contract_network
+    assert np.allclose(sum(contract_network(n) for n in nets), rhs)
+
+
+def test_sum_algebra_distributes_and_checks_types():
+    from optyx_b200.core import zw
+    a, b, c = zw.Create(1), zw.Create(2), zw.W(2)
+    s = (a + b) >> c
+    assert [len(t.boxes) for t in s.terms] == [2, 2] and s.cod == c.cod
+    assert len(sum([a, b, a]).terms) == 3
+    t = zw.Create(0) @ (a + b)
+    assert len(t.terms) == 2 and len(t.cod) == 2
+    with pytest.raises(ValueError):
+        a + c
