@@ -128,6 +128,24 @@ class Diagram(diagram.Diagram):
             res = res >> (l @ mid @ r)
         return res
 
+    @classmethod
+    def from_bosonic_operator(cls, n_modes: int, operators, scalar=1):
+        """channel.py:459-479: a product of creation / annihilation operators
+        ``[(mode, is_dagger), ...]`` as a ZW channel (annihilation = split one photon
+        off and select it)."""
+        from . import zw
+        d = Diagram.id(qmode ** n_modes)
+        annil = Channel("annil", zw.Split(2) >> zw.Select(1) @ zw.Id(1))
+        create = annil.dagger()
+        for idx, dagger in operators:
+            if not 0 <= idx < n_modes:
+                raise ValueError(f"Index {idx} out of bounds.")
+            box = create if dagger else annil
+            d = d >> (Diagram.id(qmode ** idx) @ box @ Diagram.id(qmode ** (n_modes - idx - 1)))
+        if scalar != 1:
+            d = Channel(f"{scalar}", diagram.Scalar(scalar)) @ d
+        return d
+
     def eval(self, backend=None, **kwargs):
         """channel.py:564-574; the default backend here is the B200 one."""
         from .backends import B200Backend

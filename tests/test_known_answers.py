@@ -365,3 +365,22 @@ def test_sum_algebra_distributes_and_checks_types():
     assert len(t.terms) == 2 and len(t.cod) == 2
     with pytest.raises(ValueError):
         a + c
+
+
+def test_bosonic_operator_hamiltonian_sum():
+    """test_channel.py:36-64: a hopping Hamiltonian a_0^dag a_1 + a_1^dag a_0 as a
+    formal sum of channels; its Kraus tensor and its CP-doubled evaluation describe
+    the same operator (the doubled tensor is kraus (x) conj(kraus) summed per term)."""
+    from optyx_b200.core.channel import Diagram
+    matrix = [[0, 1], [1, 0]]
+    terms = [Diagram.from_bosonic_operator(2, [(i, False), (j, True)], scalar=matrix[i][j])
+             for i in range(2) for j in range(2)]
+    ham = Diagram.sum_factory(terms)
+    assert len(ham.terms) == 4 and ham.is_pure
+    kraus = oracle_eval(ham)                       # pure: AMP tensor of the Kraus sum
+    # a_0^dag a_1 |0,1> = |1,0>  and  a_1^dag a_0 |1,0> = |0,1>
+    assert kraus.shape[:2] == (2, 2)
+    assert kraus[0, 1, 1, 0] == pytest.approx(1.0) and kraus[1, 0, 0, 1] == pytest.approx(1.0)
+    assert kraus[0, 0].sum() == 0 and kraus[1, 1, 1, 1] == pytest.approx(0.0)
+    with pytest.raises(ValueError):
+        Diagram.from_bosonic_operator(2, [(2, False)])
