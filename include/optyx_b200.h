@@ -190,6 +190,22 @@ int b2_probs_dm(int32_t ndim, const int32_t* dims, const int32_t* axis_kind,
                 const void* t_dev, double* p_dev, uint8_t* seen_dev,
                 double* max_imag_dev, int32_t dtype, void* stream);
 
+/* (5) permanents: amplitudes of a pure linear-optical circuit (the reference's
+ * PermanentBackend, backends.py:1019-1098; Matrix.eval path.py:345-384; npperm
+ * path.py:141-163).  u_dev: m x m single-particle matrix (complex128, row
+ * major); rows_dev[n]: input mode of each created photon (device, at least one
+ * element); cols_dev[n_configs][n]:
+ * output mode of each detected photon, per configuration; norm_dev[n_configs]:
+ * 1 / sqrt(prod in! out!).  amp_dev[c] = norm[c] * perm(U[rows, cols_c])
+ * (Glynn's formula in Gray-code order, one warp per configuration, the 2^(n-1)
+ * sign vectors split over the lanes).  n <= B2_PERM_MAX_N, m <= B2_PERM_MAX_M. */
+#define B2_PERM_MAX_N 30
+#define B2_PERM_MAX_M 64
+int b2_permanent_amplitudes(const void* u_dev, int32_t m, const int32_t* rows_dev,
+                            int32_t n, const uint8_t* cols_dev,
+                            const double* norm_dev, int64_t n_configs,
+                            void* amp_dev, void* stream);
+
 /* micro-benchmarks used by bench.py to measure the FP64 pipes of this GPU:
  * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = DMMA m16n8k16 (falls back to 1 if the
  * shape is unavailable).  Launches `iters` dependent-chain iterations on a

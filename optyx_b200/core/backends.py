@@ -443,3 +443,110 @@ class B200Backend(AbstractBackend):
         return EvalResult(ResultTensor(shape[:n], shape[n:], array),
                           output_types=diagram.cod, state_type=state_type,
                           _device=dev if self.keep_on_device else None)
+
+
+class PermanentBackend(AbstractBackend):
+    """Pure linear-optical circuits through matrix permanents on the GPU
+    (reference ``PermanentBackend``, backends.py:1019-1098; ``Matrix.eval``
+    path.py:345-384).
+
+    Supported diagrams: ``photonic.Create`` boxes, linear-optical gates
+    (``photonic.AbstractGate`` subclasses: BS / TBS / MZI / Phase / Gate / ansatz),
+    mode swaps and identities, with no open input wires.  Anything else raises
+    ``AssertionError`` (the reference's behaviour for non-LO circuits,
+    test_backends.py:470-474).  Amplitudes of all ``C(n + m - 1, n)`` output
+    occupations come from ``b2_permanent_amplitudes`` (csrc/permanent.cu)."""
+
+    MAX_DENSE = 1 << 26
+
+    @staticmethod
+    def _single_particle(diagram):
+        """(T, creations): ``T[slot, wire]`` = single-photon amplitude from the
+        slot-th created mode to the wire-th output mode."""
+        from .. import photonic
+        if len(diagram.dom) != 0:
+            raise NotImplementedError("PermanentBackend: open input wires are not supported; "
+                                      "compose the input state with photonic.Create")
+        T = np.zeros((0, 0), dtype=np.complex128)
+        creations = []
+        for left, box, right in diagram.layers():
+            o = len(left)
+            if isinstance(box, photonic.Create):
+                k = len(box.photons)
+                n_s, n_w = T.shape
+                new = np.zeros((n_s + k, n_w + k), dtype=np.complex128)
+                new[:n_s, :o] = T[:, :o]
+                new[:n_s, o + k:] = T[:, o:]
+                new[n_s:, o:o + k] = np.eye(k)
+                T = new
+                creations.extend(int(p) for p in box.photons)
+            elif isinstance(box, photonic.AbstractGate):
+                w = len(box.dom)
+                assert len(box.cod) == w, "PermanentBackend: gates must preserve the mode count"
+                G = np.asarray(box.array, dtype=np.complex128).reshape(w, w)
+                T[:, o:o + w] = T[:, o:o + w] @ G
+            elif isinstance(box, channel.Swap):
+                assert len(box.dom) == 2, "PermanentBackend: only single-mode swaps"
+                T[:, [o, o + 1]] = T[:, [o + 1, o]]
+            else:
+                raise AssertionError(f"PermanentBackend: {type(box).__name__} is not linear optical")
+        if any(t != "qmode" for t in diagram.cod.inside):
+            raise AssertionError("PermanentBackend: the outputs must be quantum modes")
+        return T, creations
+
+    def amplitudes_table(self, diagram):
+        """(occupations [n_configs, m], amplitudes [n_configs]) of every output
+        configuration with the created number of photons."""
+        import itertools
+        from math import factorial
+        from .. import runtime as rt
+        from ..executor import require_cuda
+        T, creations = self._single_particle(diagram)
+        n, m = sum(creations), T.shape[1]
+        if n == 0:
+            raise ValueError("The diagram does not include any photon creations. "
+                             "n_photons must be greater than 0.")
+        torch = require_cuda()
+        lib = rt.load()
+        rows = np.array([slot for slot, c in enumerate(creations) for _ in range(c)], dtype=np.int32)
+        cols = np.array(list(itertools.combinations_with_replacement(range(m), n)), dtype=np.uint8)
+        occ = np.zeros((len(cols), m), dtype=np.int64)
+        np.add.at(occ, (np.repeat(np.arange(len(cols)), n), cols.reshape(-1).astype(np.int64)), 1)
+        fact = np.array([factorial(k) for k in range(n + 1)], dtype=np.float64)
+        norm = 1.0 / np.sqrt(np.prod(fact[occ], axis=1) * np.prod(fact[np.array(creations)]))
+        # the kernel takes a square m' x m' matrix: rows = slots, columns = wires
+        mm = max(T.shape)
+        U = np.zeros((mm, mm), dtype=np.complex128)
+        U[:T.shape[0], :T.shape[1]] = T
+        dev = torch.device("cuda", torch.cuda.current_device())
+        u_d = torch.from_numpy(U).to(dev)
+        rows_d = torch.from_numpy(rows).to(dev)
+        cols_d = torch.from_numpy(cols).to(dev)
+        norm_d = torch.from_numpy(norm).to(dev)
+        amp_d = torch.empty(len(cols), dtype=torch.complex128, device=dev)
+        rt.check(lib.b2_permanent_amplitudes(u_d.data_ptr(), mm, rows_d.data_ptr(), n,
+                                             cols_d.data_ptr(), norm_d.data_ptr(), len(cols),
+                                             amp_d.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream),
+                 "b2_permanent_amplitudes")
+        return occ, amp_d.cpu().numpy()
+
+    def prob_dist(self, diagram) -> dict:
+        """``{occupation: |amplitude|^2}`` without the dense tensor (large circuits)."""
+        occ, amp = self.amplitudes_table(diagram)
+        p = np.abs(amp) ** 2
+        keep = np.flatnonzero(p)
+        return dict(zip(map(tuple, occ[keep].tolist()), p[keep].tolist()))
+
+    def eval(self, diagram: channel.Diagram, **extra: Any) -> EvalResult:
+        if hasattr(diagram, "terms"):
+            raise NotImplementedError("PermanentBackend: formal sums are not supported")
+        occ, amp = self.amplitudes_table(diagram)
+        n, m = int(occ[0].sum()), occ.shape[1]
+        if float(n + 1) ** m > self.MAX_DENSE:
+            raise ValueError(f"dense result of {(n + 1)}^{m} entries is too large: use "
+                             "PermanentBackend.prob_dist / amplitudes_table")
+        dense = np.zeros((n + 1,) * m, dtype=np.complex128)        # amplitudes_2_tensor
+        dense[tuple(occ.T)] = amp
+        return EvalResult(ResultTensor((), dense.shape, dense), output_types=diagram.cod,
+                          state_type=StateType.AMP)

@@ -1,0 +1,138 @@
+// GPU permanents for pure linear-optical circuits -- the other
+// evaluation algorithm the reference offers for this path (PermanentBackend,
+// optyx/core/backends.py:1019-1098; amplitude formula Matrix.eval path.py:345-384;
+// permanent = Glynn's formula in Gray-code order, npperm path.py:141-163).
+//
+//   amp[c] = norm[c] * perm(A_c),   A_c[i][j] = U[rows[i]][cols_c[j]]   (n x n)
+//   perm(A) = 2^(1-n) * sum_{delta in {+-1}^n, delta_0 = +1} (prod_k delta_k) prod_j (sum_i delta_i A[i][j])
+//
+// One warp per output configuration.  The 2^(n-1) sign vectors are split into 32
+// contiguous Gray-code ranges, one per lane: a lane builds its column sums for the
+// first code of its range (n^2 adds), then walks the range with one row update
+// (n complex adds) and one n-term complex product per code.  U lives in shared
+// memory (m <= 64: 64 KB); the warp's n x n submatrix is gathered into registers-
+// adjacent shared memory once.  FP64 throughout (compute bound: ~8 n flops per code).
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr int PM_WARPS = 4;          // warps (configurations) per CTA
+
+__global__ void __launch_bounds__(PM_WARPS * 32)
+permanent_kernel(const double2* __restrict__ U, int m, int n, const int* __restrict__ rows_g,
+                 const unsigned char* __restrict__ cols, const double* __restrict__ norm,
+                 long long n_configs, double2* __restrict__ amp) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    double2* Us = reinterpret_cast<double2*>(pm_smem);                 // [m][m]
+    double2* As = Us + m * m;                                          // [PM_WARPS][n][n]
+    __shared__ int rows[B2_PERM_MAX_N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < m * m; i += blockDim.x) Us[i] = U[i];
+    if (threadIdx.x < n) rows[threadIdx.x] = rows_g[threadIdx.x];
+    __syncthreads();
+    double2* A = As + warp * n * n;
+    const long long total = n > 0 ? (1ll << (n - 1)) : 1;
+    for (long long c = (long long)blockIdx.x * PM_WARPS + warp; c < n_configs;
+         c += (long long)gridDim.x * PM_WARPS) {
+        const unsigned char* cc = cols + c * n;
+        __syncwarp();
+        for (int e = lane; e < n * n; e += 32) {
+            const int i = e / n, j = e - i * n;
+            A[e] = Us[rows[i] * m + cc[j]];
+        }
+        __syncwarp();
+        double sx = 0.0, sy = 0.0;
+        if (n == 0) {
+            if (lane == 0) sx = 1.0;
+        } else {
+            // this lane's range of Gray-code ranks [g0, g1)
+            const long long per = (total + 31) / 32;
+            const long long g0 = lane * per, g1 = g0 + per < total ? g0 + per : total;
+            if (g0 < g1) {
+                // sign vector of rank g: bits of gray(g) = g ^ (g >> 1) say which of rows
+                // 1..n-1 are negated (row 0 keeps delta = +1)
+                double2 v[B2_PERM_MAX_N];
+                long long gray = g0 ^ (g0 >> 1);
+                int sign = 1;
+                #pragma unroll 1
+                for (int j = 0; j < n; ++j) {
+                    double2 s = A[j];                                  // row 0
+                    for (int i = 1; i < n; ++i) {
+                        const double2 a = A[i * n + j];
+                        if ((gray >> (i - 1)) & 1) { s.x -= a.x; s.y -= a.y; }
+                        else { s.x += a.x; s.y += a.y; }
+                    }
+                    v[j] = s;
+                }
+                sign = (__popcll(gray) & 1) ? -1 : 1;
+                for (long long gi = g0; gi < g1; ++gi) {
+                    if (gi != g0) {
+                        // rank gi differs from gi - 1 in bit ctz(gi): flip that row
+                        const int b = __ffsll(gi) - 1;                 // row b + 1
+                        const bool now_neg = ((gi ^ (gi >> 1)) >> b) & 1;
+                        const double f = now_neg ? -2.0 : 2.0;
+                        const double2* ar = A + (b + 1) * n;
+                        #pragma unroll 1
+                        for (int j = 0; j < n; ++j) {
+                            v[j].x = fma(f, ar[j].x, v[j].x);
+                            v[j].y = fma(f, ar[j].y, v[j].y);
+                        }
+                        sign = -sign;
+                    }
+                    double px = v[0].x, py = v[0].y;
+                    #pragma unroll 1
+                    for (int j = 1; j < n; ++j) {
+                        const double tx = px * v[j].x - py * v[j].y;
+                        py = px * v[j].y + py * v[j].x;
+                        px = tx;
+                    }
+                    sx += sign * px; sy += sign * py;
+                }
+            }
+        }
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, off);
+            sy += __shfl_xor_sync(0xffffffffu, sy, off);
+        }
+        if (lane == 0) {
+            const double scale = norm[c] * (n > 0 ? ldexp(1.0, 1 - n) : 1.0);
+            amp[c] = make_double2(sx * scale, sy * scale);
+        }
+    }
+}
+
+}  // namespace b2
+
+extern "C" int b2_permanent_amplitudes(const void* u_dev, int32_t m, const int32_t* rows_dev,
+                                       int32_t n, const uint8_t* cols_dev,
+                                       const double* norm_dev, int64_t n_configs,
+                                       void* amp_dev, void* stream) {
+    using namespace b2;
+    if (n_configs <= 0) return 0;
+    if (!u_dev || !cols_dev || !norm_dev || !amp_dev || !rows_dev) {
+        set_error("b2_permanent_amplitudes: null pointer");
+        return 1;
+    }
+    if (m < 1 || m > B2_PERM_MAX_M || n < 0 || n > B2_PERM_MAX_N) {
+        set_error("b2_permanent_amplitudes: m = %d (max %d), n = %d (max %d)", m, B2_PERM_MAX_M, n,
+                  B2_PERM_MAX_N);
+        return 1;
+    }
+    int sms = num_sms();
+    if (sms <= 0) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)(m * m + PM_WARPS * n * n) * sizeof(double2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(permanent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    long long blocks = (n_configs + PM_WARPS - 1) / PM_WARPS;
+    const long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    permanent_kernel<<<(unsigned)blocks, PM_WARPS * 32, smem, s>>>(
+        (const double2*)u_dev, m, n, rows_dev, cols_dev, norm_dev, n_configs, (double2*)amp_dev);
+    set_last_kernel("permanent");
+    return check_launch("b2_permanent_amplitudes");
+}

@@ -317,6 +317,51 @@ def test_formal_sums_on_device():
     assert p[(1,)] == pytest.approx(0.6, abs=1e-12) and p[(0,)] == pytest.approx(0.4, abs=1e-12)
 
 
+@pytest.mark.parametrize("name", ["BS", "phase_tbs", "MZI", "chip", "bunched"])
+def test_permanent_backend_matches_tensor_network_backend(name):
+    """test_backends.py:482-509: PermanentBackend == QuimbBackend on Create >> circuit
+    (amplitudes, prob_dist, tensor to 1e-12) -- here GPU permanents vs the CUDA
+    tensor-network path, and both vs the oracle."""
+    from optyx_b200 import photonic
+    from optyx_b200.core.backends import PermanentBackend
+    circ, photons = {
+        "BS": (photonic.BS, (1, 1)),
+        "phase_tbs": (photonic.Phase(0.2) @ photonic.Phase(0.3) >> photonic.TBS(0.3), (1, 1)),
+        "MZI": (photonic.MZI(0.2, 0.8), (1, 1)),
+        "chip": (photonic.seeded_ansatz(4, 4, seed=7), (1, 1, 1, 1)),
+        "bunched": (photonic.seeded_ansatz(3, 3, seed=2), (2, 0, 1)),
+    }[name]
+    d = photonic.Create(*photons) >> circ
+    tn = d.eval(B200Backend())
+    pm = d.eval(PermanentBackend())
+    assert pm.state_type is StateType.AMP
+    n = sum(photons)
+    want = oracle_eval(d)
+    # the tensor-network result is truncated by the light cone; embed it in (n+1)^m
+    full = np.zeros((n + 1,) * len(photons), dtype=complex)
+    full[tuple(slice(0, s) for s in want.shape)] = want
+    assert np.abs(pm.tensor.array - full).max() <= 1e-12
+    a_tn, a_pm = tn.amplitudes(), pm.amplitudes()
+    assert set(a_tn) == set(a_pm)
+    assert all(abs(a_tn[k] - a_pm[k]) <= 1e-10 for k in a_tn)
+    p_tn, p_pm = tn.prob_dist(), PermanentBackend().prob_dist(d)
+    assert all(abs(p_tn[k] - p_pm.get(k, 0.0)) <= 1e-10 for k in p_tn)
+
+
+def test_permanent_backend_12_modes_6_photons_is_normalised():
+    """The BASELINE cfg3 interferometer without loss and distinguishability: 12 modes,
+    6 photons, 12 376 output configurations, far beyond an exact tensor-network
+    contraction; unitarity => the probabilities sum to 1."""
+    from optyx_b200 import photonic
+    from optyx_b200.core.backends import PermanentBackend
+    d = photonic.Create(1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0) >> photonic.seeded_ansatz(12, 12, seed=0)
+    p = PermanentBackend().prob_dist(d)
+    assert len(p) <= 12376 and all(sum(k) == 6 for k in p)
+    assert sum(p.values()) == pytest.approx(1.0, abs=1e-10)
+    with pytest.raises(AssertionError):
+        (d >> photonic.NumberResolvingMeasurement(12)).eval(PermanentBackend())
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""

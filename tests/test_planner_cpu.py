@@ -102,3 +102,21 @@ def test_quimb_adapter_on_stand_in_objects():
     assert np.allclose(contract_network(net), want, rtol=1e-12, atol=1e-12)
     with pytest.raises(ValueError):
         network_from_quimb(tn, output_inds=("i", "zzz"))
+
+
+def test_permanent_backend_host_logic():
+    """PermanentBackend: single-particle matrix of Create >> gates,
+    reference error behaviour for non-LO circuits (test_backends.py:470-479)."""
+    from optyx_b200 import photonic
+    from optyx_b200.core.backends import PermanentBackend
+    d = photonic.Create(1, 0) @ photonic.Create(2) >> photonic.seeded_ansatz(3, 3, seed=1) \
+        >> photonic.Swap(1, 1) @ photonic.Id(1)
+    T, creations = PermanentBackend._single_particle(d)
+    assert creations == [1, 0, 2] and T.shape == (3, 3)
+    assert np.allclose(T @ T.conj().T, np.eye(3), atol=1e-12)
+    with pytest.raises(AssertionError):
+        PermanentBackend._single_particle(d >> photonic.NumberResolvingMeasurement(3))
+    with pytest.raises(AssertionError):
+        PermanentBackend._single_particle(photonic.Create(1) >> photonic.PhotonLoss(0.5))
+    with pytest.raises(NotImplementedError):
+        PermanentBackend._single_particle(photonic.BS)
