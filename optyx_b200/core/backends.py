@@ -510,8 +510,8 @@ class PermanentBackend(AbstractBackend):
         lib = rt.load()
         rows = np.array([slot for slot, c in enumerate(creations) for _ in range(c)], dtype=np.int32)
         cols = np.array(list(itertools.combinations_with_replacement(range(m), n)), dtype=np.uint8)
-        occ = np.zeros((len(cols), m), dtype=np.int64)
-        np.add.at(occ, (np.repeat(np.arange(len(cols)), n), cols.reshape(-1).astype(np.int64)), 1)
+        flat = (np.arange(len(cols), dtype=np.int64)[:, None] * m + cols.astype(np.int64)).reshape(-1)
+        occ = np.bincount(flat, minlength=len(cols) * m).reshape(len(cols), m)
         fact = np.array([factorial(k) for k in range(n + 1)], dtype=np.float64)
         norm = 1.0 / np.sqrt(np.prod(fact[occ], axis=1) * np.prod(fact[np.array(creations)]))
         # the kernel takes a square m' x m' matrix: rows = slots, columns = wires
@@ -524,12 +524,17 @@ class PermanentBackend(AbstractBackend):
         cols_d = torch.from_numpy(cols).to(dev)
         norm_d = torch.from_numpy(norm).to(dev)
         amp_d = torch.empty(len(cols), dtype=torch.complex128, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         rt.check(lib.b2_permanent_amplitudes(u_d.data_ptr(), mm, rows_d.data_ptr(), n,
                                              cols_d.data_ptr(), norm_d.data_ptr(), len(cols),
                                              amp_d.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream),
                  "b2_permanent_amplitudes")
-        return occ, amp_d.cpu().numpy()
+        e1.record()
+        amp = amp_d.cpu().numpy()
+        self.last_kernel_ms = e0.elapsed_time(e1)
+        return occ, amp
 
     def prob_dist(self, diagram) -> dict:
         """``{occupation: |amplitude|^2}`` without the dense tensor (large circuits)."""

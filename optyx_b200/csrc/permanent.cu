@@ -18,6 +18,9 @@ namespace b2 {
 
 constexpr int PM_WARPS = 4;          // warps (configurations) per CTA
 
+// NMAX: compile-time bound of n -- the column sums v[] stay in registers (fully
+// unrolled, predicated loops) for NMAX <= 16
+template <int NMAX>
 __global__ void __launch_bounds__(PM_WARPS * 32)
 permanent_kernel(const double2* __restrict__ U, int m, int n, const int* __restrict__ rows_g,
                  const unsigned char* __restrict__ cols, const double* __restrict__ norm,
@@ -51,18 +54,20 @@ permanent_kernel(const double2* __restrict__ U, int m, int n, const int* __restr
             if (g0 < g1) {
                 // sign vector of rank g: bits of gray(g) = g ^ (g >> 1) say which of rows
                 // 1..n-1 are negated (row 0 keeps delta = +1)
-                double2 v[B2_PERM_MAX_N];
+                double2 v[NMAX];
                 long long gray = g0 ^ (g0 >> 1);
                 int sign = 1;
-                #pragma unroll 1
-                for (int j = 0; j < n; ++j) {
-                    double2 s = A[j];                                  // row 0
-                    for (int i = 1; i < n; ++i) {
-                        const double2 a = A[i * n + j];
-                        if ((gray >> (i - 1)) & 1) { s.x -= a.x; s.y -= a.y; }
-                        else { s.x += a.x; s.y += a.y; }
+                #pragma unroll
+                for (int j = 0; j < NMAX; ++j) {
+                    if (j < n) {
+                        double2 s = A[j];                              // row 0
+                        for (int i = 1; i < n; ++i) {
+                            const double2 a = A[i * n + j];
+                            if ((gray >> (i - 1)) & 1) { s.x -= a.x; s.y -= a.y; }
+                            else { s.x += a.x; s.y += a.y; }
+                        }
+                        v[j] = s;
                     }
-                    v[j] = s;
                 }
                 sign = (__popcll(gray) & 1) ? -1 : 1;
                 for (long long gi = g0; gi < g1; ++gi) {
@@ -72,19 +77,23 @@ permanent_kernel(const double2* __restrict__ U, int m, int n, const int* __restr
                         const bool now_neg = ((gi ^ (gi >> 1)) >> b) & 1;
                         const double f = now_neg ? -2.0 : 2.0;
                         const double2* ar = A + (b + 1) * n;
-                        #pragma unroll 1
-                        for (int j = 0; j < n; ++j) {
-                            v[j].x = fma(f, ar[j].x, v[j].x);
-                            v[j].y = fma(f, ar[j].y, v[j].y);
+                        #pragma unroll
+                        for (int j = 0; j < NMAX; ++j) {
+                            if (j < n) {
+                                v[j].x = fma(f, ar[j].x, v[j].x);
+                                v[j].y = fma(f, ar[j].y, v[j].y);
+                            }
                         }
                         sign = -sign;
                     }
                     double px = v[0].x, py = v[0].y;
-                    #pragma unroll 1
-                    for (int j = 1; j < n; ++j) {
-                        const double tx = px * v[j].x - py * v[j].y;
-                        py = px * v[j].y + py * v[j].x;
-                        px = tx;
+                    #pragma unroll
+                    for (int j = 1; j < NMAX; ++j) {
+                        if (j < n) {
+                            const double tx = px * v[j].x - py * v[j].y;
+                            py = px * v[j].y + py * v[j].x;
+                            px = tx;
+                        }
                     }
                     sx += sign * px; sy += sign * py;
                 }
@@ -123,16 +132,25 @@ extern "C" int b2_permanent_amplitudes(const void* u_dev, int32_t m, const int32
     if (sms <= 0) return 1;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = (size_t)(m * m + PM_WARPS * n * n) * sizeof(double2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(permanent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
     long long blocks = (n_configs + PM_WARPS - 1) / PM_WARPS;
     const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
-    permanent_kernel<<<(unsigned)blocks, PM_WARPS * 32, smem, s>>>(
-        (const double2*)u_dev, m, n, rows_dev, cols_dev, norm_dev, n_configs, (double2*)amp_dev);
+#define B2_PERM_LAUNCH(NM)                                                                     \
+    do {                                                                                       \
+        static bool attr_done = false;                                                         \
+        if (!attr_done) {                                                                      \
+            cudaFuncSetAttribute(permanent_kernel<NM>,                                         \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+            attr_done = true;                                                                  \
+        }                                                                                      \
+        permanent_kernel<NM><<<(unsigned)blocks, PM_WARPS * 32, smem, s>>>(                    \
+            (const double2*)u_dev, m, n, rows_dev, cols_dev, norm_dev, n_configs,              \
+            (double2*)amp_dev);                                                                \
+    } while (0)
+    if (n <= 8) B2_PERM_LAUNCH(8);
+    else if (n <= 16) B2_PERM_LAUNCH(16);
+    else B2_PERM_LAUNCH(B2_PERM_MAX_N);
+#undef B2_PERM_LAUNCH
     set_last_kernel("permanent");
     return check_launch("b2_permanent_amplitudes");
 }
