@@ -206,6 +206,22 @@ int b2_permanent_amplitudes(const void* u_dev, int32_t m, const int32_t* rows_de
                             const double* norm_dev, int64_t n_configs,
                             void* amp_dev, void* stream);
 
+/* (5b) the same for LOSSY / partially distinguishable interferometers measured on
+ * some modes: probabilities of the detected photon counts, marginalised on the
+ * device over every unmeasured mode (loss environments, discarded modes, internal
+ * states).  v_dev: n x M complex128, row i = single-particle output amplitudes of
+ * photon i over ALL M output modes; configurations (multisets of n output modes)
+ * are enumerated on the device in lexicographic order from their rank
+ * (binom_dev[(a) * (n + 1) + b] = C(a, b), a <= M + n); every configuration adds
+ * scale * |perm|^2 / prod(out!) to hist_dev[sum_j mode_stride_dev[mode_j]]
+ * (hist_dev zero-filled by the caller, n_bins entries).                       */
+#define B2_PERM_HIST_MAX_M 128
+int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
+                           const int64_t* binom_dev,
+                           const int32_t* mode_stride_dev, double scale,
+                           int64_t n_configs, int32_t n_bins, double* hist_dev,
+                           void* stream);
+
 /* micro-benchmarks used by bench.py to measure the FP64 pipes of this GPU:
  * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = DMMA m16n8k16 (falls back to 1 if the
  * shape is unavailable).  Launches `iters` dependent-chain iterations on a

@@ -536,6 +536,142 @@ class PermanentBackend(AbstractBackend):
         self.last_kernel_ms = e0.elapsed_time(e1)
         return occ, amp
 
+    # ---- lossy / partially distinguishable interferometers ----------------------
+    @staticmethod
+    def _photon_rows(diagram):
+        """Parse ``Create(.., internal_states) >> {gates, PhotonLoss, swaps} >>
+        {NumberResolvingMeasurement | Discard | open}`` (NOT inflated: the internal
+        degree of freedom is handled here).  Returns ``(V, measured, d)``: ``V[i]`` =
+        single-particle output amplitudes of photon i over all output modes
+        (spatial mode x internal state, then the loss environments), ``measured[w]``
+        = position of output mode w among the measured spatial modes or -1."""
+        from .. import photonic
+        if len(diagram.dom) != 0:
+            raise NotImplementedError("PermanentBackend: open input wires are not supported")
+        d_int = 1
+        for box in diagram.boxes:
+            if isinstance(box, photonic.Create) and box.internal_states is not None:
+                states = box.internal_states if isinstance(box.internal_states, tuple) \
+                    else (box.internal_states,)
+                d_int = len(states[0])
+        eye = np.eye(d_int)
+        T = np.zeros((0, 0), dtype=np.complex128)      # [photon, wire * d_int + k]
+        env = np.zeros((0, 0), dtype=np.complex128)    # [photon, loss mode]
+        wires_alive = 0
+        measured = []                                  # per final wire: True / False / None (open)
+        for left, box, right in diagram.layers():
+            o = len(left)
+            if isinstance(box, photonic.Create):
+                k = len(box.photons)
+                states = box.internal_states
+                if states is not None and not isinstance(states, tuple):
+                    states = (states,)
+                n_p, n_w = T.shape[0], T.shape[1] // d_int
+                n_new = sum(int(p) for p in box.photons)
+                new = np.zeros((n_p + n_new, (n_w + k) * d_int), dtype=np.complex128)
+                new[:n_p, :o * d_int] = T[:, :o * d_int]
+                new[:n_p, (o + k) * d_int:] = T[:, o * d_int:]
+                row, s_idx = n_p, 0
+                for j, cnt in enumerate(box.photons):
+                    for _ in range(int(cnt)):
+                        vec = np.zeros(d_int, dtype=np.complex128)
+                        if states is None:
+                            vec[0] = 1.0
+                        else:
+                            vec[:] = np.asarray(states[s_idx], dtype=np.complex128)
+                            s_idx += 1
+                        new[row, (o + j) * d_int:(o + j + 1) * d_int] = vec
+                        row += 1
+                T = new
+                env = np.vstack([env, np.zeros((n_new, env.shape[1]), dtype=np.complex128)]) \
+                    if env.size or env.shape[1] else np.zeros((n_p + n_new, 0), dtype=np.complex128)
+                measured[o:o] = [None] * k
+            elif isinstance(box, photonic.AbstractGate):
+                w = len(box.dom)
+                assert len(box.cod) == w, "PermanentBackend: gates must preserve the mode count"
+                G = np.kron(np.asarray(box.array, dtype=np.complex128).reshape(w, w), eye)
+                T[:, o * d_int:(o + w) * d_int] = T[:, o * d_int:(o + w) * d_int] @ G
+            elif isinstance(box, photonic.PhotonLoss):
+                p = float(box.p_survive)
+                blk = T[:, o * d_int:(o + 1) * d_int]
+                env = np.hstack([env, blk * (1.0 - p) ** 0.5])
+                T[:, o * d_int:(o + 1) * d_int] = blk * p ** 0.5
+            elif isinstance(box, channel.Swap):
+                assert len(box.dom) == 2, "PermanentBackend: only single-mode swaps"
+                a = slice(o * d_int, (o + 1) * d_int)
+                b = slice((o + 1) * d_int, (o + 2) * d_int)
+                tmp = T[:, a].copy()
+                T[:, a] = T[:, b]
+                T[:, b] = tmp
+                measured[o], measured[o + 1] = measured[o + 1], measured[o]
+            elif isinstance(box, channel.Measure) and all(t == "qmode" for t in box.dom.inside):
+                for j in range(len(box.dom)):
+                    assert measured[o + j] is None, "PermanentBackend: mode measured twice"
+                    measured[o + j] = True
+            elif isinstance(box, channel.Discard) and all(t == "qmode" for t in box.dom.inside):
+                for j in range(len(box.dom)):
+                    measured[o + j] = False
+            else:
+                raise AssertionError(f"PermanentBackend: {type(box).__name__} is not linear optical")
+        # wires still open count as measured; discarded wires stay in V (unmeasured)
+        # although the diagram no longer lists them
+        flags = [True if f is None else f for f in measured]
+        V = np.hstack([T, env])
+        pos, where = 0, []
+        for f in flags:
+            where.extend([pos if f else -1] * d_int)
+            pos += 1 if f else 0
+        where.extend([-1] * env.shape[1])
+        return V, np.array(where, dtype=np.int64), pos
+
+    def prob_dist_measured(self, diagram) -> dict:
+        """Detected-count distribution of a lossy, partially distinguishable
+        interferometer (the BASELINE cfg3 shape at full size): all permanents, the
+        ``1 / prod(out!)`` weights and the marginalisation over loss environments,
+        discarded modes and internal states run on the device
+        (``b2_permanent_histogram``).  ``diagram`` is the un-inflated channel
+        diagram ``Create(.., internal_states) >> ... >> Measure / Discard``."""
+        from math import comb
+        from .. import runtime as rt
+        from ..executor import require_cuda
+        V, where, k = self._photon_rows(diagram)
+        n, M = V.shape
+        if n == 0:
+            raise ValueError("The diagram does not include any photon creations. "
+                             "n_photons must be greater than 0.")
+        torch = require_cuda()
+        lib = rt.load()
+        n_bins = (n + 1) ** k
+        stride = np.where(where >= 0, (n + 1) ** np.maximum(k - 1 - where, 0), 0).astype(np.int32)
+        binom = np.array([[comb(a, b) for b in range(n + 1)] for a in range(M + n + 1)],
+                         dtype=np.int64)
+        n_configs = comb(M + n - 1, n)
+        # identical creation operators (same mode, same internal state) are bunched: 1 / c!
+        from math import factorial
+        scale, seen = 1.0, {}
+        for row in V:
+            key = row.tobytes()
+            seen[key] = seen.get(key, 0) + 1
+        for c in seen.values():
+            scale /= factorial(c)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        v_d = torch.from_numpy(np.ascontiguousarray(V)).to(dev)
+        b_d = torch.from_numpy(binom).to(dev)
+        s_d = torch.from_numpy(stride).to(dev)
+        hist = torch.zeros(n_bins, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rt.check(lib.b2_permanent_histogram(v_d.data_ptr(), n, M, b_d.data_ptr(), s_d.data_ptr(),
+                                            scale, n_configs, n_bins, hist.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream),
+                 "b2_permanent_histogram")
+        e1.record()
+        h = hist.cpu().numpy()
+        self.last_kernel_ms, self.last_configs = e0.elapsed_time(e1), n_configs
+        keep = np.flatnonzero(h)
+        keys = np.vstack(np.unravel_index(keep, (n + 1,) * k)).T.tolist() if k else [[]] * len(keep)
+        return dict(zip(map(tuple, keys), h[keep].tolist()))
+
     def prob_dist(self, diagram) -> dict:
         """``{occupation: |amplitude|^2}`` without the dense tensor (large circuits)."""
         occ, amp = self.amplitudes_table(diagram)

@@ -88,6 +88,7 @@ class Create(Channel):
 
     def __init__(self, *photons: int, internal_states=None):
         self.photons = photons
+        self.internal_states = internal_states
         super().__init__(f"Create({photons})",
                          zw.Create(*photons, internal_states=internal_states))
 

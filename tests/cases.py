@@ -140,7 +140,8 @@ def random_internal_state(rng, dim=2):
     return v / np.linalg.norm(v)
 
 
-def cfg3_interferometer(width=4, n_photons=2, measured=2, loss=0.9, seed=0, depth=None):
+def cfg3_interferometer(width=4, n_photons=2, measured=2, loss=0.9, seed=0, depth=None,
+                        inflate=True):
     """SURVEY 8(d) cfg3 (scaled by arguments): lossy interferometer with
     partially distinguishable photons, ``.inflate(2)``."""
     rng = np.random.default_rng(2025)
@@ -152,7 +153,7 @@ def cfg3_interferometer(width=4, n_photons=2, measured=2, loss=0.9, seed=0, dept
     d = d >> photonic.seeded_ansatz(width, depth, seed)
     d = d >> photonic.NumberResolvingMeasurement(measured) @ photonic.Discard(width - measured) \
         if measured < width else d >> photonic.NumberResolvingMeasurement(width)
-    return d.inflate(2)
+    return d.inflate(2) if inflate else d
 
 
 def fusion_ii_teleportation():

@@ -362,6 +362,42 @@ def test_permanent_backend_12_modes_6_photons_is_normalised():
         (d >> photonic.NumberResolvingMeasurement(12)).eval(PermanentBackend())
 
 
+@pytest.mark.parametrize("shape", [(4, 2, 2), (5, 3, 2), (4, 3, 4)])
+def test_lossy_distinguishable_permanents_match_tensor_network(shape):
+    """cfg3-shaped circuits (loss on every mode, partially distinguishable photons,
+    some modes measured, the rest discarded): detected-count distribution from GPU
+    permanents (device enumeration + marginalisation) == CP-doubled tensor network."""
+    from cases import cfg3_interferometer
+    from optyx_b200.core.backends import PermanentBackend
+    width, n_photons, measured = shape
+    tn = cfg3_interferometer(width=width, n_photons=n_photons, measured=measured).eval(
+        B200Backend()).prob_dist()
+    pm = PermanentBackend().prob_dist_measured(
+        cfg3_interferometer(width=width, n_photons=n_photons, measured=measured, inflate=False))
+    assert sum(pm.values()) == pytest.approx(1.0, abs=1e-10)
+    keys = set(k for k, v in tn.items() if v > 1e-13) | set(k for k, v in pm.items() if v > 1e-13)
+    for k in keys:
+        assert abs(tn.get(tuple(k), 0.0) - pm.get(tuple(k), 0.0)) <= 1e-10, (k, tn.get(k), pm.get(k))
+
+
+def test_cfg3_full_size_through_permanents():
+    """BASELINE cfg3 at its full size -- 12 modes, 6 photons, PhotonLoss(0.9) on every
+    mode, partially distinguishable photons (internal dimension 2), 4 modes measured,
+    8 discarded: 22 957 480 output configurations over 48 modes, beyond any exact
+    tensor-network contraction.  Size-independent properties:
+    normalisation, photon-number bound, loss monotonicity of the vacuum outcome."""
+    from cases import cfg3_interferometer
+    from optyx_b200.core.backends import PermanentBackend
+    pb = PermanentBackend()
+    p = pb.prob_dist_measured(cfg3_interferometer(width=12, n_photons=6, measured=4, inflate=False))
+    assert pb.last_configs == 22957480
+    assert sum(p.values()) == pytest.approx(1.0, abs=1e-9)
+    assert all(len(k) == 4 and sum(k) <= 6 for k in p) and all(v >= 0 for v in p.values())
+    q = PermanentBackend().prob_dist_measured(
+        cfg3_interferometer(width=12, n_photons=6, measured=4, loss=0.5, inflate=False))
+    assert q[(0, 0, 0, 0)] > p[(0, 0, 0, 0)]          # more loss -> more often nothing detected
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""

@@ -120,3 +120,34 @@ def test_permanent_backend_host_logic():
         PermanentBackend._single_particle(photonic.Create(1) >> photonic.PhotonLoss(0.5))
     with pytest.raises(NotImplementedError):
         PermanentBackend._single_particle(photonic.BS)
+
+
+def test_lossy_distinguishable_photon_rows_against_the_tensor_network_oracle():
+    """Host half of PermanentBackend.prob_dist_measured: the photon row vectors over
+    (spatial mode x internal state + loss environments) and the measured-mode map,
+    contracted here with the ORACLE's permanent and marginalised in Python, give
+    the same detected-count distribution as the CP-doubled tensor-network oracle."""
+    import itertools
+    from math import factorial
+    import cases
+    from oracle import evalresult as oe
+    from oracle.permanent import npperm
+    from optyx_b200.core.backends import PermanentBackend
+    d = cases.cfg3_interferometer(width=4, n_photons=2, measured=2, inflate=False)
+    V, where, k = PermanentBackend._photon_rows(d)
+    n, M = V.shape
+    assert (n, M, k) == (2, 16, 2) and np.allclose((np.abs(V) ** 2).sum(axis=1), 1.0)
+    hist = {}
+    for cols in itertools.combinations_with_replacement(range(M), n):
+        occ = np.bincount(cols, minlength=M)
+        w = abs(npperm(V[:, list(cols)])) ** 2 / np.prod([factorial(int(x)) for x in occ])
+        key = [0] * k
+        for c in cols:
+            if where[c] >= 0:
+                key[where[c]] += 1
+        hist[tuple(key)] = hist.get(tuple(key), 0.0) + w
+    inflated = cases.cfg3_interferometer(width=4, n_photons=2, measured=2)
+    want = oe.prob_dist_mixed(cases.oracle_eval(inflated), list(inflated.cod.inside))
+    total = sum(want.values())
+    assert sum(hist.values()) == pytest.approx(1.0, abs=1e-12)
+    assert max(abs(hist.get(key, 0.0) - v / total) for key, v in want.items()) <= 1e-12
