@@ -260,6 +260,122 @@ permanent_hist_kernel(const double2* __restrict__ V, int n, int m,
             if (hs[i] != 0.0) atomicAdd(&hist[i], hs[i]);
 }
 
+// Thread-per-configuration variant for few photons (2^(n-1) sign vectors are too few
+// to feed 32 lanes: the per-lane set-up would dominate).  Every THREAD owns a
+// contiguous range of ranks, keeps its column sums in registers and reads the
+// photon rows straight from shared memory (no submatrix gather).
+constexpr int PT_THREADS = 128;
+
+template <int NMAX>
+__global__ void __launch_bounds__(PT_THREADS)
+permanent_hist_thread_kernel(const double2* __restrict__ V, int n, int m,
+                             const long long* __restrict__ binom,
+                             const int* __restrict__ mode_stride, double scale,
+                             long long n_configs, int n_bins, double* __restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char pt_smem[];
+    double2* Vs = reinterpret_cast<double2*>(pt_smem);                 // [n][m]
+    double* hs = reinterpret_cast<double*>(Vs + n * m);
+    int* strides = reinterpret_cast<int*>(hs + (n_bins <= PH_SMEM_BINS ? n_bins : 0));
+    const bool smem_hist = n_bins <= PH_SMEM_BINS;
+    for (int i = threadIdx.x; i < n * m; i += blockDim.x) Vs[i] = V[i];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) strides[i] = mode_stride[i];
+    if (smem_hist) for (int i = threadIdx.x; i < n_bins; i += blockDim.x) hs[i] = 0.0;
+    __syncthreads();
+    const long long n_thr = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_t = (n_configs + n_thr - 1) / n_thr;
+    const long long r0 = tid * per_t, r1 = r0 + per_t < n_configs ? r0 + per_t : n_configs;
+    const long long total = 1ll << (n - 1);
+    const double pre = ldexp(1.0, 2 - 2 * n) * scale;
+    int cols[NMAX];
+    if (r0 < r1) {
+        long long r = r0;
+        int prev = 0;
+        #pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j < n) {
+                const int L = n - j - 1;
+                int v = prev;
+                for (; v < m - 1; ++v) {
+                    const long long cnt = binom[(long long)(m - v + L - 1) * (n + 1) + L];
+                    if (r < cnt) break;
+                    r -= cnt;
+                }
+                cols[j] = v; prev = v;
+            }
+        }
+    }
+    for (long long rk = r0; rk < r1; ++rk) {
+        // column sums for the all-plus sign vector, then the Gray-code walk
+        double2 v[NMAX];
+        #pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j < n) {
+                double2 s = make_double2(0.0, 0.0);
+                for (int i = 0; i < n; ++i) { const double2 a = Vs[i * m + cols[j]]; s.x += a.x; s.y += a.y; }
+                v[j] = s;
+            }
+        }
+        double sx = 0.0, sy = 0.0;
+        int sign = 1;
+        for (long long gi = 0; gi < total; ++gi) {
+            if (gi != 0) {
+                const int b = __ffsll(gi) - 1;
+                const bool now_neg = ((gi ^ (gi >> 1)) >> b) & 1;
+                const double f = now_neg ? -2.0 : 2.0;
+                const double2* vr = Vs + (b + 1) * m;
+                #pragma unroll
+                for (int j = 0; j < NMAX; ++j) {
+                    if (j < n) {
+                        const double2 a = vr[cols[j]];
+                        v[j].x = fma(f, a.x, v[j].x);
+                        v[j].y = fma(f, a.y, v[j].y);
+                    }
+                }
+                sign = -sign;
+            }
+            double px = v[0].x, py = v[0].y;
+            #pragma unroll
+            for (int j = 1; j < NMAX; ++j) {
+                if (j < n) {
+                    const double tx = px * v[j].x - py * v[j].y;
+                    py = px * v[j].y + py * v[j].x;
+                    px = tx;
+                }
+            }
+            sx += sign * px; sy += sign * py;
+        }
+        int bin = 0, run = 1;
+        double inv = 1.0;
+        #pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j < n) {
+                bin += strides[cols[j]];
+                if (j > 0) {
+                    run = cols[j - 1] == cols[j] ? run + 1 : 1;
+                    inv /= (double)run;
+                }
+            }
+        }
+        const double w = pre * (sx * sx + sy * sy) * inv;
+        if (w != 0.0) { if (smem_hist) atomicAdd(&hs[bin], w); else atomicAdd(&hist[bin], w); }
+        int jb = -1;
+        #pragma unroll
+        for (int j = 0; j < NMAX; ++j) if (j < n && cols[j] < m - 1) jb = j;
+        if (jb >= 0) {
+            int nv = 0;
+            #pragma unroll
+            for (int j = 0; j < NMAX; ++j) if (j == jb) nv = cols[j] + 1;
+            #pragma unroll
+            for (int j = 0; j < NMAX; ++j) if (j < n && j >= jb) cols[j] = nv;
+        }
+    }
+    __syncthreads();
+    if (smem_hist)
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+            if (hs[i] != 0.0) atomicAdd(&hist[i], hs[i]);
+}
+
 }  // namespace b2
 
 extern "C" int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
@@ -298,6 +414,27 @@ extern "C" int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
             (const double2*)v_dev, n, m, (const long long*)binom_dev, mode_stride_dev, scale,  \
             n_configs, n_bins, hist_dev);                                                      \
     } while (0)
+    if (n <= 8 && n_configs >= 4096) {
+        // few photons, many configurations: one thread per configuration
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(permanent_hist_thread_kernel<8>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_done = true;
+        }
+        const size_t smem_t = (size_t)(n * m) * sizeof(double2) +
+                              (size_t)(n_bins <= PH_SMEM_BINS ? n_bins : 0) * sizeof(double) +
+                              (size_t)m * sizeof(int);
+        long long tb = (n_configs + PT_THREADS * 8 - 1) / (PT_THREADS * 8);
+        const long long tcap = (long long)sms * 8;
+        if (tb > tcap) tb = tcap;
+        if (tb < 1) tb = 1;
+        permanent_hist_thread_kernel<8><<<(unsigned)tb, PT_THREADS, smem_t, s>>>(
+            (const double2*)v_dev, n, m, (const long long*)binom_dev, mode_stride_dev, scale,
+            n_configs, n_bins, hist_dev);
+        set_last_kernel("permanent_hist_thread");
+        return check_launch("b2_permanent_histogram");
+    }
     if (n <= 8) B2_PH_LAUNCH(8); else B2_PH_LAUNCH(16);
 #undef B2_PH_LAUNCH
     set_last_kernel("permanent_hist");
