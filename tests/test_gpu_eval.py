@@ -380,6 +380,32 @@ def test_lossy_distinguishable_permanents_match_tensor_network(shape):
         assert abs(tn.get(tuple(k), 0.0) - pm.get(tuple(k), 0.0)) <= 1e-10, (k, tn.get(k), pm.get(k))
 
 
+def test_lossy_permanents_beyond_tensor_network_reach_match_oracle_permanents():
+    """8 modes, 4 photons, loss, partial distinguishability, 4 measured (52 360
+    configurations over 32 modes; the tensor network would need 2^55 MACs): device
+    histogram == the same sum done in Python with the ORACLE's permanent."""
+    import itertools
+    from math import factorial
+    from cases import cfg3_interferometer
+    from oracle.permanent import npperm
+    from optyx_b200.core.backends import PermanentBackend
+    d = cfg3_interferometer(width=8, n_photons=4, measured=4, inflate=False)
+    got = PermanentBackend().prob_dist_measured(d)
+    V, where, k = PermanentBackend._photon_rows(d)
+    n, M = V.shape
+    want = {}
+    for cols in itertools.combinations_with_replacement(range(M), n):
+        key = [0] * k
+        for c in cols:
+            if where[c] >= 0:
+                key[where[c]] += 1
+        occ = np.bincount(cols, minlength=M)
+        w = abs(npperm(V[:, list(cols)])) ** 2 / np.prod([factorial(int(x)) for x in occ])
+        want[tuple(key)] = want.get(tuple(key), 0.0) + w
+    assert set(k_ for k_, v in want.items() if v > 1e-14) <= set(got)
+    assert max(abs(got.get(k_, 0.0) - v) for k_, v in want.items()) <= 1e-12
+
+
 def test_cfg3_full_size_through_permanents():
     """BASELINE cfg3 at its full size -- 12 modes, 6 photons, PhotonLoss(0.9) on every
     mode, partially distinguishable photons (internal dimension 2), 4 modes measured,

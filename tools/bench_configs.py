@@ -122,5 +122,26 @@ backend = B200Backend()
 batched("cfg5a_fusion_link_x1024",
         lambda j: cases.fusion_link((math.cos(j * (math.pi / 2) / 1023), math.sin(j * (math.pi / 2) / 1023)), "bell"))
 batched("cfg5b_fusion_teleport_x1024", lambda j: cases.fusion_teleport_input(j / 1024))
+def permanents(name, w, n, k, reps=5):
+    """cfg3 through PermanentBackend.prob_dist_measured (loss + partial distinguishability)."""
+    from math import comb
+    from optyx_b200.core.backends import PermanentBackend
+    d = cases.cfg3_interferometer(width=w, n_photons=n, measured=k, inflate=False)
+    pb = PermanentBackend()
+    pb.prob_dist_measured(d)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        p = pb.prob_dist_measured(cases.cfg3_interferometer(width=w, n_photons=n, measured=k, inflate=False))
+    t_e2e = (time.perf_counter() - t0) / reps
+    flops = pb.last_configs * (2 ** (n - 1)) * (8.0 * n + 2)
+    out[name] = {"modes": w, "photons": n, "measured": k, "output_modes": 4 * w,
+                 "configurations": pb.last_configs, "outcomes": len(p),
+                 "prob_total": float(sum(p.values())), "device_ms_per_eval": pb.last_kernel_ms,
+                 "e2e_ms_per_eval": t_e2e * 1e3,
+                 "fp64_tflops": flops / (pb.last_kernel_ms * 1e-3) / 1e12}
+    print(name, out[name], flush=True)
+
+
+permanents("cfg3_full_12mode_6photon_k4_permanents", 12, 6, 4)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
