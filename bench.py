@@ -68,12 +68,27 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()                 # nvidia-smi takes a moment to print its first line
+            while not self.lines and time.time() - t0 < 3.0:
+                time.sleep(0.01)
+            self.lines.clear()               # keep only samples taken under load
         except OSError:
             self.proc = None
         return self
+
+    def hold_load(self, fn, sync, seconds=0.3, min_samples=4):
+        """Keep the same kernels running (untimed) until enough samples exist: the
+        timed region itself can be shorter than one sampling period."""
+        t0 = time.time()
+        while self.proc is not None and (len(self.lines) < min_samples or time.time() - t0 < seconds):
+            for _ in range(20):
+                fn()
+            sync()
+            if time.time() - t0 > 3.0:
+                break
 
     def _read(self):
         for line in self.proc.stdout:
@@ -216,6 +231,9 @@ def main():
         step_fn()
     barrier()
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):         # the sampler start-up left the GPU idle
+            step_fn()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -237,6 +255,7 @@ def main():
         k1.record()
         torch.cuda.synchronize()
         dom_secs = k0.elapsed_time(k1) * 1e-3 / args.steps
+        clocks.hold_load(step_fn, torch.cuda.synchronize)
     if world > 1:
         tt = torch.tensor([secs], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
