@@ -28,7 +28,7 @@ torch.cuda.synchronize()
 got = dC.cpu().numpy().astype(np.complex128)
 want = A.astype(np.complex128) @ B.astype(np.complex128)
 err = np.abs(got - want)
-print("variant", os.environ.get("B2_G4_VARIANT"), "max err", err.max(), "scale", np.abs(want).max())
+print("max err", err.max(), "scale", np.abs(want).max())
 if err.max() > 1e-4:
     print("got[0,:4]", got[0, :4])
     print("want[0,:4]", want[0, :4])
