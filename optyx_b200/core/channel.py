@@ -79,19 +79,13 @@ class Diagram(diagram.Diagram):
     def inflate(self, d: int) -> "Diagram":
         """channel.py:260-275"""
         assert isinstance(d, int) and d > 0
-        res = Diagram.id(self.dom.inflate(d))
-        for left, box, right in self.layers():
-            res = res >> (Diagram.id(left.inflate(d)) @ box.inflate(d)
-                          @ Diagram.id(right.inflate(d)))
-        return res
+        return self._apply_functor(lambda ty: ty.inflate(d), lambda box: box.inflate(d),
+                                   factory=Diagram)
 
     def double(self) -> diagram.Diagram:
         """channel.py:277-285: functor ob -> ob.double, box -> box.double()."""
-        res = diagram.Diagram.id(self.dom.double())
-        for left, box, right in self.layers():
-            res = res >> (diagram.Diagram.id(left.double()) @ box.double()
-                          @ diagram.Diagram.id(right.double()))
-        return res
+        return self._apply_functor(lambda ty: ty.double(), lambda box: box.double(),
+                                   factory=diagram.Diagram)
 
     @property
     def is_pure(self) -> bool:

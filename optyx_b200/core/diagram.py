@@ -197,9 +197,27 @@ class Diagram:
             offsets.extend(o + off for o in d.offsets)
         return self.diagram_factory(self.cod, self.dom, boxes, offsets)
 
+    def _apply_functor(self, on_ob, on_box, factory=None) -> "Diagram":
+        """``F(self)`` for a monoidal functor given on objects and boxes, built in one
+        pass: layer ``left @ box @ right`` becomes ``F(box)`` whiskered at offset
+        ``len(F(left))`` (the same diagram as composing ``id @ F(box) @ id`` layer by
+        layer, without the quadratic list copies)."""
+        factory = factory or self.diagram_factory
+        boxes, offsets = [], []
+        for left, box, right in self.layers():
+            image = on_box(box)
+            shift = len(on_ob(left))
+            boxes.extend(image.boxes)
+            offsets.extend(o + shift for o in image.offsets)
+        return factory(on_ob(self.dom), on_ob(self.cod), boxes, offsets)
+
     def conjugate(self) -> "Diagram":
         """Per-box conjugation functor, diagram.py:277-284."""
-        res = self.id(self.dom)
+        images = [box.conjugate() for box in self.boxes]
+        if all(im.dom == box.dom and im.cod == box.cod for im, box in zip(images, self.boxes)):
+            it = iter(images)
+            return self._apply_functor(lambda ty: ty, lambda box: next(it))
+        res = self.id(self.dom)           # a box whose conjugate changes type (diagram.py:506-519)
         for left, box, right in self.layers():
             res = res >> (self.id(left) @ box.conjugate() @ self.id(right))
         return res
@@ -210,10 +228,7 @@ class Diagram:
 
         def ob(x: Ty) -> Ty:
             return Ty._make(sum(((o,) * d if o == "mode" else (o,) for o in x.inside), ()))
-        res = Diagram.id(ob(self.dom))
-        for left, box, right in self.layers():
-            res = res >> (Diagram.id(ob(left)) @ box.inflate(d) @ Diagram.id(ob(right)))
-        return res
+        return self._apply_functor(ob, lambda box: box.inflate(d), factory=Diagram)
 
     # ---- symmetric / frobenius structure -------------------------------------
     @classmethod
