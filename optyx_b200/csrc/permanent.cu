@@ -425,8 +425,13 @@ extern "C" int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
         const size_t smem_t = (size_t)(n * m) * sizeof(double2) +
                               (size_t)(n_bins <= PH_SMEM_BINS ? n_bins : 0) * sizeof(double) +
                               (size_t)m * sizeof(int);
-        long long tb = (n_configs + PT_THREADS * 8 - 1) / (PT_THREADS * 8);
-        const long long tcap = (long long)sms * 8;
+        // one resident wave, every thread an equal share of the ranks
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, permanent_hist_thread_kernel<8>,
+                                                          PT_THREADS, smem_t) != cudaSuccess || occ < 1)
+            occ = 1;
+        long long tb = (n_configs + PT_THREADS - 1) / PT_THREADS;
+        const long long tcap = (long long)sms * occ;
         if (tb > tcap) tb = tcap;
         if (tb < 1) tb = 1;
         permanent_hist_thread_kernel<8><<<(unsigned)tb, PT_THREADS, smem_t, s>>>(
