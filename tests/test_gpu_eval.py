@@ -424,6 +424,33 @@ def test_cfg3_full_size_through_permanents():
     assert q[(0, 0, 0, 0)] > p[(0, 0, 0, 0)]          # more loss -> more often nothing detected
 
 
+def test_edge_case_diagrams():
+    """Degenerate networks: identity (no leaves), scalar only, a single box,
+    disconnected components (outer product), an identically zero result."""
+    from optyx_b200 import photonic, qubits
+    from optyx_b200.core import zw
+    cases_ = {
+        "identity": qubits.Id(2),
+        "scalar": qubits.Scalar(0.25 + 0.5j),
+        "single_box": qubits.H(),
+        "outer_product": qubits.Ket(0) @ qubits.Ket(1) @ qubits.H(),
+        "zero": zw.Create(1) >> zw.Select(0),                  # test_zw.py:275-280 (bone)
+        "two_components": photonic.Create(1) @ photonic.Create(2),
+    }
+    for name, d in cases_.items():
+        want = oracle_eval(d)
+        got = d.eval(B200Backend()).tensor.array if hasattr(d, "eval") else None
+        if got is None:
+            from optyx_b200 import executor
+            got = executor.evaluate(d.to_network()).cpu().numpy()
+        assert np.shape(got) == np.shape(want), name
+        assert _close(np.asarray(got), np.asarray(want), TOL128), name
+    # an exactly-zero tensor: prob_dist raises like the reference (backends.py:231-232)
+    r = EvalResult(ResultTensor((), (3,), np.zeros(3, dtype=complex)), ("mode",), StateType.AMP)
+    with pytest.raises(ValueError):
+        r.prob_dist()
+
+
 def test_quimb_adapter_path_on_device():
     """INTEGRATION.md section 4, adapter path: dense tensors with index names (what
     ``term.to_quimb()`` yields) contracted by the CUDA kernels."""

@@ -16,7 +16,9 @@ if len(sys.argv) > 1 and sys.argv[1] in ("cfg3", "cfg1"):
     net = cases.compile_channel(cases.cfg3_interferometer(width=6, n_photons=3, measured=2)
                                 if sys.argv[1] == "cfg3" else
                                 cases.cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)))
-    plan = executor.get_plan(net)
+    import numpy as np
+    dtype = np.complex64 if os.environ.get("B2_DTYPE") == "c64" else np.complex128
+    plan = executor.get_plan(net, dtype=dtype)
     for g in plan.small_groups:                      # time every step on its own
         for k in g.steps:
             plan.steps[k].grouped = False
@@ -59,7 +61,7 @@ for st in plan.steps:
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3
-    ideal = max(st.bytes / 6.556e12, 8 * st.macs / 37e12)
+    ideal = max(st.bytes / 6.556e12, 8 * st.macs / (37e12 if plan.dtype.itemsize == 16 else 367e12))
     rows.append((t, ideal, st, sess.lib.b2_last_kernel().decode()))
 tot = sum(r[0] for r in rows)
 print(f"nslices {plan.nslices} per-slice steps {len(rows)} measured {tot*1e3:.1f} ms "
