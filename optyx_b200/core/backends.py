@@ -323,8 +323,15 @@ class B200Backend(AbstractBackend):
             import dataclasses
             try:
                 with mp.get_context("fork").Pool(workers) as pool:
-                    chunk = max(1, (count - 1) // (workers * 4))
-                    for j, res in pool.imap_unordered(_compile_job, range(1, count), chunksize=chunk):
+                    results = pool.imap_unordered(_compile_job, range(1, count))   # one job = ~10 ms
+                    for _ in range(1, count):
+                        try:
+                            # a forked child of a multi-threaded parent can, rarely, inherit a
+                            # held lock: never wait for it, finish serially instead
+                            j, res = results.next(timeout=120.0)
+                        except mp.TimeoutError:
+                            pool.terminate()
+                            break
                         if isinstance(res, tuple):       # (params of the value leaves, scalar)
                             it = iter(res[0])
                             leaves = [l if l.params is None else dataclasses.replace(l, params=next(it))
