@@ -6,7 +6,7 @@ sm_100a CUDA behind a C ABI, with the host-side mirror of the reference's
 diagram / channel / backend interface needed to drive it.
 """
 from .core.channel import bit, mode, qubit, qmode, Channel, Diagram  # noqa: F401
-from .core.backends import B200Backend, EvalResult, StateType  # noqa: F401
+from .core.backends import B200Backend, EvalResult, PermanentBackend, StateType  # noqa: F401
 
 __all__ = ["bit", "mode", "qubit", "qmode", "Channel", "Diagram", "B200Backend",
-           "EvalResult", "StateType"]
+           "PermanentBackend", "EvalResult", "StateType"]
