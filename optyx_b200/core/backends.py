@@ -12,11 +12,12 @@ the device (csrc/probs.cu) when the result is still resident there.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 from abc import ABC, abstractmethod
 from collections import defaultdict
 from dataclasses import dataclass, field
 from enum import Enum
-from typing import Any, Optional
+from typing import Any, Iterable, Optional
 
 import numpy as np
 
@@ -159,8 +160,7 @@ class EvalResult:
             return {}
         # keys as tuples of Python ints (hash/compare equal to the reference's
         # tuples of numpy ints); .tolist() makes the dict build ~10x faster
-        multi = np.vstack(np.unravel_index(flat, self.tensor.array.shape)).T.tolist()
-        return dict(zip(map(tuple, multi), p_h[flat].tolist()))
+        return dict(zip(_index_tuples(flat, nz_h, self.tensor.array.shape), p_h[flat].tolist()))
 
     def _prob_dist_mixed(self) -> dict:
         """backends.py:306-356 with the diagonal partial trace on the device."""
@@ -198,8 +198,7 @@ class EvalResult:
         flat = np.flatnonzero(seen_h)
         probs = defaultdict(float)
         if flat.size:
-            multi = np.vstack(np.unravel_index(flat, meas_shape)).T.tolist()
-            probs.update(zip(map(tuple, multi), p_h[flat].tolist()))
+            probs.update(zip(_index_tuples(flat, seen_h, meas_shape), p_h[flat].tolist()))
         return probs
 
     def _resident(self):
@@ -217,6 +216,18 @@ class EvalResult:
 def _torch():
     import torch
     return torch
+
+
+def _index_tuples(flat: np.ndarray, mask: np.ndarray, shape) -> Iterable[tuple]:
+    """Multi-indices (tuples of Python ints, C order) of the flat positions
+    ``flat == flatnonzero(mask)``.  A dense selection (a measured register where
+    every key was seen: 2^20 keys for 20 measured qubits) walks
+    ``itertools.product`` -- C-speed tuple construction -- filtered by the mask;
+    a sparse one unravels only the selected positions."""
+    if flat.size * 8 >= mask.size:
+        keys = itertools.product(*map(range, shape))
+        return keys if flat.size == mask.size else itertools.compress(keys, mask.tolist())
+    return map(tuple, np.vstack(np.unravel_index(flat, shape)).T.tolist())
 
 
 _BATCH_JOB = None        # (backend, make) inherited by the fork pool of compile_batch

@@ -16,10 +16,13 @@
 // consecutive rows = consecutive addresses.  No accumulator staging, at most
 // one barrier pair per tile, every load independent of every other.
 #include "b2_common.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
-constexpr int FM_THREADS = 256, FM_TMAX = 16384, FM_MAXM = 1024, FM_MAXN = 64, FM_U = 16;
+constexpr int FM_THREADS = 256, FM_TMAX = 65536, FM_MAXM = 1024, FM_MAXN = 64, FM_U = 16;
+constexpr int FM_STREAM_STORES = 1, FM_ROUND_ROBIN = 2, FM_DEFAULT_FLAGS = FM_STREAM_STORES | FM_ROUND_ROBIN,
+              FM_DEFAULT_RM = 4;
 constexpr int FM_KMAX = 16, FM_MAXTB = 64, FM_BTILE_BYTES = 32 * 1024, FM_SMEM_MAX = 64 * 1024;
 
 struct fm_desc {
@@ -30,13 +33,13 @@ struct fm_desc {
     long long sa[B2_MAX_MODES], sb[B2_MAX_MODES], sc[B2_MAX_MODES];
 };
 
-template <typename T, int KP, int RMAX>
+template <typename T, int KP, int RMAX, int RM = 1>
 __global__ void __launch_bounds__(FM_THREADS)
 contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                     const typename cplx<T>::type* __restrict__ A,
                     const typename cplx<T>::type* __restrict__ B,
                     typename cplx<T>::type* __restrict__ Cout, T alpha_re, T alpha_im,
-                    int accumulate) {
+                    int accumulate, int flags) {
     using C = typename cplx<T>::type;
     extern __shared__ __align__(16) unsigned char fm_smem[];
     long long* row_a = reinterpret_cast<long long*>(fm_smem);      // [TM] A offset of row i
@@ -99,14 +102,19 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
     }
 
     // contiguous range of outer tiles + odometer (outer mode 0 = fastest in C)
+    // (FM_ROUND_ROBIN: tile t = blockIdx + i * grid instead -- the CTAs resident at
+    // any moment then write NEIGHBOURING tiles, i.e. a few long contiguous runs of C
+    // instead of grid x TN short ones scattered over the whole output)
+    const bool rr = RMAX == 1 && (flags & FM_ROUND_ROBIN);
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const long long t0 = (long long)blockIdx.x * per;
-    const long long t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    const long long t0 = rr ? (long long)blockIdx.x : (long long)blockIdx.x * per;
+    const long long t1 = rr ? n_tiles : (t0 + per < n_tiles ? t0 + per : n_tiles);
+    const long long t_step = rr ? (long long)gridDim.x : (long long)RMAX;
     if (t0 >= t1) return;
     int cnt[B2_MAX_MODES];
     long long oa = 0, ob = 0, oc = 0;
-    {
-        long long rem = t0;
+    auto decode = [&](long long rem) {
+        oa = ob = oc = 0;
         for (int m = 0; m < g.n_outer; ++m) {
             const long long d = g.dim[m];
             const long long q = rem / d;
@@ -115,7 +123,8 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             cnt[m] = x;
             oa += x * g.sa[m]; ob += x * g.sb[m]; oc += x * g.sc[m];
         }
-    }
+    };
+    decode(t0);
     __syncthreads();
 
     const int n_jg = (g.TN + FM_U - 1) / FM_U;
@@ -140,13 +149,14 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             cnt[m] = 0;
         }
     };
-    for (long long t = t0; t < t1; t += R) {
-        const int nt = (int)(t1 - t < R ? t1 - t : R);
+    for (long long t = t0; t < t1; t += t_step) {
+        const int nt = rr ? 1 : (int)(t1 - t < R ? t1 - t : R);
         long long oa_r[RMAX], oc_r[RMAX];
+        if (rr && t != t0) decode(t);
         #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             if (r < nt) {
-                if (t + r != t0) advance();
+                if (!rr && t + r != t0) advance();
                 oa_r[r] = oa; oc_r[r] = oc;
             } else { oa_r[r] = oa; oc_r[r] = oc; }
         }
@@ -159,6 +169,67 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             }
             __syncthreads();
         }
+        if constexpr (RM > 1) {
+            // RM rows per thread (rows i, i + S, ..., S = TM / RM; lanes = consecutive
+            // rows): every B value read from shared memory feeds RM outputs.  The LSU
+            // data pipe -- broadcast LDS of B plus the STG of C -- is this kernel's
+            // busiest unit (ncu: 67 % with RM = 1, 28 % of it the B reads), not HBM and
+            // not the FP64 pipe.  Host guarantees TB == 1 and TM % RM == 0.
+            const int S = g.TM / RM;
+            const int n_slots = S * n_jg;
+            int prev_i = -1;
+            C a[RM][KP];
+            long long pm[RM];
+            C* cp = Cout + oc_r[0];
+            for (int w = tid; w < n_slots; w += FM_THREADS) {
+                const int jg = w / S, i = w - jg * S;
+                if (i != prev_i) {                       // S == FM_THREADS: once per tile
+                    #pragma unroll
+                    for (int q = 0; q < RM; ++q) {
+                        const C* ap = A + oa_r[0] + row_a[i + q * S];
+                        pm[q] = pos_m[i + q * S];
+                        #pragma unroll
+                        for (int k = 0; k < KP; ++k) a[q][k] = (k < g.K) ? ap[k_a[k]] : zero;
+                    }
+                    prev_i = i;
+                }
+                const int j0 = jg * FM_U;
+                const int j1 = j0 + FM_U < g.TN ? j0 + FM_U : g.TN;
+                #pragma unroll 2
+                for (int j = j0; j < j1; ++j) {
+                    C b[KP];
+                    #pragma unroll
+                    for (int k = 0; k < KP; ++k) b[k] = Bs[k * bplane + j];
+                    const long long pn = pos_n[j];
+                    #pragma unroll
+                    for (int q = 0; q < RM; ++q) {
+                        C acc = zero;
+                        if constexpr (KP >= 4) {
+                            C acc2 = zero;
+                            #pragma unroll
+                            for (int k = 0; k < KP; k += 2) {
+                                cfma(acc, a[q][k], b[k]);
+                                cfma(acc2, a[q][k + 1], b[k + 1]);
+                            }
+                            acc.x += acc2.x; acc.y += acc2.y;
+                        } else {
+                            #pragma unroll
+                            for (int k = 0; k < KP; ++k) cfma(acc, a[q][k], b[k]);
+                        }
+                        C res;
+                        if (unit_alpha) res = acc;
+                        else {
+                            res.x = alpha_re * acc.x - alpha_im * acc.y;
+                            res.y = alpha_re * acc.y + alpha_im * acc.x;
+                        }
+                        C* dst = cp + pm[q] + pn;
+                        if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
+                        if (flags & FM_STREAM_STORES) __stcs(dst, res);
+                        else *dst = res;
+                    }
+                }
+            }
+        } else
         for (int w = tid; w < n_items; w += FM_THREADS) {
             const int jg = w / g.TM, i = w - jg * g.TM;       // lanes = consecutive rows
             const long long ra = row_a[i], pm = pos_m[i];
@@ -201,11 +272,38 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                     }
                     C* dst = cp + pos_n[j];
                     if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
-                    *dst = res;
+                    if (flags & FM_STREAM_STORES) __stcs(dst, res);      // written once, never re-read
+                    else *dst = res;
                 }
             }
         }
     }
+}
+
+// Tile limits and kernel flags.  The defaults are the measured best; the
+// environment overrides exist for tools/tune_fma.py (B2_FMA_TUNE=1 re-reads them
+// on every launch so that one process can sweep configurations).
+struct fm_tune { int tmax, maxm, maxn, flags, grid_mult, rm; };
+static fm_tune tune_defaults() { return fm_tune{FM_TMAX, FM_MAXM, FM_MAXN, FM_DEFAULT_FLAGS, 0, FM_DEFAULT_RM}; }
+static fm_tune get_tune() {
+    static int mode = -1;            // 0: defaults, 1: re-read every launch
+    static fm_tune cached = tune_defaults();
+    if (mode == 0) return cached;
+    if (mode < 0) mode = getenv("B2_FMA_TUNE") ? 1 : 0;
+    if (mode == 0) return cached;
+    fm_tune t = tune_defaults();
+    auto rd = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
+    t.tmax = rd("B2_FMA_TMAX", t.tmax);
+    t.maxm = rd("B2_FMA_MAXM", t.maxm);
+    t.maxn = rd("B2_FMA_MAXN", t.maxn);
+    t.flags = rd("B2_FMA_FLAGS", t.flags);
+    t.grid_mult = rd("B2_FMA_GRID", t.grid_mult);
+    t.rm = rd("B2_FMA_RM", t.rm);
+    if (t.rm != 2 && t.rm != 4) t.rm = 1;
+    if (t.maxm > 1024) t.maxm = 1024;
+    if (t.maxn > 64) t.maxn = 64;
+    if (t.tmax > 65536) t.tmax = 65536;
+    return t;
 }
 
 // Classify the modes of the direct-kernel descriptor and build the tile.
@@ -244,7 +342,8 @@ static void refine_modes(const b2_modes& in, b2_modes& out) {
 }
 
 static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool swap_ab,
-                     size_t elem_bytes) {
+                     size_t elem_bytes, const fm_tune& tn_) {
+    const int FM_TMAX = tn_.tmax, FM_MAXM = tn_.maxm, FM_MAXN = tn_.maxn;
     const int no = md.n_out;
     long long K = 1;
     for (int m = 0; m < md.n_red; ++m) K *= md.dim[no + m];
@@ -340,7 +439,7 @@ static bool make_fma(const b2_modes& md, fm_desc& d, long long& n_tiles, bool sw
 
 template <typename T>
 int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void* b, void* c,
-                 double ar, double ai, int accumulate, cudaStream_t s) {
+                 double ar, double ai, int accumulate, cudaStream_t s, const fm_tune& tune) {
     using C = typename cplx<T>::type;
     int sms = num_sms();
     if (sms <= 0) return 1;
@@ -351,11 +450,12 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     if (smem > (size_t)FM_SMEM_MAX) { set_error("fma: tile tables need %zu B of shared memory", smem); return 1; }
     const C* A = (const C*)a; const C* B = (const C*)b; C* Cc = (C*)c;
     // tables (<= 21 KB) + the B block (<= 32 KB) can exceed the 48 KB default
-#define B2_FMA_LAUNCH_R(KPV, RV)                                                             \
+#define B2_FMA_LAUNCH_R(KPV, RV) B2_FMA_LAUNCH_RM(KPV, RV, 1)
+#define B2_FMA_LAUNCH_RM(KPV, RV, RMV)                                                       \
     do {                                                                                     \
         static bool attr_done = false;                                                       \
         if (!attr_done) {                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV, RV>,            \
+            cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV, RV, RMV>,       \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  FM_SMEM_MAX);                               \
             if (e != cudaSuccess) {                                                          \
@@ -368,20 +468,30 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
            of the tiles; a partial second wave would idle most of the GPU) */           \
         int occ = 0;                                                                         \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
-                &occ, contract_fma_kernel<T, KPV, RV>, FM_THREADS, smem) != cudaSuccess ||   \
+                &occ, contract_fma_kernel<T, KPV, RV, RMV>, FM_THREADS, smem) != cudaSuccess ||\
             occ < 1)                                                                         \
             occ = 1;                                                                         \
         long long blocks = n_tiles;                                                          \
+        if (tune.grid_mult > 0 && tune.grid_mult < occ) occ = tune.grid_mult;                \
         const long long cap = (long long)sms * occ;                                          \
         if (blocks > cap) blocks = cap;                                                      \
-        contract_fma_kernel<T, KPV, RV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(          \
-            d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate);                                 \
+        contract_fma_kernel<T, KPV, RV, RMV><<<(unsigned)blocks, FM_THREADS, smem, s>>>(     \
+            d, n_tiles, A, B, Cc, (T)ar, (T)ai, accumulate, tune.flags);                     \
     } while (0)
     // several tiles in flight per thread only where one item is little work
     const bool narrow = d.b_static && d.TN <= 8;
+    // several rows per thread (B reuse) for wide tiles without batch modes inside
+    int rm = 1;
+    if (!narrow && d.TB == 1 && d.TN >= 8) {
+        rm = tune.rm;
+        while (rm > 1 && (d.TM % (32 * rm) != 0)) rm >>= 1;
+    }
 #define B2_FMA_LAUNCH(KPV, RV)                                                               \
     do {                                                                                     \
-        if (narrow) B2_FMA_LAUNCH_R(KPV, RV); else B2_FMA_LAUNCH_R(KPV, 1);                  \
+        if (narrow) B2_FMA_LAUNCH_R(KPV, RV);                                                \
+        else if (rm == 4) B2_FMA_LAUNCH_RM(KPV, 1, 4);                                       \
+        else if (rm == 2) B2_FMA_LAUNCH_RM(KPV, 1, 2);                                       \
+        else B2_FMA_LAUNCH_R(KPV, 1);                                                        \
     } while (0)
     switch (KP) {
     case 1: B2_FMA_LAUNCH(1, 4); break;
@@ -391,6 +501,7 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
     default: B2_FMA_LAUNCH_R(16, 1); break;
     }
 #undef B2_FMA_LAUNCH_R
+#undef B2_FMA_LAUNCH_RM
 #undef B2_FMA_LAUNCH
     return check_launch("b2_contract_direct(fma)");
 }
@@ -411,9 +522,10 @@ int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double
     fm_desc d, d2;
     long long n_tiles = 0, n_tiles2 = 0;
     bool swap_ab = fine.sa[fastest] == 0;
-    bool ok = make_fma(fine, d, n_tiles, swap_ab, eb);
+    const fm_tune tune = get_tune();
+    bool ok = make_fma(fine, d, n_tiles, swap_ab, eb, tune);
     if (!ok || d.TM < 64) {
-        const bool ok2 = make_fma(fine, d2, n_tiles2, !swap_ab, eb);
+        const bool ok2 = make_fma(fine, d2, n_tiles2, !swap_ab, eb, tune);
         if (ok2 && (!ok || d2.TM > d.TM)) { d = d2; n_tiles = n_tiles2; swap_ab = !swap_ab; ok = true; }
     }
     if (!ok) return 0;
@@ -422,13 +534,13 @@ int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double
     handled = true;
     {
         static thread_local char info[96];
-        snprintf(info, sizeof(info), "fma TM=%d TN=%d TB=%d K=%d tiles=%lld bstatic=%d swap=%d",
-                 d.TM, d.TN, d.TB, d.K, n_tiles, d.b_static, (int)swap_ab);
+        snprintf(info, sizeof(info), "fma TM=%d TN=%d TB=%d K=%d tiles=%lld bstatic=%d swap=%d rm=%d",
+                 d.TM, d.TN, d.TB, d.K, n_tiles, d.b_static, (int)swap_ab, tune.rm);
         set_last_kernel(info);
     }
     if (dtype == B2_C128)
-        return launch_fma_t<double>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);
-    return launch_fma_t<float>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s);
+        return launch_fma_t<double>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s, tune);
+    return launch_fma_t<float>(d, n_tiles, pa, pb, c, ar, ai, accumulate, s, tune);
 }
 
 }  // namespace b2
