@@ -269,25 +269,34 @@ def main():
         secs = float(tt.item())
     value = world * args.steps / secs
 
-    # ---- e2e: the user call, host objects in, host numpy out
-    backend = B200Backend(target_size=target, trials=16 if target else 8)
-    res = None
-    for _ in range(3):                   # warm-up: plan cache + the pinned result
-        res = diagram.eval(backend)      # buffers of torch's caching host allocator
-    n_e2e = max(2, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        d_i = factory()
-        res = d_i.eval(backend)
-    torch.cuda.synchronize()
-    e2e_secs = (time.perf_counter() - t0) / n_e2e
-    if world > 1:
-        tt = torch.tensor([e2e_secs], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_secs = float(tt.item())
+    # ---- e2e: the user call, host objects in, host numpy out.  Measured twice: with
+    # the product default (a large result is scanned on the device and, when sparse,
+    # handed over as its non-zero list) and with the dense device->host copy forced.
+    def time_e2e(backend):
+        res = None
+        for _ in range(3):                   # warm-up: plan cache + the pinned result
+            res = diagram.eval(backend)      # buffers of torch's caching host allocator
+        n_e2e = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            d_i = factory()
+            res = d_i.eval(backend)
+        torch.cuda.synchronize()
+        e2e = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tt = torch.tensor([e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = float(tt.item())
+        return e2e, dict(B200Backend.last_d2h), res
+    e2e_secs, d2h_info, res = time_e2e(B200Backend(target_size=target, trials=16 if target else 8))
+    del res
+    e2e_dense_secs, d2h_dense_info, res = time_e2e(
+        B200Backend(target_size=target, trials=16 if target else 8, sparse_d2h=False))
     h2d = int(sess.desc_dev.numel() + sess.params_host.numel() * 16)
-    d2h = int(res.tensor.array.nbytes)
+    d2h = int(d2h_info["bytes"])
+    d2h_dense = int(res.tensor.array.nbytes)
+    del res
 
     peaks = {}
     try:
@@ -334,7 +343,16 @@ def main():
                    "host_compile_ms": t_compile * 1e3, "host_plan_ms": t_plan * 1e3},
         "clocks": clocks.summary(),
         "e2e": {"value": world / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_eval": e2e_secs * 1e3},
+                "d2h_bytes_per_step": d2h, "ms_per_eval": e2e_secs * 1e3,
+                "d2h": d2h_info.get("mode"), "result_bytes": d2h_dense,
+                "note": "host diagram -> host numpy array through diagram.eval(B200Backend()); "
+                        "'sparse' = the device scans the result and copies only its non-zero "
+                        "(index, value) list, scattered into a zero-filled host array"},
+        "e2e_dense_d2h": {"value": world / e2e_dense_secs, "unit": UNIT,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
+                          "ms_per_eval": e2e_dense_secs * 1e3,
+                          "note": "same call with B200Backend(sparse_d2h=False): the whole "
+                                  "result crosses PCIe"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "plan_roofline": plan_roofline,

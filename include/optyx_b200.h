@@ -190,6 +190,17 @@ int b2_probs_dm(int32_t ndim, const int32_t* dims, const int32_t* axis_kind,
                 const void* t_dev, double* p_dev, uint8_t* seen_dev,
                 double* max_imag_dev, int32_t dtype, void* stream);
 
+/* (4b) result hand-over for sparse results (the array EvalResult wraps,
+ * backends.py:480-494, is dense on the host; most of a GHZ / Clifford density
+ * tensor or a photon-number-conserving amplitude tensor is exact zeros): one
+ * read pass appends (flat C-order index, value) of every entry with re != 0 or
+ * im != 0 (numpy's flatnonzero test) to idx_dev / val_dev (cap entries each, unordered) and counts them in
+ * count_dev[0] (zeroed by this call).  count > cap means the list overflowed
+ * and its contents are incomplete: the caller copies the tensor densely.      */
+int b2_compact_nonzero(int64_t n, const void* t_dev, int32_t dtype, int64_t cap,
+                       int64_t* idx_dev, void* val_dev, uint64_t* count_dev,
+                       void* stream);
+
 /* (5) permanents: amplitudes of a pure linear-optical circuit (the reference's
  * PermanentBackend, backends.py:1019-1098; Matrix.eval path.py:345-384; npperm
  * path.py:141-163).  u_dev: m x m single-particle matrix (complex128, row

@@ -18,7 +18,7 @@ STAMP = os.path.join(LIBDIR, "liboptyx_b200.stamp")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["abi.cu", "leaf_build.cu", "contract_direct.cu", "contract_gemm.cu", "contract_gemm_c64.cu", "contract_ctile.cu", "contract_fma.cu", "contract_small.cu", "permanent.cu",
-           "probs.cu"]
+           "probs.cu", "compact.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

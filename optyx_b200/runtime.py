@@ -20,7 +20,7 @@ MAX_RED_DIRECT = 16
 EXPORTS = [
     "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
     "b2_contract_direct", "b2_contract_gemm", "b2_contract_small_groups", "b2_axpy", "b2_fill_zero",
-    "b2_probs_amp", "b2_probs_dm", "b2_permanent_amplitudes", "b2_permanent_histogram",
+    "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
     "b2_fp64_peak_kernel",
 ]
 
@@ -119,6 +119,7 @@ def load():
     lib.b2_fill_zero.argtypes = [i64, vp, i32, vp]
     lib.b2_probs_amp.argtypes = [i64, vp, vp, vp, i32, vp]
     lib.b2_probs_dm.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, vp, i32, vp]
+    lib.b2_compact_nonzero.argtypes = [i64, vp, i32, i64, vp, vp, vp, vp]
     lib.b2_permanent_amplitudes.argtypes = [vp, i32, vp, i32, vp, vp, i64, vp, vp]
     lib.b2_permanent_histogram.argtypes = [vp, i32, i32, vp, vp, dbl, i64, i32, vp, vp]
     lib.b2_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]

@@ -481,3 +481,46 @@ def test_cfg3_standard_size_properties():
     assert sum(p.values()) == pytest.approx(1.0, abs=1e-9)
     assert all(v >= -1e-12 for v in p.values())
     assert all(sum(int(i) for i in k) <= 2 for k, v in p.items() if v > 1e-12)
+
+
+def test_sparse_result_hand_over_equals_dense_copy(monkeypatch):
+    """B200Backend._to_host: a large, mostly-zero result crosses PCIe as its list of
+    non-zero entries (b2_compact_nonzero) and equals the dense copy; a dense result,
+    or one below the size threshold, takes the dense copy."""
+    import torch
+    rng = np.random.default_rng(5)
+    for dtype, tdtype in ((np.complex128, torch.complex128), (np.complex64, torch.complex64)):
+        host = np.zeros((2,) * 22, dtype=dtype)                # 64 MB / 32 MB
+        flat = host.reshape(-1)
+        where = rng.choice(flat.size, size=1000, replace=False)
+        flat[where] = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(dtype)
+        dev = torch.from_numpy(host).cuda()
+        got = B200Backend(dtype=np.dtype(dtype).name)._to_host(dev)
+        assert B200Backend.last_d2h["mode"] == "sparse" and B200Backend.last_d2h["nonzeros"] == 1000
+        assert B200Backend.last_d2h["bytes"] == 8 + 1000 * (8 + host.itemsize)
+        assert got.shape == host.shape and got.dtype == host.dtype and got.flags.c_contiguous
+        assert np.array_equal(got, host)
+        flat[::3] = 1.0                                        # a third non-zero: dense copy
+        dev = torch.from_numpy(host).cuda()
+        got = B200Backend(dtype=np.dtype(dtype).name)._to_host(dev)
+        assert B200Backend.last_d2h["mode"] == "dense"
+        assert np.array_equal(got, host)
+        got = B200Backend(sparse_d2h=False)._to_host(dev)
+        assert B200Backend.last_d2h == {"mode": "dense", "bytes": host.nbytes}
+        del dev
+    # through eval: both hand-overs return the same array
+    d = ghz(20, open_qubits=11, noise=0.95)                   # (2,)^22: 64 MB
+    a = d.eval(B200Backend()).tensor.array
+    b = d.eval(B200Backend(sparse_d2h=False)).tensor.array
+    assert a.shape == b.shape == (2,) * 22 and _close(a, b, 1e-13)
+    ghz(8, open_qubits=4).eval(B200Backend())
+    assert B200Backend.last_d2h["mode"] == "dense"            # below the size threshold
+    monkeypatch.setattr(B200Backend, "SPARSE_MIN_BYTES", 0)   # scan small results too
+    modes = {}
+    for name in ("cfg1_4mode", "cfg1_6mode", "ghz8_noisy_measured", "mzi_chip_pure",
+                 "clifford_t_8x6", "fusion_ii"):
+        a = CASES[name]().eval(B200Backend()).tensor.array
+        modes[name] = B200Backend.last_d2h["mode"]
+        b = CASES[name]().eval(B200Backend(sparse_d2h=False)).tensor.array
+        # two evals differ in the last bits where split-K atomics order the sums
+        assert a.shape == b.shape and _close(a, b, 1e-13), (name, modes)

@@ -334,3 +334,41 @@ def test_fp64_peak_microbench_runs():
         rt.check(lib.b2_fp64_peak_kernel(kind, 64, sink.data_ptr(), C.byref(flops), 0))
         assert flops.value > 0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,fill", [(1, 1.0), (31, 0.5), (100_003, 0.01), (1 << 20, 0.0),
+                                    (1 << 20, 0.001), (70_001, 1.0)])
+def test_compact_nonzero_matches_flatnonzero(dtype, n, fill):
+    """b2_compact_nonzero == np.flatnonzero + the values (unordered list); -0.0 and
+    exact zeros are skipped, NaN is kept; an overflowing list reports count > cap."""
+    torch = _torch()
+    lib = rt.load()
+    rng = np.random.default_rng(n + int(fill * 1000))
+    host = np.zeros(n, dtype=dtype)
+    mask = rng.random(n) < fill
+    host[mask] = (rng.standard_normal(mask.sum()) + 1j * rng.standard_normal(mask.sum())).astype(dtype)
+    if n > 40:
+        host[7] = complex(-0.0, 0.0)
+        host[11] = complex(0.0, -0.0)
+        host[13] = complex(0.0, 3.0)
+        host[n - 1] = complex(float("nan"), 0.0)
+    want = np.flatnonzero(host)           # NaN != 0 -> kept
+    dev = torch.from_numpy(host).cuda()
+    for cap in (max(1, want.size), max(1, want.size // 2)):
+        idx = torch.full((cap,), -1, dtype=torch.int64, device="cuda")
+        val = torch.zeros(cap, dtype=dev.dtype, device="cuda")
+        cnt = torch.full((1,), 123, dtype=torch.int64, device="cuda")
+        rt.check(lib.b2_compact_nonzero(n, dev.data_ptr(), rt.dtype_code(dtype), cap, idx.data_ptr(),
+                                        val.data_ptr(), cnt.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "compact")
+        count = int(cnt.item())
+        if want.size <= cap:
+            assert count == want.size
+            got_idx = idx[:count].cpu().numpy()
+            order = np.argsort(got_idx)
+            assert np.array_equal(got_idx[order], want)
+            got_val = val[:count].cpu().numpy()[order]
+            assert np.array_equal(got_val, host[want], equal_nan=True)
+        else:
+            assert count > cap            # overflow: the caller must copy densely
