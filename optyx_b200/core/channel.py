@@ -61,6 +61,9 @@ qubit = Ty("qubit")
 qmode = Ty("qmode")
 
 
+_DOUBLE_WIRING: dict = {}
+
+
 class Diagram(diagram.Diagram):
     """channel.py:245-574"""
     ty_factory = Ty
@@ -219,16 +222,23 @@ class Channel(_CBox):
         def get_perm(n):
             return sorted(sorted(list(range(n))), key=lambda i: i % 2)
 
-        cod = self.cod.single()
-        top_spiders = get_spiders(self.dom)
-        top_perm = D.permutation(get_perm(len(top_spiders.cod)), top_spiders.cod)
-        swap_env = D.id(cod @ self.env) @ D.swap(cod, self.env)
-        discard = D.id(cod) @ D.spiders(2, 0, self.env) @ D.id(cod)
-        new_cod = diagram.Ty._make(sum(((o, o) for o in cod.inside), ()))
-        bot_perm = D.permutation(get_perm(2 * len(cod)), new_cod).dagger()
-        bot_spiders = get_spiders(self.cod).dagger()
-        top = top_spiders >> top_perm
-        bot = swap_env >> discard >> bot_perm >> bot_spiders
+        # the wiring around ``kraus (x) conj(kraus)`` depends on the types only:
+        # built once per (dom, cod, env) -- diagrams are immutable values
+        key = (self.dom.inside, self.cod.inside, self.env.inside)
+        hit = _DOUBLE_WIRING.get(key)
+        if hit is None:
+            cod = self.cod.single()
+            top_spiders = get_spiders(self.dom)
+            top_perm = D.permutation(get_perm(len(top_spiders.cod)), top_spiders.cod)
+            swap_env = D.id(cod @ self.env) @ D.swap(cod, self.env)
+            discard = D.id(cod) @ D.spiders(2, 0, self.env) @ D.id(cod)
+            new_cod = diagram.Ty._make(sum(((o, o) for o in cod.inside), ()))
+            bot_perm = D.permutation(get_perm(2 * len(cod)), new_cod).dagger()
+            bot_spiders = get_spiders(self.cod).dagger()
+            hit = (top_spiders >> top_perm, swap_env >> discard >> bot_perm >> bot_spiders)
+            if len(_DOUBLE_WIRING) < 4096:
+                _DOUBLE_WIRING[key] = hit
+        top, bot = hit
         return top >> (self.kraus @ self.kraus.conjugate()) >> bot
 
     def dagger(self):
