@@ -204,11 +204,27 @@ class Diagram:
         layer, without the quadratic list copies)."""
         factory = factory or self.diagram_factory
         boxes, offsets = [], []
-        for left, box, right in self.layers():
+        # a monoidal functor maps a type wire by wire: track, per wire of the current
+        # layer, how many wires its image has, so that ``len(F(left))`` is a prefix sum
+        # instead of a type built per layer
+        mk = type(self.dom)._make
+        width_of: dict = {}
+
+        def widths(ty):
+            res = []
+            for o in ty.inside:
+                w = width_of.get(o)
+                if w is None:
+                    w = width_of[o] = len(on_ob(mk((o,))))
+                res.append(w)
+            return res
+        cur = widths(self.dom)
+        for box, off in zip(self.boxes, self.offsets):
             image = on_box(box)
-            shift = len(on_ob(left))
+            shift = sum(cur[:off])
             boxes.extend(image.boxes)
-            offsets.extend(o + shift for o in image.offsets)
+            offsets.extend([o + shift for o in image.offsets] if shift else image.offsets)
+            cur[off:off + len(box.dom.inside)] = widths(box.cod)
         return factory(on_ob(self.dom), on_ob(self.cod), boxes, offsets)
 
     def conjugate(self) -> "Diagram":
@@ -771,6 +787,9 @@ class ConeTracker:
     tests/test_known_answers.py::test_forward_cone_equals_backward_walk)."""
 
     def __init__(self, dom: Ty, input_dims: Sequence[int]):
+        from .zw import Create, Divide, Endo, Multiply
+        self._uncapped = (Swap, Endo, Divide, Multiply)
+        self._create = Create
         self.weights: List[int] = []
         self.frontier: List[int] = []
         for t, dim in zip(dom.inside, input_dims):
@@ -794,20 +813,22 @@ class ConeTracker:
         return s
 
     def max_dim(self, left: int, box) -> float:
-        from .zw import Divide, Endo, Multiply
-        if len(box.dom) == 0 or isinstance(box, (Swap, Endo, Divide, Multiply)):
+        dom = box.dom.inside
+        if not dom or isinstance(box, self._uncapped):
             return UNCAPPED
         mask = 0
-        for k, t in enumerate(box.dom.inside):
+        frontier = self.frontier
+        for k, t in enumerate(dom):
             if t == "mode":
-                mask |= self.frontier[left + k]
+                mask |= frontier[left + k]
         return max(self._weight(mask) + 1, 2)
 
     def apply(self, left: int, prev_box) -> bool:
         """Push one recorded (replacement) box; False if its span does not fit
         the frontier (the backward walk clamps such offsets, utils.py:466-476)."""
-        from .zw import Create
-        n_dom, n_cod = len(prev_box.dom), len(prev_box.cod)
+        Create = self._create
+        dom = prev_box.dom.inside
+        n_dom, n_cod = len(dom), len(prev_box.cod.inside)
         if left < 0 or left + n_dom > len(self.frontier):
             return False
         if isinstance(prev_box, Swap):
@@ -815,9 +836,10 @@ class ConeTracker:
             f[left], f[left + 1] = f[left + 1], f[left]
             return True
         mask = 0
-        for k, t in enumerate(prev_box.dom.inside):
+        frontier = self.frontier
+        for k, t in enumerate(dom):
             if t == "mode":
-                mask |= self.frontier[left + k]
+                mask |= frontier[left + k]
         if isinstance(prev_box, Create):
             new = []
             for c in range(n_cod):
@@ -852,33 +874,42 @@ def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
     n_wires = len(d.dom)
     prev_layers: List[Tuple[int, object]] = []
     cones = ConeTracker(d.dom, input_dims) if FORWARD_CONES else None
+    history: List[Tuple[int, list]] = []
+    check = __debug__
     for box, left in zip(d.boxes, d.offsets):
-        right = calculate_right_offset(n_wires, left, len(box.dom))
+        n_dom, n_cod = len(box.dom.inside), len(box.cod.inside)
+        end = left + n_dom
         if cones is not None:
             max_dim = cones.max_dim(left, box)
         else:
+            right = calculate_right_offset(n_wires, left, n_dom)
             max_dim = get_max_dim_for_box(left, box, right, list(input_dims), prev_layers)
-        dims_in = layer_dims[left:left + len(box.dom)]
+        dims_in = layer_dims[left:end]
         dims_out = [int(max_dim) if i > max_dim else int(i)
                     for i in box.determine_output_dimensions(list(dims_in))]
         repl = box.photon_number_transform(dims_in, dims_out)
         if isinstance(repl, Diagram) and not isinstance(repl, Box):
             repl = [_LayerView(l @ bx.dom @ r, l @ bx.cod @ r) for l, bx, r in repl.layers()]
-        prev_layers += [(left, rb) for rb in repl]
-        if cones is not None:
+        if cones is None or not FORWARD_CONES:
+            prev_layers += [(left, rb) for rb in repl]
+        else:
+            # the literal walker only needs the history once the forward tracker gives up
+            history.append((left, repl))
             for rb in repl:
                 if not cones.apply(left, rb):
                     # an offset the backward walk would clamp: replay everything
                     # recorded so far through the literal walker from here on
                     cones = None
+                    prev_layers += [(lf, rb2) for lf, rp in history for rb2 in rp]
                     break
-        outs = box.emit(b, wires[left:left + len(box.dom)], dims_in, dims_out)
-        assert len(outs) == len(box.cod), (box, outs)
-        for o, dd in zip(outs, dims_out):
-            assert b.dim(o) == dd, (box, b.dim(o), dd, dims_in, dims_out)
-        wires[left:left + len(box.dom)] = outs
-        layer_dims[left:left + len(box.dom)] = dims_out
-        n_wires += len(box.cod) - len(box.dom)
+        outs = box.emit(b, wires[left:end], dims_in, dims_out)
+        if check:
+            assert len(outs) == n_cod, (box, outs)
+            for o, dd in zip(outs, dims_out):
+                assert b.dim(o) == dd, (box, b.dim(o), dd, dims_in, dims_out)
+        wires[left:end] = outs
+        layer_dims[left:end] = dims_out
+        n_wires += n_cod - n_dom
     # the per-wire identity Z boxes the reference appends (diagram.py:367-374)
     # are identities on a shared index: nothing to emit
     if own:

@@ -19,6 +19,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence, Tuple
 
+import math
+
 import numpy as np
 
 # ---- leaf kinds (mirrored in include/optyx_b200.h and oracle/leaves.py) ----
@@ -58,7 +60,7 @@ class Leaf:
 
     @property
     def size(self) -> int:
-        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        return math.prod(self.shape)
 
 
 @dataclass
@@ -157,36 +159,35 @@ class NetworkBuilder:
 
     # -- finish ---------------------------------------------------------------
     def finish(self, dom_inds: Sequence[int], cod_inds: Sequence[int]) -> Network:
-        out = tuple(self.find(i) for i in list(dom_inds) + list(cod_inds))
+        find = self.find
+        out = tuple(find(i) for i in list(dom_inds) + list(cod_inds))
+        # compact relabel in first-use order (leaves, then open indices)
+        relabel: Dict[int, int] = {}
         leaves: List[Leaf] = []
-        used = set()
         for leaf in self.leaves:
-            inds = tuple(self.find(i) for i in leaf.inds)
-            used.update(inds)
-            leaves.append(Leaf(leaf.kind, leaf.shape, inds, leaf.ipar,
-                               leaf.params, leaf.name))
+            inds = []
+            for i in leaf.inds:
+                r = find(i)
+                k = relabel.get(r)
+                if k is None:
+                    k = relabel[r] = len(relabel)
+                inds.append(k)
+            leaves.append(Leaf(leaf.kind, leaf.shape, tuple(inds), leaf.ipar, leaf.params, leaf.name))
         scalar = self.scalar
+        # a closed index touched by no leaf is a loop: Spider(0,0,Dim(d)) = d
+        # (checked before the open ends below add their ``ones`` leaves)
+        open_roots = set(out)
+        for i in range(len(self._parent)):
+            if self._parent[i] == i and i not in relabel and i not in open_roots:
+                scalar = scalar * self._dim[i]
         # an open index touched by no leaf is the free end of a spider: ones
         for i in dict.fromkeys(out):
-            if i not in used:
-                leaves.append(Leaf(K_ONES, (self._dim[i],), (i,), 0, None, "ones"))
-                used.add(i)
-        # a closed index touched by no leaf is a loop: Spider(0,0,Dim(d)) = d
-        roots = {self.find(i) for i in range(len(self._parent))}
-        for r in roots:
-            if r not in used:
-                scalar = scalar * self._dim[r]
-        # compact relabel
-        relabel: Dict[int, int] = {}
-        for leaf in leaves:
-            for i in leaf.inds:
-                relabel.setdefault(i, len(relabel))
-        for i in out:
-            relabel.setdefault(i, len(relabel))
+            if i not in relabel:
+                relabel[i] = len(relabel)
+                leaves.append(Leaf(K_ONES, (self._dim[i],), (relabel[i],), 0, None, "ones"))
         net = Network(
-            leaves=[Leaf(l.kind, l.shape, tuple(relabel[i] for i in l.inds),
-                         l.ipar, l.params, l.name) for l in leaves],
-            dims={relabel[i]: self._dim[i] for i in relabel},
+            leaves=leaves,
+            dims={k: self._dim[i] for i, k in relabel.items()},
             output_inds=tuple(relabel[i] for i in out),
             scalar=scalar,
             n_dom=len(dom_inds),
