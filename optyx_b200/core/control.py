@@ -174,6 +174,9 @@ class ControlledPhaseShift(ClassicalBox):
                                     self.is_dagger)
 
 
+_TRUTH_TABLES: dict = {}
+
+
 class ClassicalFunctionBox(ClassicalBox):
     """control.py:317-376"""
 
@@ -197,6 +200,29 @@ class ClassicalFunctionBox(ClassicalBox):
             return None
         return out
 
+    def _truth_table(self, g_in, g_out) -> np.ndarray:
+        """Dense 0/1 array of the function, axes (out..., in...): one call of the user
+        function per input basis state (control.py:341-371).  Tables of plain
+        module-level functions (no closure state) are memoised per dims: a batch of
+        structurally identical diagrams asks for the same table once per diagram."""
+        fn = self.function
+        cacheable = getattr(fn, "__closure__", 1) is None and \
+            getattr(fn, "__qualname__", "<locals>").find("<locals>") < 0
+        key = (fn, g_in, g_out)
+        if cacheable:
+            hit = _TRUTH_TABLES.get(key)
+            if hit is not None:
+                return hit
+        table = np.zeros((*g_out, *g_in), dtype=complex)
+        for inp in itertools.product(*[range(x) for x in g_in]):
+            out = self._transition(tuple(inp), g_out)
+            if out is not None:
+                table[tuple(out) + tuple(inp)] = 1.0
+        if cacheable and len(_TRUTH_TABLES) < 1024:
+            table.setflags(write=False)
+            _TRUTH_TABLES[key] = table
+        return table
+
     def determine_output_dimensions(self, input_dims):
         if self.cod == Mode(self.output_size):
             return [diagram.MAX_DIM] * self.output_size
@@ -209,11 +235,7 @@ class ClassicalFunctionBox(ClassicalBox):
         # runs over the generator's inputs, which for a dagger box are the
         # actual outputs
         g_in, g_out = (dims_out, dims_in) if self.is_dagger else (dims_in, dims_out)
-        table = np.zeros((*[int(x) for x in g_out], *[int(x) for x in g_in]), dtype=complex)
-        for inp in itertools.product(*[range(int(x)) for x in g_in]):
-            out = self._transition(tuple(inp), tuple(g_out))
-            if out is not None:
-                table[tuple(out) + tuple(inp)] = 1.0
+        table = self._truth_table(tuple(int(x) for x in g_in), tuple(int(x) for x in g_out))
         outs = [b.new_index(int(x)) for x in dims_out]
         # table axes are (generator out..., generator in...)
         inds = (list(ins) + outs) if self.is_dagger else (outs + list(ins))

@@ -322,6 +322,22 @@ def _swap11():
     return diagram.Swap(diagram.mode, diagram.mode)
 
 
+def fusion_I_function(x):
+    """photonic.py:975-984 (module level: a pure function, its truth table is memoised)"""
+    a, b = x[0], x[1]
+    s = (a % 2) ^ (b % 2)
+    k = int(s * b + (1 - s) * (1 - (a + b) / 2)) % 2
+    return [s, k]
+
+
+def fusion_II_function(x):
+    """photonic.py:1114-1124"""
+    a, b, d = x[0], x[1], x[3]
+    s = (a % 2) ^ (b % 2)
+    k = int(s * (b + d) + (1 - s) * (1 - (a + b) / 2)) % 2
+    return [s, k]
+
+
 def FusionTypeI():
     """photonic.py:917-996"""
     from .classical import ClassicalFunction
@@ -330,11 +346,6 @@ def FusionTypeI():
              >> M(2) @ _swap11() >> M(1) @ _swap11() @ M(1))
     fusion = Channel("Fusion I", kraus)
 
-    def fusion_I_function(x):
-        a, b = x[0], x[1]
-        s = (a % 2) ^ (b % 2)
-        k = int(s * b + (1 - s) * (1 - (a + b) / 2)) % 2
-        return [s, k]
     return (fusion >> qmode ** 2 @ NumberResolvingMeasurement(2)
             >> qmode ** 2 @ ClassicalFunction(fusion_I_function, mode ** 2, bit ** 2))
 
@@ -348,11 +359,6 @@ def FusionTypeII():
              >> M(2) @ _swap11() >> M(1) @ _swap11() @ M(1) >> h() @ M(2))
     fusion = Channel("Fusion II", kraus)
 
-    def fusion_II_function(x):
-        a, b, d = x[0], x[1], x[3]
-        s = (a % 2) ^ (b % 2)
-        k = int(s * (b + d) + (1 - s) * (1 - (a + b) / 2)) % 2
-        return [s, k]
     return (fusion >> NumberResolvingMeasurement(4)
             >> ClassicalFunction(fusion_II_function, mode ** 4, bit ** 2))
 
