@@ -129,3 +129,19 @@ def test_product_evalresult_host_logic():
         bad.prob_dist()
     with pytest.raises(ValueError):
         _ = bad.density_matrix
+
+
+def test_index_tuples_match_unravel_index():
+    """Host side of prob_dist: keys of the selected flat positions, C order, as tuples
+    of Python ints (dense selections walk itertools.product, sparse ones unravel)."""
+    from optyx_b200.core.backends import _index_tuples
+    rng = np.random.default_rng(0)
+    for shape in [(2, 3, 4), (5,), (2,) * 10, (7, 7, 3), (1,), (4, 1, 2)]:
+        n = int(np.prod(shape))
+        for dens in (1.0, 0.5, 0.05, 0.0):
+            mask = (rng.random(n) < dens).astype(np.uint8)
+            flat = np.flatnonzero(mask)
+            got = list(_index_tuples(flat, mask, shape))
+            want = [tuple(int(x) for x in np.unravel_index(f, shape)) for f in flat]
+            assert got == want, (shape, dens)
+            assert all(type(i) is int for key in got for i in key)
