@@ -14,7 +14,10 @@
 // modes in the tile the reads are pure broadcasts), does 4*K FMAs per output
 // and stores each output straight from registers: lanes of a warp write
 // consecutive rows = consecutive addresses.  No accumulator staging, at most
-// one barrier pair per tile, every load independent of every other.
+// one barrier pair per tile, every load independent of every other.  alpha is
+// folded into the staged B block.  Wide tiles without batch modes inside run RM
+// rows per thread (B reuse, see the RM branch); stores are streaming
+// (st.global.cs) and CTAs take tiles round-robin (FM_DEFAULT_FLAGS).
 #include "b2_common.cuh"
 #include <stdlib.h>
 
@@ -131,6 +134,7 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
     const int n_items = g.TM * n_jg;
     const int bplane = g.TB * g.TN;
     const bool unit_alpha = (alpha_re == (T)1 && alpha_im == (T)0);
+    const C alpha = make_c<T>(alpha_re, alpha_im);
     const C zero = make_c<T>((T)0, (T)0);
 
     // R consecutive tiles are processed together (same work item, R tile offsets):
@@ -165,7 +169,14 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
             for (int e = tid; e < KP * bplane; e += FM_THREADS) {
                 const int k = e / bplane, r = e - k * bplane;
                 const int bt = r / g.TN, j = r - bt * g.TN;
-                Bs[e] = (k < g.K) ? B[ob + bt_off[bt] + col_b[j] + k_b[k]] : zero;
+                // alpha is folded into the staged B block (K x TB x TN multiplies per tile
+                // instead of one complex multiply per output)
+                C bv = zero;
+                if (k < g.K) {
+                    bv = B[ob + bt_off[bt] + col_b[j] + k_b[k]];
+                    if (!unit_alpha) bv = cmul(alpha, bv);
+                }
+                Bs[e] = bv;
             }
             __syncthreads();
         }
@@ -216,12 +227,7 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                             #pragma unroll
                             for (int k = 0; k < KP; ++k) cfma(acc, a[q][k], b[k]);
                         }
-                        C res;
-                        if (unit_alpha) res = acc;
-                        else {
-                            res.x = alpha_re * acc.x - alpha_im * acc.y;
-                            res.y = alpha_re * acc.y + alpha_im * acc.x;
-                        }
+                        C res = acc;
                         C* dst = cp + pm[q] + pn;
                         if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
                         if (flags & FM_STREAM_STORES) __stcs(dst, res);
@@ -264,12 +270,7 @@ contract_fma_kernel(const __grid_constant__ fm_desc g, long long n_tiles,
                         #pragma unroll
                         for (int k = 0; k < KP; ++k) cfma(acc, a[r][k], bp[k * bplane + j]);
                     }
-                    C res;
-                    if (unit_alpha) res = acc;
-                    else {
-                        res.x = alpha_re * acc.x - alpha_im * acc.y;
-                        res.y = alpha_re * acc.y + alpha_im * acc.x;
-                    }
+                    C res = acc;
                     C* dst = cp + pos_n[j];
                     if (accumulate) { const C o = *dst; res.x += o.x; res.y += o.y; }
                     if (flags & FM_STREAM_STORES) __stcs(dst, res);      // written once, never re-read
