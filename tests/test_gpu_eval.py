@@ -36,23 +36,7 @@ def _check_prob_dist(res, arr, d):
         assert abs(v - want[tuple(int(i) for i in k)]) <= 1e-10
 
 
-CASES = {
-    "lossy_hom": lambda: lossy_hom(0.8),
-    "bs_pure": lambda: photonic.Create(1, 1) >> photonic.BS,
-    "mzi_chip_pure": lambda: photonic.Create(1, 1, 1, 1) >> photonic.seeded_ansatz(4, 4, 3),
-    "cfg1_4mode": lambda: cfg1_interferometer(4, (1, 1, 0, 0)),
-    "cfg1_6mode": lambda: cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)),
-    "ghz6_measured": lambda: ghz(6, measure=True),
-    "ghz5_noisy_open3": lambda: ghz(5, open_qubits=3, noise=0.95),
-    "ghz8_noisy_measured": lambda: ghz(8, noise=0.95, measure=True),
-    "bitflip": lambda: qubits.Z(0, 1) >> qubits.BitFlipError(0.43),
-    "hom_distinguishable": lambda: distinguishable_bs(np.array([0.6, 0.8j]), np.array([1, 0])),
-    "cfg3_small": lambda: cfg3_interferometer(width=3, n_photons=2, measured=2, depth=2),
-    "cfg3_4mode": lambda: cfg3_interferometer(width=4, n_photons=2, measured=2),
-    "clifford_t_8x6": lambda: random_clifford_t(8, 6, seed=2),
-    "fusion_ii": fusion_ii_teleportation,
-    "fusion_i": fusion_i_spider,
-}
+from cases import EVAL_CASES as CASES  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

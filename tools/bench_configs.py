@@ -21,6 +21,11 @@ results = {}
 backend = B200Backend()
 
 
+def _dump():
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
+
+
 def timed(fn, reps):
     fn()
     torch.cuda.synchronize()
@@ -74,6 +79,7 @@ def single(name, factory, reps=50, dtype=np.complex128, check_against=None):
         out[name]["max_rel_err_vs_" + check_against] = float(
             np.abs(res.tensor.array - ref).max() / max(1e-300, np.abs(ref).max()))
     print(name, out[name], flush=True)
+    _dump()
 
 
 def batched(name, make, batch=1024, reps=10):
@@ -110,6 +116,7 @@ def batched(name, make, batch=1024, reps=10):
                  "e2e_evals_per_s": batch / t_e2e, "e2e_evals_per_s_serial_compile": batch / t_e2e_serial,
                  "host_cores": os.cpu_count(), "first": complex(res[0].tensor.array.reshape(-1)[0]).real}
     print(name, out[name], flush=True)
+    _dump()
 
 
 single("cfg1_hom_lossy", lambda: cases.lossy_hom(0.8))
@@ -140,6 +147,7 @@ def permanents(name, w, n, k, reps=5):
                  "e2e_ms_per_eval": t_e2e * 1e3,
                  "fp64_tflops": flops / (pb.last_kernel_ms * 1e-3) / 1e12}
     print(name, out[name], flush=True)
+    _dump()
 
 
 permanents("cfg3_full_12mode_6photon_k4_permanents", 12, 6, 4)
