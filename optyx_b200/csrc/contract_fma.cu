@@ -523,7 +523,19 @@ int launch_fma(const b2_modes& md, const void* a, const void* b, void* c, double
     fm_desc d, d2;
     long long n_tiles = 0, n_tiles2 = 0;
     bool swap_ab = fine.sa[fastest] == 0;
-    const fm_tune tune = get_tune();
+    fm_tune tune = get_tune();
+    if (!getenv("B2_FMA_TUNE")) {
+        // the 1024 x 64 tiles, the streaming stores and 4 rows per thread pay on outputs
+        // far larger than L2 (the multi-GB final pair of a density tensor).  A mid-size
+        // output (a batched plan's tens-of-MB intermediates, measured on cfg5a) needs
+        // more, smaller tiles to fill the GPU, and its consumer finds it in L2 only if
+        // it is stored with the default policy.
+        long long total = 1;
+        for (int i = 0; i < fine.n_out; ++i) total *= fine.dim[i];
+        if (total < (long long)FM_TMAX * 1184) { tune.tmax = 16384; tune.rm = 2; }
+        if (total * (long long)eb < (256ll << 20))
+            tune.flags &= ~(FM_STREAM_STORES | FM_ROUND_ROBIN);   // contiguous tiles: B / A reuse in L1
+    }
     bool ok = make_fma(fine, d, n_tiles, swap_ab, eb, tune);
     if (!ok || d.TM < 64) {
         const bool ok2 = make_fma(fine, d2, n_tiles2, !swap_ab, eb, tune);

@@ -23,7 +23,8 @@ backend = B200Backend()
 
 def _dump():
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
+    name = "configs_only.json" if globals().get("ONLY") else "configs.json"
+    json.dump(out, open(os.path.join("gpurun_out", name), "w"), indent=1)
 
 
 def timed(fn, reps):
@@ -119,6 +120,11 @@ def batched(name, make, batch=1024, reps=10):
     _dump()
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+if ONLY:                                   # e.g. `bench_configs.py cfg5`: only matching rows
+    _single, _batched = single, batched
+    single = lambda name, *a, **k: _single(name, *a, **k) if ONLY in name else None       # noqa: E731
+    batched = lambda name, *a, **k: _batched(name, *a, **k) if ONLY in name else None     # noqa: E731
 single("cfg1_hom_lossy", lambda: cases.lossy_hom(0.8))
 single("cfg1_6mode_3photon", lambda: cases.cfg1_interferometer(6, (1, 1, 1, 0, 0, 0)))
 single("cfg3_6mode_3photon_k2", lambda: cases.cfg3_interferometer(width=6, n_photons=3, measured=2), reps=3)
@@ -150,6 +156,6 @@ def permanents(name, w, n, k, reps=5):
     _dump()
 
 
-permanents("cfg3_full_12mode_6photon_k4_permanents", 12, 6, 4)
-os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
+if not ONLY or ONLY in "cfg3_full_12mode_6photon_k4_permanents":
+    permanents("cfg3_full_12mode_6photon_k4_permanents", 12, 6, 4)
+_dump()
