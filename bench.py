@@ -37,7 +37,7 @@ FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profil
 
 def workload(name: str, small: bool = False):
     """(diagram factory, description).  ``small``: the bounded CPU sample."""
-    import cases
+    from optyx_b200 import workloads as cases
     if name == "cfg2":
         n, k = (20, 14)        # the CPU arm runs the full-size workload too (~20 s/eval)
         return (lambda: cases.ghz(n, open_qubits=k, noise=0.95),
@@ -174,7 +174,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cases import compile_channel
     from optyx_b200 import executor, runtime as rt
     from optyx_b200.core.backends import B200Backend
 
@@ -198,8 +197,8 @@ def main():
     factory, desc = workload(args.workload)
     diagram = factory()
     t0 = time.perf_counter()
-    net = compile_channel(diagram) if False else B200Backend()._get_network(
-        diagram, nested_eval=B200Backend()._nested_eval)
+    compile_backend = B200Backend()
+    net = compile_backend._get_network(diagram, nested_eval=compile_backend._nested_eval)
     t_compile = time.perf_counter() - t0
     t0 = time.perf_counter()
     target = float(2 ** 26) if args.workload == "cfg4" else None      # cfg4 must be sliced

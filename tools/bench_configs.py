@@ -12,7 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import cases  # noqa: E402
+from optyx_b200 import workloads as cases  # noqa: E402
 from optyx_b200 import executor  # noqa: E402
 from optyx_b200.core.backends import B200Backend  # noqa: E402
 

@@ -27,7 +27,7 @@ for m, n in ((8, 4), (12, 6), (12, 8), (16, 8), (14, 10)):
                 "kernel_tflops": flops / (pb.last_kernel_ms * 1e-3) / 1e12})
     print(json.dumps(out[-1]), flush=True)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import cases
+from optyx_b200 import workloads as cases
 for w, n, k in ((6, 3, 2), (8, 4, 4), (12, 6, 4)):
     d = cases.cfg3_interferometer(width=w, n_photons=n, measured=k, inflate=False)
     pb = PermanentBackend()

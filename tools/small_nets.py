@@ -3,7 +3,7 @@ import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import cases
+from optyx_b200 import workloads as cases
 from optyx_b200 import executor, planner
 def timed(fn, reps=50):
     fn(); torch.cuda.synchronize()

@@ -12,7 +12,7 @@ import torch  # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import cases  # noqa: E402
+from optyx_b200 import workloads as cases  # noqa: E402
 from optyx_b200 import executor, runtime  # noqa: E402
 
 KEYS = ("B2_FMA_TMAX", "B2_FMA_MAXM", "B2_FMA_MAXN", "B2_FMA_FLAGS", "B2_FMA_GRID", "B2_FMA_RM")
