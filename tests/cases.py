@@ -12,6 +12,8 @@ from oracle.contract import contract_network
 from optyx_b200 import classical, photonic, qubits
 from optyx_b200.core import channel, diagram, zw, zx
 from optyx_b200.core.channel import Channel, Discard, Measure, bit, mode, qmode, qubit
+from optyx_b200.workloads import *  # noqa: F401,F403  (the diagram builders live in the package)
+from optyx_b200.workloads import EVAL_CASES  # noqa: F401
 
 
 def oracle_nested(net):
@@ -45,8 +47,6 @@ def oracle_eval(d) -> np.ndarray:
     return contract_network(net)
 
 
-from optyx_b200.workloads import *  # noqa: F401,F403,E402  (the diagram builders live in the package)
-from optyx_b200.workloads import EVAL_CASES  # noqa: F401,E402
 
 
 def statevector_clifford_t(n, depth, seed=0):
