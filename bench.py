@@ -312,9 +312,10 @@ def main():
         "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak_val,
         "unit": unit, "frac": achieved / peak_val,
         # dram__bytes_read+write of this kernel from `ncu --set full` on the
-        # quarter-size instance (1.0385 GB per launch, profiles/r01_fma_final_step.md)
-        # scaled by 4; the full-size capture does not finish under ncu's replay
-        "traffic": 4.154e9 if args.workload == "cfg2" else None,
+        # quarter-size instance (1.0179 GB written + 1.4 MB read per launch of the
+        # 4-rows-per-thread kernel, profiles/r01_fma_final_step.md) scaled by 4; the
+        # full-size capture does not finish under ncu's replay
+        "traffic": 4.077e9 if args.workload == "cfg2" else None,
         "peak_source": ("FP64 DMMA peak measured on this pool (profiles/r01_probe.json)" if tensor_bound
                         else "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"),
         "kernel": f"b2_contract_{dom.kernel} ({'final step, ' if dom.final else ''}(batch,M,N,K)={dom.mnk})",
