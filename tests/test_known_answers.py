@@ -384,3 +384,31 @@ def test_bosonic_operator_hamiltonian_sum():
     assert kraus[0, 0].sum() == 0 and kraus[1, 1, 1, 1] == pytest.approx(0.0)
     with pytest.raises(ValueError):
         Diagram.from_bosonic_operator(2, [(2, False)])
+
+
+# ---- host compile internals: the one-pass functor equals the layer-by-layer definition -------
+def _functor_by_layers(d, on_ob, on_box, factory):
+    """F(d) as the reference builds it: id >> (F(left) @ F(box) @ F(right)) per layer."""
+    res = factory.id(on_ob(d.dom))
+    for left, box, right in d.layers():
+        res = res >> (factory.id(on_ob(left)) @ on_box(box) @ factory.id(on_ob(right)))
+    return res
+
+
+@pytest.mark.parametrize("name", ["lossy_hom", "cfg1_4mode", "fusion_ii", "hom_distinguishable",
+                                  "ghz5_noisy_open3"])
+def test_one_pass_functors_equal_layer_by_layer_application(name):
+    from cases import EVAL_CASES
+    d = EVAL_CASES[name]()
+    fast = d.double()
+    slow = _functor_by_layers(d, lambda ty: ty.double(), lambda box: box.double(), diagram.Diagram)
+    assert fast.dom == slow.dom and fast.cod == slow.cod
+    assert fast.offsets == slow.offsets
+    assert [type(b) for b in fast.boxes] == [type(b) for b in slow.boxes]
+    assert np.allclose(contract_network(fast.to_network(nested_eval=oracle_nested)),
+                       contract_network(slow.to_network(nested_eval=oracle_nested)))
+    base = cfg3_interferometer(width=3, n_photons=2, measured=2, depth=2, inflate=False)
+    fast = base.inflate(2)
+    slow = _functor_by_layers(base, lambda ty: ty.inflate(2), lambda box: box.inflate(2),
+                              channel.Diagram)
+    assert fast.dom == slow.dom and fast.cod == slow.cod and fast.offsets == slow.offsets
