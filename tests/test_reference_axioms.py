@@ -269,3 +269,28 @@ def test_two_mode_gates_with_multi_photon_inputs_match_permanents(ev, name, p1, 
         inside = all(o < s for o, s in zip(out, arr.shape))
         got = arr[out] if inside else 0.0          # an axis the light cone cut shorter
         assert abs(got - want) <= 1e-10, (name, out, got, want, arr.shape)
+
+
+# ---- test_zw_2_circuit.py:126-215: the same gates as channels, post-selected, doubled ---------
+# (CPU only: scalar probabilities of the CP-doubled diagram against |permanent amplitude|^2)
+def _channel_cases():
+    out = []
+    for p1, p2 in ((1, 2), (2, 1)):
+        for bias in (0, 0.5):
+            out.append((f"BBS{bias}", p1, p2, lambda bias=bias: photonic.BBS(bias)))
+            out.append((f"TBS{bias}", p1, p2, lambda bias=bias: photonic.TBS(bias)))
+    for p1, p2, theta, phi in itertools.product((1, 2), (1, 2), (0, 0.5), (0, 1, 0.5)):
+        out.append((f"MZI{theta},{phi}", p1, p2, lambda t=theta, p=phi: photonic.MZI(t, p)))
+    return out
+
+
+@pytest.mark.parametrize("name,p1,p2,gate", _channel_cases())
+def test_post_selected_channel_probability_matches_permanent(name, p1, p2, gate):
+    from oracle.permanent import lo_amplitude
+    g = gate()
+    d = photonic.Create(p1, p2) >> g >> classical.Select(p1, p2)
+    prob = _oracle(d.double())
+    U = np.asarray(g.array, dtype=complex).reshape(2, 2)
+    want = abs(lo_amplitude(U, (p1, p2), (p1, p2))) ** 2
+    assert np.ndim(prob) == 0
+    assert abs(complex(prob) - want) <= 1e-10, (name, prob, want)
