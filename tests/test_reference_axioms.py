@@ -294,3 +294,87 @@ def test_post_selected_channel_probability_matches_permanent(name, p1, p2, gate)
     want = abs(lo_amplitude(U, (p1, p2), (p1, p2))) ** 2
     assert np.ndim(prob) == 0
     assert abs(complex(prob) - want) <= 1e-10, (name, prob, want)
+
+
+# ---- test_feed_forward.py:190-330: classical function boxes, controlled phase shifts ----------
+# (CPU only)
+def _arr_and_ndom(d, input_dims=None):
+    net = d.to_tensor(input_dims, nested_eval=oracle_nested)
+    return contract_network(net), net.n_dom
+
+
+def _tensor_dagger(arr, n_dom):
+    """``tensor.dagger()`` of an array whose axes are (dom..., cod...)."""
+    nd = arr.ndim
+    return np.conj(arr).transpose(list(range(n_dom, nd)) + list(range(n_dom)))
+
+
+def _close_on_overlap(a, b):
+    if a.shape != b.shape:
+        blk = tuple(slice(0, min(x, y)) for x, y in zip(a.shape, b.shape))
+        return a.ndim == b.ndim and np.allclose(a[blk], b[blk])
+    return np.allclose(a, b)
+
+
+def _dagger_consistent(d):
+    arr, n_dom = _arr_and_ndom(d)
+    return _close_on_overlap(_tensor_dagger(arr, n_dom), _arr_and_ndom(d.dagger())[0])
+
+
+CLASSICAL_FUNCTIONS = [
+    (lambda x: [x[0] ^ x[1]], [1, 1]),
+    (lambda x: [x[0], x[0]], [[1], [1]]),
+    (lambda x: [x[0] ^ x[1], x[0]], [[1, 1], [1, 0]]),
+    (lambda x: [x[0] ^ x[1], x[0] ^ x[1]], [[1, 1], [1, 1]]),
+]
+
+
+@pytest.mark.parametrize("which", range(4))
+def test_logical_matrix_box(which):
+    function, m = CLASSICAL_FUNCTIONS[which]
+    m = np.array(m)
+    if m.ndim == 1:
+        m = m.reshape(1, -1)
+    cod, dom = diagram.Bit(len(m)), diagram.Bit(len(m[0]))
+    f_arr = _oracle(control.ClassicalFunctionBox(function, dom, cod))
+    assert np.allclose(f_arr, _oracle(control.BinaryMatrixBox(m)))
+    assert _dagger_consistent(control.BinaryMatrixBox(m))
+
+
+REAL_FUNCS = [lambda x: [x[0] * 0.234, x[0] * 0.912, x[0] * 0.184], lambda x: [0.23 * x[0]],
+              lambda x: [0.8362, 0.193, 0.654]]
+
+
+@pytest.mark.parametrize("which", range(3))
+def test_controlled_phase_shift_dagger_and_numeric(which):
+    f = REAL_FUNCS[which]
+    n = len(f([0]))
+    assert _dagger_consistent(control.ControlledPhaseShift(f, n))
+    assert _dagger_consistent(Mode(n) @ Create(4) >> control.ControlledPhaseShift(f, n))
+    for x in range(5):
+        diag = Create(x) @ Mode(n) >> control.ControlledPhaseShift(f, n)
+        zbox = diagram.Id(Mode(0))
+        for y in f([x]):
+            zbox = zbox @ ZBox(1, 1, lambda i, y=y: np.exp(2 * np.pi * 1j * y) ** i)
+        assert np.allclose(_oracle(zbox), _oracle(diag))
+        assert np.allclose(_oracle(zbox.dagger()), _oracle(diag.dagger()))
+        assert _dagger_consistent(zbox)
+
+
+@pytest.mark.parametrize("f,n", [(lambda x: [x[0]], 1),
+                                 (lambda x: [0.23 * x[0], 0.456 * x[0], 0.876 * x[0], 0.654 * x[0]], 4),
+                                 (lambda x: [0.23 * x[0]], 1),
+                                 (lambda x: [0.23 * x[0], 0.456 * x[0], 0.876 * x[0]], 3)])
+def test_controlled_phase_shift_dagger_2(f, n):
+    assert _dagger_consistent(control.ControlledPhaseShift(f, n))
+
+
+def test_photon_threshold_detector_dagger():
+    assert _dagger_consistent(PhotonThresholdDetector())
+
+
+def test_matrix_to_zw():
+    """test_feed_forward.py:321-337"""
+    d1 = photonic.matrix_to_zw(np.array([[1, 1], [1, 1]]))
+    d2 = (W(2) @ W(2) >> Mode(1) @ Swap(Mode(1), Mode(1)) @ Mode(1) >> W(2).dagger() @ W(2).dagger())
+    assert np.allclose(_oracle(d1), _oracle(d2))
