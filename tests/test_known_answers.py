@@ -412,3 +412,21 @@ def test_one_pass_functors_equal_layer_by_layer_application(name):
     slow = _functor_by_layers(base, lambda ty: ty.inflate(2), lambda box: box.inflate(2),
                               channel.Diagram)
     assert fast.dom == slow.dom and fast.cod == slow.cod and fast.offsets == slow.offsets
+
+
+# ---- optyx/photonic.py module docstring (lines 131-138, 165-177, 199-243) ---------------------
+def test_photonic_module_docstring_examples():
+    hom = photonic.Create(1, 1) >> photonic.BS >> classical.Select(1, 1)
+    assert float(np.round(dbl(hom).real, 1)) == 0.0               # impossible for an ideal BS
+    lossy = (photonic.Create(1, 1) >> photonic.PhotonLoss(0.2) @ photonic.Id(1) >> photonic.BS
+             >> classical.Select(1, 0))
+    assert float(np.round(dbl(lossy).real, 1)) == 0.4
+    rng = np.random.default_rng(11)
+    s1 = rng.random(2) + 1j * rng.random(2)
+    s1 /= np.linalg.norm(s1)
+    s2 = rng.random(2) + 1j * rng.random(2)
+    s2 /= np.linalg.norm(s2)
+    chan = (photonic.Create(1, 1, internal_states=(s1, s2)) >> photonic.BS
+            >> photonic.NumberResolvingMeasurement(2)).inflate(2)
+    result = dbl(chan)
+    assert np.isclose(result[1, 1].real, 0.5 - 0.5 * abs(np.dot(s1, s2.conjugate())) ** 2)
