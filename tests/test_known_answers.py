@@ -430,3 +430,17 @@ def test_photonic_module_docstring_examples():
             >> photonic.NumberResolvingMeasurement(2)).inflate(2)
     result = dbl(chan)
     assert np.isclose(result[1, 1].real, 0.5 - 0.5 * abs(np.dot(s1, s2.conjugate())) ** 2)
+
+
+# ---- gate docstrings (photonic.py:414-420, 556-570, 632-637, 726-741): g >> g.dagger() = id ----
+@pytest.mark.parametrize("gate", [photonic.BBS(0.4), photonic.TBS(0.25), photonic.MZI(0.3, 0.7),
+                                  photonic.Phase(0.35) @ photonic.Id(1), photonic.HadamardBS()])
+@pytest.mark.parametrize("photons", [(1, 1), (2, 0), (1, 0), (0, 2)])
+def test_gate_followed_by_its_dagger_is_identity(gate, photons):
+    got = oracle_eval(photonic.Create(*photons) >> gate >> gate.dagger())
+    want = oracle_eval(photonic.Create(*photons))
+    n = sum(photons)
+    for out in np.ndindex(*got.shape):
+        ref = want[out] if all(o < s for o, s in zip(out, want.shape)) else 0.0
+        assert abs(got[out] - ref) <= 1e-10, (photons, out, got[out], ref)
+    assert abs(got[photons] - want[photons]) <= 1e-10 and abs(want[photons]) > 0 and n >= 1
