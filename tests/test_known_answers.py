@@ -444,3 +444,14 @@ def test_gate_followed_by_its_dagger_is_identity(gate, photons):
         ref = want[out] if all(o < s for o, s in zip(out, want.shape)) else 0.0
         assert abs(got[out] - ref) <= 1e-10, (photons, out, got[out], ref)
     assert abs(got[photons] - want[photons]) <= 1e-10 and abs(want[photons]) > 0 and n >= 1
+
+
+# ---- optyx/classical.py module docstring (lines 93-131) --------------------------------------
+def test_classical_module_docstring_examples():
+    target = dbl(classical.XorBit(2))
+    f = classical.ClassicalFunction(lambda b: [b[0] ^ b[1]], bit ** 2, bit)
+    m = classical.BinaryMatrix([[1, 1]])
+    assert np.allclose(dbl(f), target)
+    assert np.allclose(dbl(m), target)
+    parity = classical.AddN(2) >> classical.Mod2()
+    assert np.allclose(dbl(classical.Digit(3, 2) >> parity >> classical.PostselectBit(1)), 1)
