@@ -455,3 +455,16 @@ def test_classical_module_docstring_examples():
     assert np.allclose(dbl(m), target)
     parity = classical.AddN(2) >> classical.Mod2()
     assert np.allclose(dbl(classical.Digit(3, 2) >> parity >> classical.PostselectBit(1)), 1)
+
+
+# ---- optyx/qubits.py:152-173: the docstring circuit, evaluated by hand ----
+def test_qubits_docstring_teleportation_variant_by_hand():
+    """Kraus operators by hand: K_rs = (-1)^{rs} Z^r X^s |r><r|, so the channel is
+    rho -> Tr(rho) * 1 and the doubled tensor is delta(ket_in, bra_in) delta(ket_out, bra_out)."""
+    from cases import teleportation
+    got = oracle_eval(teleportation())
+    want = np.einsum("ab,cd->abcd", np.eye(2), np.eye(2))
+    assert got.shape == (2, 2, 2, 2) and np.allclose(got, want)
+    # the identity channel is the same pair of Kronecker deltas under another axis order
+    identity = np.einsum("ac,bd->abcd", np.eye(2), np.eye(2))
+    assert not np.allclose(got, identity) and np.allclose(got.transpose(0, 2, 1, 3), identity)
