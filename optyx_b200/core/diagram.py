@@ -731,46 +731,9 @@ class _LayerView:
 
 
 # ---- light-cone truncation (optyx/utils/utils.py:347-510) ---------------------
-def calculate_right_offset(total_wires: int, left_offset: int, span_len: int) -> int:
-    return total_wires - span_len - left_offset
-
-
-def get_max_dim_for_box(left_offset: int, box, right_offset: int, input_dims: List[int],
-                        prev_layers) -> float:
-    """Photon-count bound of the wires a box can see (utils.py:436-510)."""
-    from .zw import Create, Divide, Endo, Multiply
-    if len(box.dom) == 0 or isinstance(box, (Swap, Endo, Divide, Multiply)):
-        return UNCAPPED
-    dim_for_box = 0
-    if "mode" not in box.dom.inside:
-        # an empty cone stays empty through every earlier layer (utils.py:359-373,
-        # 494-500), so the walk below would return max(0 + 1, 2): skip the
-        # O(#boxes) walk -- exact, and it makes qubit circuits O(#boxes) overall
-        return 2
-    cone: List[bool] = ([False] * left_offset + [t == "mode" for t in box.dom.inside]
-                        + [False] * right_offset)
-    for prev_left, prev_box in prev_layers[::-1]:
-        total = len(cone)
-        cod_len = len(prev_box.cod)
-        max_left = max(0, total - cod_len)
-        adj_left = min(max(prev_left, 0), max_left)
-        prev_right = calculate_right_offset(total, adj_left, cod_len)
-        span = range(adj_left, adj_left + cod_len)
-        connected = any(cone[i] for i in span)
-        if connected and isinstance(prev_box, Create):
-            dim_for_box += sum(prev_box.photons[i - adj_left] for i in span if cone[i])
-        if isinstance(prev_box, Swap):
-            cone = (cone[:adj_left] + [cone[adj_left + 1]] + [cone[adj_left]]
-                    + cone[adj_left + 2:])
-        else:
-            end = total - prev_right
-            cone = (cone[:adj_left]
-                    + [connected if t == "mode" else False for t in prev_box.dom.inside]
-                    + cone[end:])
-    dim_for_box += sum(2 * d for wire, d in zip(cone, input_dims) if wire) + 1
-    return max(dim_for_box, 2)
-
-
+# The reference walks ALL earlier layers backwards for every box; the literal
+# restatement of that walk lives in the test oracle (oracle/compile.py), which the
+# forward formulation below is checked against box by box.
 class ConeTracker:
     """Forward formulation of the light-cone walk (utils.py:436-510).
 
@@ -783,8 +746,8 @@ class ConeTracker:
     hands the union of the cones of its mode-typed inputs to each of its
     outputs; a swap swaps two cones.  The bound of a box is the total weight of
     the union over its mode inputs, + 1, at least 2 -- identical, by
-    construction, to what the backward walk returns (checked against it in
-    tests/test_known_answers.py::test_forward_cone_equals_backward_walk)."""
+    construction, to what the backward walk returns (checked box by box against
+    the oracle's literal walk, tests/test_oracle_compile.py)."""
 
     def __init__(self, dom: Ty, input_dims: Sequence[int]):
         from .zw import Create, Divide, Endo, Multiply
@@ -825,7 +788,7 @@ class ConeTracker:
 
     def apply(self, left: int, prev_box) -> bool:
         """Push one recorded (replacement) box; False if its span does not fit
-        the frontier (the backward walk clamps such offsets, utils.py:466-476)."""
+        the frontier."""
         Create = self._create
         dom = prev_box.dom.inside
         n_dom, n_cod = len(dom), len(prev_box.cod.inside)
@@ -851,16 +814,16 @@ class ConeTracker:
         return True
 
 
-FORWARD_CONES = True     # False: the literal backward walk (slow, reference-shaped)
-
-
 def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
                     builder: Optional[nw.NetworkBuilder] = None,
-                    in_inds: Optional[List[int]] = None, nested_eval=None):
+                    in_inds: Optional[List[int]] = None, nested_eval=None,
+                    trace: Optional[list] = None):
     """``Diagram.to_tensor`` (diagram.py:301-375): walk the boxes keeping the
     per-wire truncation dims, cap each box's outputs by its light cone, emit
     leaves.  Returns ``(Network, cod_dims)`` (or ``(out_inds, cod_dims)`` when
-    emitting into a caller's builder, used for nested diagrams)."""
+    emitting into a caller's builder, used for nested diagrams).  ``trace``
+    collects ``(box, dims_in, dims_out)`` per box (the truncation bookkeeping the
+    parity tests compare with the oracle's literal walk)."""
     if input_dims is None:
         input_dims = [2 for _ in range(len(d.dom))]
     else:
@@ -871,37 +834,28 @@ def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
     layer_dims = [int(x) for x in input_dims]
     wires = [b.new_index(x) for x in layer_dims] if in_inds is None else list(in_inds)
     dom_inds = list(wires)
-    n_wires = len(d.dom)
-    prev_layers: List[Tuple[int, object]] = []
-    cones = ConeTracker(d.dom, input_dims) if FORWARD_CONES else None
-    history: List[Tuple[int, list]] = []
+    cones = ConeTracker(d.dom, input_dims)
     check = __debug__
     for box, left in zip(d.boxes, d.offsets):
         n_dom, n_cod = len(box.dom.inside), len(box.cod.inside)
         end = left + n_dom
-        if cones is not None:
-            max_dim = cones.max_dim(left, box)
-        else:
-            right = calculate_right_offset(n_wires, left, n_dom)
-            max_dim = get_max_dim_for_box(left, box, right, list(input_dims), prev_layers)
+        max_dim = cones.max_dim(left, box)
         dims_in = layer_dims[left:end]
         dims_out = [int(max_dim) if i > max_dim else int(i)
                     for i in box.determine_output_dimensions(list(dims_in))]
         repl = box.photon_number_transform(dims_in, dims_out)
         if isinstance(repl, Diagram) and not isinstance(repl, Box):
             repl = [_LayerView(l @ bx.dom @ r, l @ bx.cod @ r) for l, bx, r in repl.layers()]
-        if cones is None or not FORWARD_CONES:
-            prev_layers += [(left, rb) for rb in repl]
-        else:
-            # the literal walker only needs the history once the forward tracker gives up
-            history.append((left, repl))
-            for rb in repl:
-                if not cones.apply(left, rb):
-                    # an offset the backward walk would clamp: replay everything
-                    # recorded so far through the literal walker from here on
-                    cones = None
-                    prev_layers += [(lf, rb2) for lf, rp in history for rb2 in rp]
-                    break
+        for rb in repl:
+            if not cones.apply(left, rb):
+                # the reference's backward walk clamps such an offset into the frame
+                # (utils.py:466-476); no box of the reference records one, so this is a
+                # malformed photon_number_transform rather than a case to emulate
+                raise NotImplementedError(
+                    f"light-cone replacement {rb!r} of {box!r} does not fit the diagram at "
+                    f"offset {left}")
+        if trace is not None:
+            trace.append((box, list(dims_in), list(dims_out)))
         outs = box.emit(b, wires[left:end], dims_in, dims_out)
         if check:
             assert len(outs) == n_cod, (box, outs)
@@ -909,7 +863,6 @@ def compile_diagram(d: Diagram, input_dims: Optional[List[int]] = None,
                 assert b.dim(o) == dd, (box, b.dim(o), dd, dims_in, dims_out)
         wires[left:end] = outs
         layer_dims[left:end] = dims_out
-        n_wires += n_cod - n_dom
     # the per-wire identity Z boxes the reference appends (diagram.py:367-374)
     # are identities on a shared index: nothing to emit
     if own:

@@ -75,7 +75,7 @@ def pair_contract(a: np.ndarray, ia: Sequence[int], b: np.ndarray,
 
 def _greedy_order(inds_list: List[List[int]], dims: Dict[int, int],
                   output: Sequence[int], rng: random.Random | None):
-    """SSA pair order.  ``rng=None``: smallest-result-first greedy;
+    """SSA pair order.  ``rng=None``: greedy on size(result) - size(a) - size(b);
     otherwise a seeded random connected pair each step."""
     live = {k: set(v) for k, v in enumerate(inds_list)}
     count: Dict[int, int] = {}           # how many live tensors carry index q
@@ -116,7 +116,9 @@ def _greedy_order(inds_list: List[List[int]], dims: Dict[int, int],
         if rng is not None:
             i, j = rng.choice(cands)
         else:
-            i, j = min(cands, key=lambda p: (size(result_inds(*p)), p))
+            # the usual greedy score: how much the pair shrinks what is alive
+            i, j = min(cands, key=lambda p: (size(result_inds(*p)) - size(live[p[0]])
+                                             - size(live[p[1]]), p))
         new = result_inds(i, j)
         order.append((i, j, new))
         for k in (i, j):
@@ -134,21 +136,20 @@ def _greedy_order(inds_list: List[List[int]], dims: Dict[int, int],
     return order
 
 
-def contract_network(net, order: str = "greedy", seed: int = 0,
-                     arrays: List[np.ndarray] | None = None) -> np.ndarray:
-    """Dense result of ``net`` (an ``optyx_b200.core.network.Network`` or any
-    object with ``leaves``, ``dims``, ``output_inds``, ``scalar``): complex128
-    array of shape ``[dims[i] for i in output_inds]``."""
-    if arrays is None:
-        arrays = _leaves.build_all(net.leaves)
-    tensors = {k: (arr, list(l.inds)) for k, (arr, l) in
-               enumerate(zip(arrays, net.leaves))}
-    out_unique = list(dict.fromkeys(net.output_inds))
+def contract_arrays(arrays: List[np.ndarray], inds_list: List[List[int]],
+                    dims: Dict[int, int], output_inds: Sequence[int], scalar: complex = 1.0,
+                    order: str = "greedy", seed: int = 0) -> np.ndarray:
+    """Dense result of a tensor network given as plain arrays + integer index
+    labels (an index may sit on any number of tensors and may repeat on one):
+    complex128 array of shape ``[dims[i] for i in output_inds]``."""
+    tensors = {k: (np.asarray(arr), list(ix)) for k, (arr, ix) in
+               enumerate(zip(arrays, inds_list))}
+    out_unique = list(dict.fromkeys(output_inds))
     if not tensors:
         result, rinds = np.array(1.0 + 0j), []
     else:
         rng = None if order == "greedy" else random.Random(seed)
-        ssa = _greedy_order([t[1] for t in tensors.values()], net.dims,
+        ssa = _greedy_order([t[1] for t in tensors.values()], dims,
                             out_unique, rng)
         nxt = len(tensors)
         for i, j, keep in ssa:
@@ -165,13 +166,24 @@ def contract_network(net, order: str = "greedy", seed: int = 0,
     # open indices that no tensor carries cannot occur (builder adds ONES)
     result = result.transpose([rinds.index(i) for i in out_unique]) \
         if rinds else result
-    result = result * net.scalar
-    if len(out_unique) != len(net.output_inds):
+    result = result * scalar
+    if len(out_unique) != len(output_inds):
         # repeated open index: expand onto the generalised diagonal
-        full = np.zeros([net.dims[i] for i in net.output_inds], dtype=complex)
-        it = np.ndindex(*[net.dims[i] for i in out_unique])
+        full = np.zeros([dims[i] for i in output_inds], dtype=complex)
+        it = np.ndindex(*[dims[i] for i in out_unique])
         for idx in it:
             pos = dict(zip(out_unique, idx))
-            full[tuple(pos[i] for i in net.output_inds)] = result[idx]
+            full[tuple(pos[i] for i in output_inds)] = result[idx]
         result = full
     return np.require(result, dtype=complex, requirements="C")
+
+
+def contract_network(net, order: str = "greedy", seed: int = 0,
+                     arrays: List[np.ndarray] | None = None) -> np.ndarray:
+    """Dense result of ``net`` (an ``optyx_b200.core.network.Network`` or any
+    object with ``leaves``, ``dims``, ``output_inds``, ``scalar``): complex128
+    array of shape ``[dims[i] for i in output_inds]``."""
+    if arrays is None:
+        arrays = _leaves.build_all(net.leaves)
+    return contract_arrays(arrays, [list(l.inds) for l in net.leaves], net.dims,
+                           net.output_inds, net.scalar, order, seed)

@@ -21,7 +21,9 @@ def oracle_nested(net):
 
 
 def compile_channel(d: channel.Diagram):
-    """AbstractBackend._get_discopy_tensor (backends.py:406-415)."""
+    """The PRODUCT's host compile (``AbstractBackend._get_discopy_tensor``,
+    backends.py:406-415) with nested sub-networks contracted by the CPU oracle: the
+    leaf-descriptor network the CUDA path would execute."""
     if d.is_pure:
         return d.get_kraus().to_network(nested_eval=oracle_nested)
     return d.double().to_network(nested_eval=oracle_nested)
@@ -33,20 +35,35 @@ def _pad_to(arr: np.ndarray, shape) -> np.ndarray:
     return out
 
 
+def _sum_terms(d, one) -> np.ndarray:
+    # formal sum (backends.py:473-476 + diagram.py:737-765): every term on its
+    # own, zero-padded to the largest extent of each axis, then added
+    arrs = [one(t) for t in d.terms]
+    shape = tuple(max(a.shape[k] for a in arrs) for k in range(arrs[0].ndim))
+    return sum(_pad_to(a, shape) for a in arrs)
+
+
 def oracle_eval(d) -> np.ndarray:
+    """The checker: ``QuimbBackend.eval(d).tensor.array`` restated on the CPU by
+    ``oracle/compile.py`` + ``oracle/contract.py`` -- CP doubling, per-box
+    conjugation, light-cone truncation (literal backward walk), dense truncation
+    arrays and contraction, none of it shared with ``optyx_b200``."""
+    from oracle.compile import eval_dense
     if hasattr(d, "terms"):
-        # formal sum (backends.py:473-476 + diagram.py:737-765): every term on its
-        # own, zero-padded to the largest extent of each axis, then added
-        arrs = [oracle_eval(t) for t in d.terms]
-        shape = tuple(max(a.shape[k] for a in arrs) for k in range(arrs[0].ndim))
-        return sum(_pad_to(a, shape) for a in arrs)
+        return _sum_terms(d, oracle_eval)
+    return eval_dense(d)
+
+
+def product_compile_oracle_eval(d) -> np.ndarray:
+    """The product's host compile contracted by the CPU oracle (isolates the host
+    compile from the kernels)."""
+    if hasattr(d, "terms"):
+        return _sum_terms(d, product_compile_oracle_eval)
     if isinstance(d, channel.Diagram):
         net = compile_channel(d)
     else:
         net = d.to_network(nested_eval=oracle_nested)
     return contract_network(net)
-
-
 
 
 def statevector_clifford_t(n, depth, seed=0):

@@ -315,29 +315,6 @@ def test_cfg5_fusion_link_fidelity_and_feed_forward_teleport():
     assert np.allclose(got, want)
 
 
-def test_forward_cone_equals_backward_walk():
-    """The O(n) forward light-cone propagation gives the same truncation dims
-    (hence the same network) as the literal backward walk of utils.py:436-510."""
-    import math
-    from cases import fusion_link, fusion_teleport_input, teleportation
-    from optyx_b200.core import diagram as dg
-    cases_ = [lossy_hom(0.8), cfg1_interferometer(5, (1, 1, 1, 0, 0)), ghz(5, noise=0.9, open_qubits=2),
-              distinguishable_bs(np.array([0.6, 0.8j]), np.array([1, 0])),
-              cfg3_interferometer(width=4, n_photons=2, measured=2), fusion_ii_teleportation(),
-              fusion_i_spider(), fusion_link((math.cos(0.3), math.sin(0.3)), "discard"),
-              fusion_teleport_input(0.2), photonic.Create(2, 1) >> photonic.BS >> photonic.NumOp() @ photonic.Id(1),
-              photonic.Create(1, 1, 1) >> photonic.seeded_ansatz(3, 3, 1) >> photonic.PhotonThresholdMeasurement(1) @ photonic.Id(2)]
-    for d in cases_:
-        keys = []
-        for flag in (True, False):
-            dg.FORWARD_CONES = flag
-            try:
-                keys.append(compile_channel(d).structure_key())
-            finally:
-                dg.FORWARD_CONES = True
-        assert keys[0] == keys[1]
-
-
 def test_branching_sum_equals_w():
     """test_zw.py:284-292: Create(1) >> W(2) == Create(1) @ Create(0) + Create(0) @ Create(1)
     (formal sums: diagram.py:710-765, terms padded to a common shape and added)."""
