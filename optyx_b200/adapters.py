@@ -31,8 +31,6 @@ def network_from_arrays(arrays: Sequence[np.ndarray], inds: Sequence[Sequence[Ha
         arr = np.asarray(arr)
         if arr.ndim != len(names):
             raise ValueError(f"tensor of rank {arr.ndim} with {len(names)} index names")
-        if arr.ndim > nw.MAX_LEAF_RANK:
-            raise ValueError(f"leaf rank {arr.ndim} exceeds {nw.MAX_LEAF_RANK}: fuse or split it")
         ids = []
         for name, d in zip(names, arr.shape):
             k = label.setdefault(name, len(label))

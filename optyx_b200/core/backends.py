@@ -368,6 +368,9 @@ class B200Backend(AbstractBackend):
         Either a list of ``diagrams``, or a factory ``make(j)`` with ``count``:
         the latter also spreads the host compile over ``workers`` processes."""
         from .. import executor
+        if self.target_size is not None or self.distributed:
+            raise ValueError("eval_batch runs one unsliced plan per batch on one device: "
+                             "target_size / distributed apply to eval() only")
         if diagrams is not None:
             diagrams = list(diagrams)
             nets = [self._get_network(d, nested_eval=self._nested_eval) for d in diagrams]
@@ -612,10 +615,19 @@ class PermanentBackend(AbstractBackend):
                     else (box.internal_states,)
                 d_int = len(states[0])
         eye = np.eye(d_int)
-        T = np.zeros((0, 0), dtype=np.complex128)      # [photon, wire * d_int + k]
+        # T[photon, block * d_int + k]: one column BLOCK per spatial mode ever created;
+        # blocks are never removed or reordered.  ``live[w]`` = block of the w-th wire of
+        # the current diagram layer: every box is indexed through it, so a discarded
+        # wire (which leaves the diagram but stays an unmeasured output mode) cannot
+        # shift the wires to its right onto the wrong columns.
+        T = np.zeros((0, 0), dtype=np.complex128)
         env = np.zeros((0, 0), dtype=np.complex128)    # [photon, loss mode]
-        wires_alive = 0
-        measured = []                                  # per final wire: True / False / None (open)
+        live = []                                      # wire position -> block
+        state = []                                     # per block: None open / True measured / False discarded
+
+        def cols(blocks):
+            return np.concatenate([np.arange(b * d_int, (b + 1) * d_int) for b in blocks]) \
+                if len(blocks) else np.zeros(0, dtype=np.int64)
         for left, box, right in diagram.layers():
             o = len(left)
             if isinstance(box, photonic.Create):
@@ -623,11 +635,10 @@ class PermanentBackend(AbstractBackend):
                 states = box.internal_states
                 if states is not None and not isinstance(states, tuple):
                     states = (states,)
-                n_p, n_w = T.shape[0], T.shape[1] // d_int
+                n_p, n_b = T.shape[0], len(state)
                 n_new = sum(int(p) for p in box.photons)
-                new = np.zeros((n_p + n_new, (n_w + k) * d_int), dtype=np.complex128)
-                new[:n_p, :o * d_int] = T[:, :o * d_int]
-                new[:n_p, (o + k) * d_int:] = T[:, o * d_int:]
+                new = np.zeros((n_p + n_new, (n_b + k) * d_int), dtype=np.complex128)
+                new[:n_p, :n_b * d_int] = T
                 row, s_idx = n_p, 0
                 for j, cnt in enumerate(box.photons):
                     for _ in range(int(cnt)):
@@ -637,49 +648,47 @@ class PermanentBackend(AbstractBackend):
                         else:
                             vec[:] = np.asarray(states[s_idx], dtype=np.complex128)
                             s_idx += 1
-                        new[row, (o + j) * d_int:(o + j + 1) * d_int] = vec
+                        new[row, (n_b + j) * d_int:(n_b + j + 1) * d_int] = vec
                         row += 1
                 T = new
-                env = np.vstack([env, np.zeros((n_new, env.shape[1]), dtype=np.complex128)]) \
-                    if env.size or env.shape[1] else np.zeros((n_p + n_new, 0), dtype=np.complex128)
-                measured[o:o] = [None] * k
+                env = np.vstack([env, np.zeros((n_new, env.shape[1]), dtype=np.complex128)])
+                live[o:o] = list(range(n_b, n_b + k))
+                state.extend([None] * k)
             elif isinstance(box, photonic.AbstractGate):
                 w = len(box.dom)
                 assert len(box.cod) == w, "PermanentBackend: gates must preserve the mode count"
+                assert all(state[b] is None for b in live[o:o + w]), \
+                    "PermanentBackend: gate on a measured mode"
                 G = np.kron(np.asarray(box.array, dtype=np.complex128).reshape(w, w), eye)
-                T[:, o * d_int:(o + w) * d_int] = T[:, o * d_int:(o + w) * d_int] @ G
+                c = cols(live[o:o + w])
+                T[:, c] = T[:, c] @ G
             elif isinstance(box, photonic.PhotonLoss):
                 p = float(box.p_survive)
-                blk = T[:, o * d_int:(o + 1) * d_int]
+                c = cols(live[o:o + 1])
+                blk = T[:, c]
                 env = np.hstack([env, blk * (1.0 - p) ** 0.5])
-                T[:, o * d_int:(o + 1) * d_int] = blk * p ** 0.5
+                T[:, c] = blk * p ** 0.5
             elif isinstance(box, channel.Swap):
                 assert len(box.dom) == 2, "PermanentBackend: only single-mode swaps"
-                a = slice(o * d_int, (o + 1) * d_int)
-                b = slice((o + 1) * d_int, (o + 2) * d_int)
-                tmp = T[:, a].copy()
-                T[:, a] = T[:, b]
-                T[:, b] = tmp
-                measured[o], measured[o + 1] = measured[o + 1], measured[o]
+                live[o], live[o + 1] = live[o + 1], live[o]
             elif isinstance(box, channel.Measure) and all(t == "qmode" for t in box.dom.inside):
                 for j in range(len(box.dom)):
-                    assert measured[o + j] is None, "PermanentBackend: mode measured twice"
-                    measured[o + j] = True
+                    assert state[live[o + j]] is None, "PermanentBackend: mode measured twice"
+                    state[live[o + j]] = True
             elif isinstance(box, channel.Discard) and all(t == "qmode" for t in box.dom.inside):
                 for j in range(len(box.dom)):
-                    measured[o + j] = False
+                    assert state[live[o + j]] is None, "PermanentBackend: measured mode discarded"
+                    state[live[o + j]] = False
+                del live[o:o + len(box.dom)]            # the wires leave the diagram
             else:
                 raise AssertionError(f"PermanentBackend: {type(box).__name__} is not linear optical")
-        # wires still open count as measured; discarded wires stay in V (unmeasured)
-        # although the diagram no longer lists them
-        flags = [True if f is None else f for f in measured]
+        # key order = the diagram's final wires; wires still open count as measured;
+        # discarded blocks stay in V as unmeasured output modes
+        where = np.full(len(state) * d_int + env.shape[1], -1, dtype=np.int64)
+        for pos, b in enumerate(live):
+            where[b * d_int:(b + 1) * d_int] = pos
         V = np.hstack([T, env])
-        pos, where = 0, []
-        for f in flags:
-            where.extend([pos if f else -1] * d_int)
-            pos += 1 if f else 0
-        where.extend([-1] * env.shape[1])
-        return V, np.array(where, dtype=np.int64), pos
+        return V, where, len(live)
 
     def prob_dist_measured(self, diagram) -> dict:
         """Detected-count distribution of a lossy, partially distinguishable

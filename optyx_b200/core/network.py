@@ -43,7 +43,47 @@ KIND_NAMES = {
     K_DUALRAIL: "dualrail", K_PTD: "ptd", K_EMBED: "embed",
 }
 
-MAX_LEAF_RANK = 8
+MAX_LEAF_RANK = 8       # closed-form leaves decoded per axis on the device (b2_leaf_desc.dims)
+
+
+def closed_form_values(kind: int, shape: Tuple[int, ...], ipar: int = 0) -> np.ndarray:
+    """Host values (C order, complex128) of a closed-form leaf, used ONLY when its rank
+    exceeds what the device descriptor decodes (``MAX_LEAF_RANK``: a ``W`` / ``Add`` with
+    eight or more legs); such a leaf travels as ``K_DENSE`` like every other host-valued
+    array.  Same predicates as csrc/leaf_build.cu."""
+    shape = tuple(int(d) for d in shape)
+    idx = np.indices(shape, dtype=np.int64) if shape else np.zeros((0,), dtype=np.int64)
+    if kind == K_ONES:
+        return np.ones(shape, dtype=np.complex128).reshape(-1)
+    if kind == K_ONEHOT:
+        return (idx[0] == ipar).astype(np.complex128).reshape(-1)
+    if kind in (K_SUM, K_ADD):
+        rest = idx[1:].sum(axis=0)
+        hit = rest == idx[0]
+        if kind == K_ADD:
+            return hit.astype(np.complex128).reshape(-1)
+        fact = np.array([math.factorial(k) for k in range(int(max(shape)) * len(shape) + 1)],
+                        dtype=object)
+        num = fact[rest]
+        den = np.ones(shape, dtype=object)
+        for a in range(1, len(shape)):
+            den = den * fact[idx[a]]
+        vals = np.zeros(shape, dtype=np.float64)
+        vals[hit] = [math.sqrt(int(n) // int(d)) for n, d in zip(num[hit], den[hit])]
+        return vals.astype(np.complex128).reshape(-1)
+    if kind == K_MUL:
+        return (np.prod(idx[1:], axis=0) == idx[0]).astype(np.complex128).reshape(-1)
+    if kind == K_DIV:
+        return ((idx[2] != 0) & (idx[1] == idx[0] * idx[2])).astype(np.complex128).reshape(-1)
+    if kind == K_MOD2:
+        return (idx[1] % 2 == idx[0]).astype(np.complex128).reshape(-1)
+    if kind == K_DUALRAIL:
+        return ((idx[1] == 1 - idx[0]) & (idx[2] == idx[0])).astype(np.complex128).reshape(-1)
+    if kind == K_PTD:
+        return (idx[0] == np.minimum(idx[1], 1)).astype(np.complex128).reshape(-1)
+    if kind == K_EMBED:
+        return (idx[0] == idx[1]).astype(np.complex128).reshape(-1)
+    raise ValueError(f"leaf kind {kind} has no closed form")
 
 
 @dataclass
@@ -92,15 +132,25 @@ class Network:
         return sum(l.size for l in self.leaves)
 
     def validate(self) -> None:
+        """Raises ``ValueError`` on a malformed network (also under ``python -O``)."""
         for leaf in self.leaves:
-            assert len(leaf.shape) == len(leaf.inds), leaf
-            assert len(leaf.shape) <= MAX_LEAF_RANK, leaf
+            if len(leaf.shape) != len(leaf.inds):
+                raise ValueError(f"leaf {leaf.name!r}: {len(leaf.shape)} axes, {len(leaf.inds)} indices")
+            # host-valued leaves (VEC / DENSE) are flat on the device, so their rank is
+            # unbounded; closed-form kinds are decoded per axis by the array-build kernel
+            if leaf.kind not in (K_VEC, K_DENSE) and len(leaf.shape) > MAX_LEAF_RANK:
+                raise ValueError(f"closed-form leaf {leaf.name!r} of rank {len(leaf.shape)} > "
+                                 f"{MAX_LEAF_RANK}: NetworkBuilder.add converts these to DENSE")
             for d, i in zip(leaf.shape, leaf.inds):
-                assert self.dims[i] == d, (leaf, i, self.dims[i])
+                if self.dims.get(i) != d:
+                    raise ValueError(f"leaf {leaf.name!r}: index {i} has extent {self.dims.get(i)}, "
+                                     f"axis has {d}")
             if leaf.kind in (K_VEC, K_DENSE):
-                assert leaf.params is not None and leaf.params.size == leaf.size
+                if leaf.params is None or leaf.params.size != leaf.size:
+                    raise ValueError(f"leaf {leaf.name!r}: host values missing or of the wrong size")
         for i in self.output_inds:
-            assert i in self.dims
+            if i not in self.dims:
+                raise ValueError(f"open index {i} has no extent")
 
 
 class NetworkBuilder:
@@ -150,6 +200,8 @@ class NetworkBuilder:
     def add(self, kind: int, inds: Sequence[int], ipar: int = 0,
             params=None, name: str = "") -> None:
         shape = tuple(self.dim(i) for i in inds)
+        if params is None and kind not in (K_VEC, K_DENSE) and len(shape) > MAX_LEAF_RANK:
+            kind, params, ipar = K_DENSE, closed_form_values(kind, shape, ipar), 0
         if params is not None:
             params = np.ascontiguousarray(params, dtype=np.complex128).reshape(-1)
         self.leaves.append(Leaf(kind, shape, tuple(inds), ipar, params, name))

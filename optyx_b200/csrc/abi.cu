@@ -6,7 +6,7 @@
 namespace b2 {
 
 static thread_local char g_err[512] = "";
-static int g_sms = 0;
+static int g_sms[kMaxDevices] = {};   // per device
 static thread_local const char* g_last_kernel = "";
 
 void set_last_kernel(const char* name) { g_last_kernel = name; }
@@ -28,18 +28,23 @@ int check_launch(const char* what) {
 }
 
 // No CPU fallback: without a device every compute entry point fails here.
+int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-    if (g_sms > 0) return g_sms;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return -1; }
+    if (dev >= 0 && dev < kMaxDevices && g_sms[dev] > 0) return g_sms[dev];
     int sms = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess || sms <= 0) {
         set_error("cannot query SM count: %s", cudaGetErrorString(e));
         return -1;
     }
-    g_sms = sms;
+    if (dev >= 0 && dev < kMaxDevices) g_sms[dev] = sms;
     return sms;
 }
 

@@ -33,6 +33,20 @@ __device__ __forceinline__ C cmul(const C a, const C b) {
     return r;
 }
 
+// "done once PER DEVICE" flags (kernel function attributes are per device, and one
+// process may drive several devices)
+constexpr int kMaxDevices = 64;
+struct once_flags { bool done[kMaxDevices] = {}; };
+int current_device();                       // -1 without a device
+inline bool is_done(const once_flags& f) {
+    const int d = current_device();
+    return d >= 0 && d < kMaxDevices && f.done[d];
+}
+inline void mark_done(once_flags& f) {
+    const int d = current_device();
+    if (d >= 0 && d < kMaxDevices) f.done[d] = true;
+}
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();

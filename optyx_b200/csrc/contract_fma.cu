@@ -454,8 +454,8 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
 #define B2_FMA_LAUNCH_R(KPV, RV) B2_FMA_LAUNCH_RM(KPV, RV, 1)
 #define B2_FMA_LAUNCH_RM(KPV, RV, RMV)                                                       \
     do {                                                                                     \
-        static bool attr_done = false;                                                       \
-        if (!attr_done) {                                                                    \
+        static b2::once_flags attr_done;                                                       \
+        if (!b2::is_done(attr_done)) {                                                                    \
             cudaError_t e = cudaFuncSetAttribute(contract_fma_kernel<T, KPV, RV, RMV>,       \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  FM_SMEM_MAX);                               \
@@ -463,7 +463,7 @@ int launch_fma_t(const fm_desc& d, long long n_tiles, const void* a, const void*
                 set_error("fma smem attr: %s", cudaGetErrorString(e));                       \
                 return 1;                                                                    \
             }                                                                                \
-            attr_done = true;                                                                \
+            b2::mark_done(attr_done);                                                                \
         }                                                                                    \
         /* persistent grid = exactly one resident wave (every CTA gets an equal share   \
            of the tiles; a partial second wave would idle most of the GPU) */           \

@@ -64,20 +64,22 @@ template <bool SPLITK>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
                           const double2* __restrict__ B, double2* __restrict__ Cout,
-                          long long M, long long N, long long K, int tiles_m, int a_kfast,
-                          int b_kfast, double alpha_re, double alpha_im, int accumulate,
-                          int ksplit) {
+                          long long M, long long N, long long K, int tiles_m, long long tiles_mn,
+                          int a_kfast, int b_kfast, double alpha_re, double alpha_im,
+                          int accumulate, int ksplit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     gemm_smem& sm = *reinterpret_cast<gemm_smem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
-    const long long tile = blockIdx.x;
+    // grid.x = batch x tiles (the batch extent -- eval batch times every hyper-index
+    // batch mode -- can exceed the 65535 limit of grid.y)
+    const long long tile = blockIdx.x % tiles_mn, batch_id = blockIdx.x / tiles_mn;
     const long long m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
     const int f_b = 0, f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
 
     long long ba, bb, bc;
-    decode3(blockIdx.y, g, f_b, g.n_batch, ba, bb, bc);
+    decode3(batch_id, g, f_b, g.n_batch, ba, bb, bc);
     A += ba; B += bb; Cout += bc;
 
     // per-tile row / column offsets (index permutation, decoded once per CTA)
@@ -287,20 +289,20 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
     const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
     const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    if (tiles_m * tiles_n > 2147483647ll || Bt > 65535) {
+    if (tiles_m * tiles_n * Bt > 2147483647ll) {
         set_error("b2_contract_gemm: grid too large (tiles=%lld batch=%lld)", tiles_m * tiles_n, Bt);
         return 1;
     }
-    static bool attr_set = false;
+    static b2::once_flags attr_set;
     const int smem = (int)sizeof(gemm_smem);
-    if (!attr_set) {
+    if (!b2::is_done(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(contract_gemm_c128_kernel<false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(contract_gemm_c128_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
-        attr_set = true;
+        b2::mark_done(attr_set);
     }
     // split-K when the tiles alone leave most SMs idle (small M x N, long K: the
     // reduction-heavy pairs of photonic networks).  C must be one dense block so
@@ -325,14 +327,14 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         }
     }
     set_last_kernel(ksplit > 1 ? "gemm_splitk" : "gemm");
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt, (unsigned)ksplit);
+    dim3 grid((unsigned)(tiles_m * tiles_n * Bt), 1u, (unsigned)ksplit);
     if (ksplit > 1)
         contract_gemm_c128_kernel<true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
             g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
-            a_kfast, b_kfast, alpha_re, alpha_im, accumulate, ksplit);
+            tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, ksplit);
     else
         contract_gemm_c128_kernel<false><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
             g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
-            a_kfast, b_kfast, alpha_re, alpha_im, accumulate, 1);
+            tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, 1);
     return check_launch("b2_contract_gemm");
 }

@@ -161,8 +161,8 @@ template <int NT>
 __global__ void __launch_bounds__(G4_THREADS, 1)
 contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* __restrict__ A,
                          const float2* __restrict__ B, float2* __restrict__ Cout, long long M,
-                         long long N, long long K, int tiles_m, int a_kfast, int b_kfast,
-                         float alpha_re, float alpha_im, int accumulate) {
+                         long long N, long long K, int tiles_m, long long tiles_mn, int a_kfast,
+                         int b_kfast, float alpha_re, float alpha_im, int accumulate) {
     extern __shared__ __align__(1024) unsigned char g4_raw[];
     g4_smem<NT>& sm = *reinterpret_cast<g4_smem<NT>*>(g4_raw);
     constexpr int NP = 2 * NT;                               // real columns of D
@@ -174,13 +174,14 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
     constexpr int B_ITEMS = NT * G4_KG / G4_CONV;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile = blockIdx.x;
+    // grid.x = batch x tiles (a batch extent can exceed the 65535 limit of grid.y)
+    const long long tile = blockIdx.x % tiles_mn, batch_id = blockIdx.x / tiles_mn;
     const long long m0 = (tile % tiles_m) * G4_BM, n0 = (tile / tiles_m) * NT;
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
 
     {
         long long ba, bb, bc;
-        g4_decode3(blockIdx.y, g, 0, g.n_batch, ba, bb, bc);
+        g4_decode3(batch_id, g, 0, g.n_batch, ba, bb, bc);
         A += ba; B += bb; Cout += bc;
     }
     if (tid < G4_BM) {
@@ -447,21 +448,22 @@ static int launch_c64_nt(const b2_gemm_modes& g, const float2* a, const float2* 
                          long long Bt, long long M, long long N, long long K, int a_kfast,
                          int b_kfast, double ar, double ai, int accumulate, cudaStream_t s) {
     const long long tiles_m = (M + G4_BM - 1) / G4_BM, tiles_n = (N + NT - 1) / NT;
-    if (tiles_m * tiles_n > 2147483647ll || Bt > 65535) {
+    if (tiles_m * tiles_n * Bt > 2147483647ll) {
         set_error("b2_contract_gemm(c64): grid too large (tiles=%lld batch=%lld)", tiles_m * tiles_n, Bt);
         return 1;
     }
     const int smem = (int)sizeof(g4_smem<NT>) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static b2::once_flags attr_set;
+    if (!b2::is_done(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(contract_gemm_c64_kernel<NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("b2_contract_gemm(c64): smem attr: %s", cudaGetErrorString(e)); return 1; }
-        attr_set = true;
+        b2::mark_done(attr_set);
     }
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)Bt);
+    dim3 grid((unsigned)(tiles_m * tiles_n * Bt));
     contract_gemm_c64_kernel<NT><<<grid, G4_THREADS, smem, s>>>(
-        g, a, b, c, M, N, K, (int)tiles_m, a_kfast, b_kfast, (float)ar, (float)ai, accumulate);
+        g, a, b, c, M, N, K, (int)tiles_m, tiles_m * tiles_n, a_kfast, b_kfast, (float)ar,
+        (float)ai, accumulate);
     return check_launch("b2_contract_gemm(c64 tcgen05)");
 }
 

@@ -125,8 +125,8 @@ extern "C" int b2_contract_small_groups(const b2_small_step* steps_dev,
     }
     if (num_sms() <= 0) return 1;
     cudaStream_t s = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static b2::once_flags attr_done;
+    if (!b2::is_done(attr_done)) {
         cudaError_t e1 = cudaFuncSetAttribute(contract_small_groups_kernel<double>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SCRATCH_MAX);
         cudaError_t e2 = cudaFuncSetAttribute(contract_small_groups_kernel<float>,
@@ -136,7 +136,7 @@ extern "C" int b2_contract_small_groups(const b2_small_step* steps_dev,
                       cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
             return 1;
         }
-        attr_done = true;
+        b2::mark_done(attr_done);
     }
     if (dtype == B2_C128)
         contract_small_groups_kernel<double><<<(unsigned)n_groups, SM_THREADS, scratch_bytes, s>>>(

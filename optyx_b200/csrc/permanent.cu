@@ -404,11 +404,11 @@ extern "C" int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
     if (blocks > cap) blocks = cap;
 #define B2_PH_LAUNCH(NM)                                                                       \
     do {                                                                                       \
-        static bool attr_done = false;                                                         \
-        if (!attr_done) {                                                                      \
+        static b2::once_flags attr_done;                                                         \
+        if (!b2::is_done(attr_done)) {                                                                      \
             cudaFuncSetAttribute(permanent_hist_kernel<NM>,                                    \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);     \
-            attr_done = true;                                                                  \
+            b2::mark_done(attr_done);                                                                  \
         }                                                                                      \
         permanent_hist_kernel<NM><<<(unsigned)blocks, PH_WARPS * 32, smem, s>>>(               \
             (const double2*)v_dev, n, m, (const long long*)binom_dev, mode_stride_dev, scale,  \
@@ -416,11 +416,11 @@ extern "C" int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
     } while (0)
     if (n <= 8 && n_configs >= 4096) {
         // few photons, many configurations: one thread per configuration
-        static bool attr_done = false;
-        if (!attr_done) {
+        static b2::once_flags attr_done;
+        if (!b2::is_done(attr_done)) {
             cudaFuncSetAttribute(permanent_hist_thread_kernel<8>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_done = true;
+            b2::mark_done(attr_done);
         }
         const size_t smem_t = (size_t)(n * m) * sizeof(double2) +
                               (size_t)(n_bins <= PH_SMEM_BINS ? n_bins : 0) * sizeof(double) +
@@ -470,11 +470,11 @@ extern "C" int b2_permanent_amplitudes(const void* u_dev, int32_t m, const int32
     if (blocks > cap) blocks = cap;
 #define B2_PERM_LAUNCH(NM)                                                                     \
     do {                                                                                       \
-        static bool attr_done = false;                                                         \
-        if (!attr_done) {                                                                      \
+        static b2::once_flags attr_done;                                                         \
+        if (!b2::is_done(attr_done)) {                                                                      \
             cudaFuncSetAttribute(permanent_kernel<NM>,                                         \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
-            attr_done = true;                                                                  \
+            b2::mark_done(attr_done);                                                                  \
         }                                                                                      \
         permanent_kernel<NM><<<(unsigned)blocks, PM_WARPS * 32, smem, s>>>(                    \
             (const double2*)u_dev, m, n, rows_dev, cols_dev, norm_dev, n_configs,              \

@@ -48,8 +48,9 @@ def run_sliced(sess, net):
     the whole (replica) and no collective runs."""
     rank, size = world()
     plan = sess.plan
-    if sess.desc_dev is None:
-        sess.set_leaves([net])
+    # always upload this net's host-computed values: a reused Session may have seen a
+    # structurally identical net with other parameters (the descriptor table is cached)
+    sess.set_leaves([net])
     sess.build_leaves()
     if plan.nslices <= 1 or size == 1:
         sess.contract(net.scalar)

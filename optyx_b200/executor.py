@@ -36,13 +36,19 @@ def leaf_table(net: Network, plan: Plan) -> Tuple[np.ndarray, np.ndarray]:
     poff = 0
     for k, leaf in enumerate(net.leaves):
         row = table[k]
-        row["kind"], row["ndim"], row["ipar"] = leaf.kind, len(leaf.shape), leaf.ipar
-        row["dims"][:len(leaf.shape)] = leaf.shape
+        row["kind"], row["ipar"] = leaf.kind, leaf.ipar
         row["offset"], row["nelem"] = plan.leaf_offsets[k], leaf.size
         if leaf.kind in (K_VEC, K_DENSE):
+            # host-valued leaves are copied element by element: flat on the device, any
+            # rank (the planner alone knows their shape and indices)
+            row["ndim"] = 1
+            row["dims"][0] = min(leaf.size, 2 ** 31 - 1)
             row["poff"] = poff
             params.append(np.asarray(leaf.params, dtype=np.complex128).reshape(-1))
             poff += leaf.size
+        else:
+            row["ndim"] = len(leaf.shape)
+            row["dims"][:len(leaf.shape)] = leaf.shape
     unit = table[n]
     unit["kind"], unit["ndim"] = K_ONES, 1
     unit["dims"][0] = 1
@@ -82,6 +88,7 @@ class Session:
         self.desc_dev = None
         self.params_dev = None
         self.params_host = None
+        self._params_copied = None
         self.n_leaves = 0
         self.params_stride = 0
         self.graph = None
@@ -168,11 +175,17 @@ class Session:
                                            pin_memory=True)
             self.params_dev = torch.empty((plan.batch, len(p0)), dtype=torch.complex128,
                                           device=self.device)
+        if self._params_copied is not None:
+            # the previous async H2D copy may still be reading the pinned buffer
+            self._params_copied.synchronize()
         ph = self.params_host.numpy()
         ph[0] = p0
         for e in range(1, plan.batch):
             ph[e] = params_vector(nets[e])
         self.params_dev.copy_(self.params_host, non_blocking=True)
+        if self._params_copied is None:
+            self._params_copied = torch.cuda.Event()
+        self._params_copied.record()
 
     def build_leaves(self) -> None:
         plan = self.plan

@@ -102,9 +102,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
+    # build() returns at once when the library's stamp matches the sources; a stale
+    # library (sources edited since the last build: struct layouts may have drifted)
+    # is rebuilt, never loaded
+    try:
         path = _build.build()
+    except (RuntimeError, OSError) as exc:
+        raise B2Error(f"liboptyx_b200.so is missing or stale and cannot be rebuilt: {exc}") from exc
     lib = C.CDLL(path)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     lib.b2_abi_version.restype = C.c_int

@@ -122,21 +122,15 @@ def test_permanent_backend_host_logic():
         PermanentBackend._single_particle(photonic.BS)
 
 
-def test_lossy_distinguishable_photon_rows_against_the_tensor_network_oracle():
-    """Host half of PermanentBackend.prob_dist_measured: the photon row vectors over
-    (spatial mode x internal state + loss environments) and the measured-mode map,
-    contracted here with the ORACLE's permanent and marginalised in Python, give
-    the same detected-count distribution as the CP-doubled tensor-network oracle."""
+def _rows_histogram(d):
+    """Detected-count distribution from ``PermanentBackend._photon_rows`` with the
+    ORACLE's permanent, marginalised in Python (what b2_permanent_histogram does)."""
     import itertools
     from math import factorial
-    import cases
-    from oracle import evalresult as oe
     from oracle.permanent import npperm
     from optyx_b200.core.backends import PermanentBackend
-    d = cases.cfg3_interferometer(width=4, n_photons=2, measured=2, inflate=False)
     V, where, k = PermanentBackend._photon_rows(d)
     n, M = V.shape
-    assert (n, M, k) == (2, 16, 2) and np.allclose((np.abs(V) ** 2).sum(axis=1), 1.0)
     hist = {}
     for cols in itertools.combinations_with_replacement(range(M), n):
         occ = np.bincount(cols, minlength=M)
@@ -146,8 +140,101 @@ def test_lossy_distinguishable_photon_rows_against_the_tensor_network_oracle():
             if where[c] >= 0:
                 key[where[c]] += 1
         hist[tuple(key)] = hist.get(tuple(key), 0.0) + w
+    return hist, (V, where, k)
+
+
+def test_lossy_distinguishable_photon_rows_against_the_tensor_network_oracle():
+    """Host half of PermanentBackend.prob_dist_measured: the photon row vectors over
+    (spatial mode x internal state + loss environments) and the measured-mode map,
+    contracted here with the ORACLE's permanent and marginalised in Python, give
+    the same detected-count distribution as the CP-doubled tensor-network oracle."""
+    import cases
+    from oracle import evalresult as oe
+    d = cases.cfg3_interferometer(width=4, n_photons=2, measured=2, inflate=False)
+    hist, (V, where, k) = _rows_histogram(d)
+    n, M = V.shape
+    assert (n, M, k) == (2, 16, 2) and np.allclose((np.abs(V) ** 2).sum(axis=1), 1.0)
     inflated = cases.cfg3_interferometer(width=4, n_photons=2, measured=2)
     want = oe.prob_dist_mixed(cases.oracle_eval(inflated), list(inflated.cod.inside))
     total = sum(want.values())
     assert sum(hist.values()) == pytest.approx(1.0, abs=1e-12)
     assert max(abs(hist.get(key, 0.0) - v / total) for key, v in want.items()) <= 1e-12
+
+
+def _discard_cases():
+    from optyx_b200 import photonic
+    from optyx_b200.core.channel import Diagram, mode, qmode
+    P, q, cl = photonic, qmode, Diagram.id(mode)
+    meas = P.NumberResolvingMeasurement
+    u3 = P.Create(1, 1, 1) >> P.seeded_ansatz(3, 3, seed=4)
+    return {
+        # per-mode discards: must equal one Discard(q ** 2)
+        "per_mode_discards": u3 >> meas(1) @ P.Discard(1) @ P.Discard(1),
+        "block_discard": u3 >> meas(1) @ P.Discard(2),
+        "discard_id_discard": u3 >> P.Discard(1) @ meas(1) @ P.Discard(1),
+        # a gate AFTER a discard acts on the wires that are left
+        "discard_then_gate": (P.Create(1, 1, 1) >> P.PhotonLoss(0.8) @ q ** 2 >> P.BS @ q
+                              >> P.Discard(1) @ q ** 2 >> P.BBS(0.3) >> meas(2)),
+        "interleaved": (P.Create(1, 0, 1, 1) >> P.seeded_ansatz(4, 3, seed=2)
+                        >> meas(1) @ P.Discard(1) @ q ** 2 >> cl @ P.TBS(0.4)
+                        >> cl @ P.Discard(1) @ meas(1)),
+        "swap_after_discard": (u3 >> P.Discard(1) @ q ** 2 >> P.Swap(1, 1) >> P.Id(1) @ P.PhotonLoss(0.5)
+                               >> meas(2)),
+    }
+
+
+@pytest.mark.parametrize("name", ["per_mode_discards", "block_discard", "discard_id_discard",
+                                  "discard_then_gate", "interleaved", "swap_after_discard"])
+def test_photon_rows_index_boxes_through_the_live_wire_map(name):
+    """A Discard removes its wire from the diagram but not from the output modes: every
+    later box must act on the wires that are LEFT (gates / measures after a
+    discard hit the wrong columns).  Checked against the CP-doubled oracle."""
+    import cases
+    from oracle import evalresult as oe
+    d = _discard_cases()[name]
+    hist, (V, where, k) = _rows_histogram(d)
+    assert k == len(d.cod)
+    want = oe.prob_dist_mixed(cases.oracle_eval(d), list(d.cod.inside))
+    total = sum(want.values())
+    assert sum(hist.values()) == pytest.approx(1.0, abs=1e-12)
+    keys = set(want) | set(hist)
+    assert max(abs(hist.get(key, 0.0) - want.get(key, 0.0) / total) for key in keys) <= 1e-12
+
+
+def test_photon_rows_per_mode_discards_equal_a_block_discard():
+    from optyx_b200.core.backends import PermanentBackend
+    c = _discard_cases()
+    _, w1, k1 = PermanentBackend._photon_rows(c["per_mode_discards"])
+    _, w2, k2 = PermanentBackend._photon_rows(c["block_discard"])
+    assert k1 == k2 == 1 and list(w1) == list(w2) == [0, -1, -1]
+    _, w3, k3 = PermanentBackend._photon_rows(c["discard_id_discard"])
+    assert k3 == 1 and list(w3) == [-1, 0, -1]
+
+
+def test_leaf_rank_is_unbounded_for_host_valued_leaves():
+    """DENSE / VEC leaves are flat on the device (any rank); closed-form
+    kinds above the descriptor's 8 axes are built on the host as DENSE."""
+    import cases
+    from oracle.contract import contract_network
+    from optyx_b200 import executor
+    from optyx_b200.adapters import network_from_arrays
+    from optyx_b200.core import network as nw, zw
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((2,) * 10) + 1j * rng.standard_normal((2,) * 10)
+    b = rng.standard_normal((2,) * 4)
+    net = network_from_arrays([a, b], [tuple("abcdefghij"), tuple("ghij")], tuple("abcdef"))
+    net.validate()
+    plan = executor.get_plan(net)
+    table, _ = executor.leaf_table(net, plan)
+    assert table[0]["ndim"] == 1 and table[0]["dims"][0] == 1024
+    want = np.einsum("abcdefghij,ghij->abcdef", a, b)
+    assert np.allclose(emulate_plan(net, plan)[0], want)
+    # a 9-legged W: rank 10 closed form -> DENSE, same values as the oracle's generator
+    d = zw.Create(2) >> zw.W(9)
+    net = d.to_network()
+    w = [l for l in net.leaves if l.name == "W"][0]
+    assert w.kind == nw.K_DENSE and len(w.shape) == 10
+    assert np.allclose(contract_network(net), cases.oracle_eval(d))
+    bad = nw.Network([nw.Leaf(nw.K_SUM, (2,) * 10, tuple(range(10)))], {i: 2 for i in range(10)}, ())
+    with pytest.raises(ValueError):
+        bad.validate()
