@@ -291,9 +291,13 @@ class B200Backend(AbstractBackend):
     non-zero entries, see ``_to_host``).
     """
 
-    def __init__(self, dtype="complex128", target_size: Optional[int] = None, trials: int = 8,
+    def __init__(self, hyperoptimiser=None, contraction_params: Optional[dict] = None,
+                 dtype="complex128", target_size: Optional[int] = None, trials: int = 8,
                  seed: int = 0, distributed: bool = False, keep_on_device: bool = True,
                  sparse_d2h: bool = True):
+        # backends.py:436-455: stored as given, checked when a term is contracted (526-534)
+        self.hyperoptimiser = hyperoptimiser
+        self.contraction_params = contraction_params or {}
         self.dtype = np.dtype(dtype)
         if self.dtype not in (np.dtype(np.complex128), np.dtype(np.complex64)):
             raise ValueError(f"Unsupported dtype {dtype}: use complex128 or complex64")
@@ -407,17 +411,68 @@ class B200Backend(AbstractBackend):
                                       _device=dev[e] if self.keep_on_device else None))
         return results
 
+    _EXACT = {"HyperOptimizer", "ReusableHyperOptimizer"}
+    _APPROX = {"HyperCompressedOptimizer", "ReusableHyperCompressedOptimizer"}
+
+    def _optimiser_kind(self) -> Optional[str]:
+        """backends.py:516-534: exact / compressed cotengra optimisers (recognised by
+        class name, cotengra itself is never imported) or a ``planner.GivenTree``;
+        anything else is the reference's ``ValueError``."""
+        opt = self.hyperoptimiser
+        if opt is None:
+            return None
+        from ..planner import GivenTree
+        if isinstance(opt, GivenTree):
+            return "tree"
+        names = {c.__name__ for c in type(opt).__mro__}
+        if names & self._APPROX:
+            return "approx"
+        if names & self._EXACT:
+            return "exact"
+        raise ValueError("Unsupported hyperoptimiser type. Use ReusableHyperOptimizer, "
+                         "HyperOptimizer, ReusableHyperCompressedOptimizer, or "
+                         f"HyperCompressedOptimizer. Got: {type(opt)}")
+
+    def _tree_for(self, net: nw.Network, kind: str):
+        """(ssa_path, sliced index labels) of the contraction tree the optimiser finds
+        for ``net``: cotengra's ``opt.search(inputs, output, size_dict)`` ->
+        ``tree.get_ssa_path()`` / ``tree.sliced_inds`` (what quimb's
+        ``contract(optimize=opt)`` does with it, backends.py:539-545)."""
+        opt = self.hyperoptimiser
+        if kind == "tree":
+            return opt.ssa_path, tuple(opt.sliced_inds)
+        name = {q: f"i{q}" for q in net.dims}
+        back = {v: k for k, v in name.items()}
+        inputs = [tuple(name[q] for q in dict.fromkeys(leaf.inds)) for leaf in net.leaves]
+        output = tuple(name[q] for q in dict.fromkeys(net.output_inds))
+        size_dict = {name[q]: int(d) for q, d in net.dims.items()}
+        tree = opt.search(inputs, output, size_dict)
+        sliced = getattr(tree, "sliced_inds", ()) or ()
+        return [tuple(int(i) for i in e) for e in tree.get_ssa_path()], \
+            tuple(back[q] for q in sliced)
+
     def eval_network(self, net: nw.Network):
         """Device tensor of one network (plan cached by structure)."""
         from .. import executor
-        plan = executor.get_plan(net, dtype=self.dtype, target_size=self.target_size,
-                                 trials=self.trials, seed=self.seed)
+        kind = self._optimiser_kind()
+        if kind == "approx":
+            from .. import compressed
+            return compressed.contract_compressed(net, dtype=self.dtype, **self.contraction_params)
+        if kind in ("exact", "tree") and len(net.leaves) >= 2:
+            ssa_path, sliced = self._tree_for(net, kind)
+            plan = executor.get_plan(net, dtype=self.dtype, ssa_path=ssa_path, sliced_inds=sliced)
+        else:
+            plan = executor.get_plan(net, dtype=self.dtype, target_size=self.target_size,
+                                     trials=self.trials, seed=self.seed)
         self.last_plan = plan
         sess = executor.Session(plan)
         if self.distributed:
             from .. import dist
-            return dist.run_sliced(sess, net)
-        return sess.run([net])[0]
+            out = dist.run_sliced(sess, net)
+        else:
+            out = sess.run([net])[0]
+        self.last_h2d_bytes = sess.h2d_bytes
+        return out
 
     # results of at least this many bytes are scanned for sparsity before the copy
     SPARSE_MIN_BYTES = 32 << 20

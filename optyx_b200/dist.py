@@ -42,15 +42,18 @@ def allreduce_sum_(tensor):
     return tensor
 
 
-def run_sliced(sess, net):
+def run_sliced(sess, net, upload: bool = True):
     """Build leaves on every rank (cheap, deterministic), contract this rank's
     slices, all-reduce the output.  With an unsliced plan every rank computes
-    the whole (replica) and no collective runs."""
+    the whole (replica) and no collective runs.  ``upload=False``: the caller has
+    already uploaded THIS net's values with ``sess.set_leaves`` (timing loops)."""
     rank, size = world()
     plan = sess.plan
-    # always upload this net's host-computed values: a reused Session may have seen a
-    # structurally identical net with other parameters (the descriptor table is cached)
-    sess.set_leaves([net])
+    # by default always upload this net's host-computed values: a reused Session may
+    # have seen a structurally identical net with other parameters (the descriptor
+    # table is cached)
+    if upload or sess.desc_dev is None:
+        sess.set_leaves([net])
     sess.build_leaves()
     if plan.nslices <= 1 or size == 1:
         sess.contract(net.scalar)

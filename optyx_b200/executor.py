@@ -12,7 +12,7 @@ import numpy as np
 
 from . import runtime as rt
 from .core.network import K_DENSE, K_ONES, K_VEC, Network
-from .planner import ARENA, OUT, WS, Plan, Step, plan_network
+from .planner import ARENA, OUT, WS, Plan, Step, plan_from_ssa_path, plan_network
 
 
 def _torch():
@@ -183,6 +183,7 @@ class Session:
         for e in range(1, plan.batch):
             ph[e] = params_vector(nets[e])
         self.params_dev.copy_(self.params_host, non_blocking=True)
+        self.h2d_bytes = int(self.params_host.numel() * 16 + self.desc_dev.numel())
         if self._params_copied is None:
             self._params_copied = torch.cuda.Event()
         self._params_copied.record()
@@ -385,15 +386,24 @@ _PLAN_CACHE: Dict[tuple, Plan] = {}
 
 
 def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None,
-             trials: int = 8, seed: int = 0, gemm_threshold=(32, 16, 8, 4.0)) -> Plan:
+             trials: int = 8, seed: int = 0, gemm_threshold=(32, 16, 8, 4.0),
+             ssa_path=None, sliced_inds=()) -> Plan:
     """Plan cache keyed by network *structure* (the counterpart of cotengra's
-    ReusableHyperOptimizer the reference accepts, backends.py:49-56, 436-455)."""
+    ReusableHyperOptimizer the reference accepts, backends.py:49-56, 436-455).
+    ``ssa_path`` (+ ``sliced_inds``): execute that contraction tree instead of
+    searching for one (``planner.plan_from_ssa_path``)."""
+    tree_key = None if ssa_path is None else (tuple(tuple(int(i) for i in e) for e in ssa_path),
+                                              tuple(int(q) for q in sliced_inds))
     key = (net.structure_key(), np.dtype(dtype).str, batch, target_size, trials, seed,
-           tuple(gemm_threshold))
+           tuple(gemm_threshold), tree_key)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
-        plan = plan_network(net, dtype=dtype, batch=batch, trials=trials, seed=seed,
-                            target_size=target_size, gemm_threshold=gemm_threshold)
+        if ssa_path is not None:
+            plan = plan_from_ssa_path(net, ssa_path, sliced_inds, dtype=dtype, batch=batch,
+                                      gemm_threshold=gemm_threshold)
+        else:
+            plan = plan_network(net, dtype=dtype, batch=batch, trials=trials, seed=seed,
+                                target_size=target_size, gemm_threshold=gemm_threshold)
         _PLAN_CACHE[key] = plan
     return plan
 

@@ -761,6 +761,68 @@ def _reallocate_for_slices(steps: List[Step], batch: int) -> None:
                 per.release(lay.offset - base, lay.size * batch)
 
 
+@dataclass
+class GivenTree:
+    """An explicit contraction tree for ``B200Backend(hyperoptimiser=...)``: SSA pair
+    order over the network's leaves plus the indices to slice (network index labels)."""
+    ssa_path: List[Tuple[int, ...]]
+    sliced_inds: Tuple[int, ...] = ()
+
+
+def info_from_ssa_path(net: Network, ssa_path: Sequence[Sequence[int]],
+                       sliced_inds: Sequence[int] = ()) -> PathInfo:
+    """A contraction tree found elsewhere -- cotengra's ``tree.get_ssa_path()`` and
+    ``tree.sliced_inds`` for the same tensors in the same order (the reference hands its
+    network to a cotengra ``HyperOptimizer``, optyx/core/backends.py:436-455, 539-545) --
+    as a ``PathInfo``.  SSA form: leaves are ids ``0..n-1``, the k-th entry creates id
+    ``n + k``; an entry with more than two ids is contracted left to right.  Leftover
+    components (a path that stops early) are multiplied together at the end."""
+    n = len(net.leaves)
+    inputs = [frozenset(l.inds) for l in net.leaves]
+    output = frozenset(net.output_inds)
+    sliced = tuple(dict.fromkeys(int(q) for q in sliced_inds))
+    for q in sliced:
+        if q not in net.dims:
+            raise ValueError(f"sliced index {q} is not an index of the network")
+        if q in output:
+            raise ValueError(f"sliced index {q} is an open index: only summed indices can be sliced")
+    live = set(range(n))
+    path: List[Tuple[int, int]] = []
+    rename: Dict[int, int] = {}          # caller's SSA id -> ours (differs after a >2-way entry)
+    nxt_theirs, nxt_ours = n, n
+    for entry in ssa_path:
+        ids = [rename.get(int(i), int(i)) for i in entry]
+        if len(ids) < 2 or len(set(ids)) != len(ids) or any(i not in live for i in ids):
+            raise ValueError(f"invalid SSA path entry {tuple(entry)}: ids must be distinct, "
+                             "live tensors")
+        cur = ids[0]
+        for other in ids[1:]:
+            path.append((cur, other))
+            live.discard(cur)
+            live.discard(other)
+            cur = nxt_ours
+            live.add(cur)
+            nxt_ours += 1
+        rename[nxt_theirs] = cur
+        nxt_theirs += 1
+    rest = sorted(live)
+    while len(rest) > 1:
+        path.append((rest[0], rest[1]))
+        rest = rest[2:] + [nxt_ours]
+        nxt_ours += 1
+    return analyse_path(inputs, net.dims, output, path, sliced)
+
+
+def plan_from_ssa_path(net: Network, ssa_path: Sequence[Sequence[int]],
+                       sliced_inds: Sequence[int] = (), dtype=np.complex128, batch: int = 1,
+                       gemm_threshold: Tuple = (32, 16, 8, 4.0)) -> Plan:
+    """Executable plan of a GIVEN contraction tree (see ``info_from_ssa_path``):
+    layouts, kernel choice per step, slicing by pointer offsets, workspace."""
+    info = info_from_ssa_path(net, ssa_path, sliced_inds) if len(net.leaves) >= 2 \
+        else PathInfo([], (), 0.0, 0.0, 1, [])
+    return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)
+
+
 def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int = 8,
                  seed: int = 0, target_size: Optional[float] = None,
                  gemm_threshold: Tuple = (32, 16, 8, 4.0)) -> Plan:

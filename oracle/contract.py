@@ -142,9 +142,15 @@ def contract_arrays(arrays: List[np.ndarray], inds_list: List[List[int]],
     """Dense result of a tensor network given as plain arrays + integer index
     labels (an index may sit on any number of tensors and may repeat on one):
     complex128 array of shape ``[dims[i] for i in output_inds]``."""
+    arrays, inds_list = list(arrays), [list(ix) for ix in inds_list]
+    out_unique = list(dict.fromkeys(output_inds))
+    carried = {q for ix in inds_list for q in ix}
+    for q in out_unique:
+        if q not in carried:             # a bare wire (identity diagram): free end = all ones
+            arrays.append(np.ones(dims[q], dtype=complex))
+            inds_list.append([q])
     tensors = {k: (np.asarray(arr), list(ix)) for k, (arr, ix) in
                enumerate(zip(arrays, inds_list))}
-    out_unique = list(dict.fromkeys(output_inds))
     if not tensors:
         result, rinds = np.array(1.0 + 0j), []
     else:
@@ -163,7 +169,6 @@ def contract_arrays(arrays: List[np.ndarray], inds_list: List[List[int]],
             result = result.sum(axis=tuple(rinds.index(i) for i in extra))
             rinds = [i for i in rinds if i not in extra]
     result = np.asarray(result, dtype=complex)
-    # open indices that no tensor carries cannot occur (builder adds ONES)
     result = result.transpose([rinds.index(i) for i in out_unique]) \
         if rinds else result
     result = result * scalar
@@ -187,3 +192,52 @@ def contract_network(net, order: str = "greedy", seed: int = 0,
         arrays = _leaves.build_all(net.leaves)
     return contract_arrays(arrays, [list(l.inds) for l in net.leaves], net.dims,
                            net.output_inds, net.scalar, order, seed)
+
+
+def contract_along_path(arrays: List[np.ndarray], inds_list: List[List[int]],
+                        dims: Dict[int, int], output_inds: Sequence[int],
+                        ssa_path: Sequence[Tuple[int, int]], fixed: Dict[int, int] | None = None,
+                        scalar: complex = 1.0) -> np.ndarray:
+    """The same pairwise arithmetic along a GIVEN SSA pair order, with the indices in
+    ``fixed`` pinned to one value each (one SLICE of a sliced contraction, as cotengra's
+    ``contract_slice`` evaluates it; the caller sums the slices).  Used to time the CPU
+    path on a bounded sample of a sliced workload and to check sliced execution."""
+    fixed = fixed or {}
+    tensors = {}
+    for k, (arr, ix) in enumerate(zip(arrays, inds_list)):
+        arr, ix = np.asarray(arr), list(ix)
+        for q, v in fixed.items():
+            while q in ix:
+                p = ix.index(q)
+                arr = np.take(arr, v, axis=p)
+                ix.pop(p)
+        tensors[k] = (arr, ix)
+    out_unique = list(dict.fromkeys(output_inds))
+    count: Dict[int, int] = {}
+    for _, ix in tensors.values():
+        for q in set(ix):
+            count[q] = count.get(q, 0) + 1
+    nxt = len(tensors)
+    for i, j in ssa_path:
+        (a, ia), (b, ib) = tensors.pop(i), tensors.pop(j)
+        keep = {q for q in set(ia) | set(ib)
+                if q in out_unique or count[q] > (q in ia) + (q in ib)}
+        for q in set(ia):
+            count[q] -= 1
+        for q in set(ib):
+            count[q] -= 1
+        c, ic = pair_contract(a, ia, b, ib, keep)
+        for q in set(ic):
+            count[q] = count.get(q, 0) + 1
+        tensors[nxt] = (c, ic)
+        nxt += 1
+    (result, rinds), = tensors.values()
+    result, rinds = _take_diagonals(result, rinds)
+    extra = [i for i in rinds if i not in out_unique]
+    if extra:
+        result = result.sum(axis=tuple(rinds.index(i) for i in extra))
+        rinds = [i for i in rinds if i not in extra]
+    result = np.asarray(result, dtype=complex)
+    if rinds:
+        result = result.transpose([rinds.index(i) for i in out_unique])
+    return result * scalar

@@ -238,3 +238,77 @@ def test_leaf_rank_is_unbounded_for_host_valued_leaves():
     bad = nw.Network([nw.Leaf(nw.K_SUM, (2,) * 10, tuple(range(10)))], {i: 2 for i in range(10)}, ())
     with pytest.raises(ValueError):
         bad.validate()
+
+
+# ---- optimiser / contraction-tree intake (backends.py:436-455, 513-545) ---------------------
+class _FakeTree:
+    def __init__(self, ssa, sliced=()):
+        self._ssa, self.sliced_inds = ssa, tuple(sliced)
+
+    def get_ssa_path(self):
+        return self._ssa
+
+
+class HyperOptimizer:                         # recognised by NAME, like cotengra's class
+    """Stand-in for cotengra.HyperOptimizer: ``search`` returns a tree with a hand-written
+    SSA path (contract the leaves left to right) and one sliced index."""
+
+    def __init__(self, slice_first_closed=False):
+        self.slice_first_closed, self.calls = slice_first_closed, []
+
+    def search(self, inputs, output, size_dict):
+        self.calls.append((inputs, output, size_dict))
+        n = len(inputs)
+        ssa = [(0, 1)] + [(n + k - 1, k + 1) for k in range(1, n - 1)]
+        sliced = ()
+        if self.slice_first_closed:
+            closed = [q for ix in inputs for q in ix if q not in output]
+            sliced = (closed[0],) if closed else ()
+        return _FakeTree(ssa, sliced)
+
+
+def test_plan_from_hand_written_ssa_path():
+    """A given contraction tree (cotengra's tree.get_ssa_path() + sliced_inds) becomes an
+    executable plan: checked on the numpy descriptor emulator against the oracle."""
+    from optyx_b200 import planner
+    rng = np.random.default_rng(5)
+    for _ in range(10):
+        net = random_network(rng, n_leaves=6, n_inds=8)
+        n = len(net.leaves)
+        ssa = [(0, 1)] + [(n + k - 1, k + 1) for k in range(1, n - 1)]
+        closed = [q for q in net.dims if q not in net.output_inds]
+        plan = planner.plan_from_ssa_path(net, ssa, closed[:1])
+        assert [tuple(sorted(p)) for p in plan.info.path] == [tuple(sorted(p)) for p in ssa]
+        assert plan.nslices == (net.dims[closed[0]] if closed else 1)
+        assert np.allclose(emulate_plan(net, plan)[0], contract_network(net))
+    with pytest.raises(ValueError):
+        planner.plan_from_ssa_path(net, [(0, 0)])
+    with pytest.raises(ValueError):
+        planner.plan_from_ssa_path(net, ssa, [net.output_inds[0]])
+
+
+def test_backend_takes_the_tree_the_optimiser_finds():
+    from optyx_b200 import executor
+    from optyx_b200.core.backends import B200Backend
+    from optyx_b200.planner import GivenTree
+    rng = np.random.default_rng(6)
+    net = random_network(rng, n_leaves=6, n_inds=8)
+    opt = HyperOptimizer(slice_first_closed=True)
+    backend = B200Backend(hyperoptimiser=opt, contraction_params={"x": 1})
+    assert backend.hyperoptimiser is opt and backend.contraction_params == {"x": 1}
+    assert backend._optimiser_kind() == "exact"
+    ssa, sliced = backend._tree_for(net, "exact")
+    inputs, output, size_dict = opt.calls[0]
+    assert len(inputs) == len(net.leaves) and all(isinstance(q, str) for ix in inputs for q in ix)
+    assert set(size_dict.values()) <= {2, 3, 4}
+    assert all(q in net.dims and q not in net.output_inds for q in sliced)
+    plan = executor.get_plan(net, ssa_path=ssa, sliced_inds=sliced)
+    assert np.allclose(emulate_plan(net, plan)[0], contract_network(net))
+    # an explicit tree is accepted as well; anything else is the reference's ValueError
+    assert B200Backend(hyperoptimiser=GivenTree(ssa, sliced))._optimiser_kind() == "tree"
+    with pytest.raises(ValueError, match="Unsupported hyperoptimiser type"):
+        B200Backend(hyperoptimiser="greedy")._optimiser_kind()
+
+    class ReusableHyperCompressedOptimizer:
+        pass
+    assert B200Backend(hyperoptimiser=ReusableHyperCompressedOptimizer())._optimiser_kind() == "approx"
