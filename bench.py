@@ -340,8 +340,11 @@ class Bench:
 
         if plan.sliced:
             def step_fn():
-                b2dist.run_sliced(sess, net, upload=False) if world > 1 else \\
-                    (sess.build_leaves(), sess.contract(scalar))
+                if world > 1:
+                    b2dist.run_sliced(sess, net, upload=False)
+                else:
+                    sess.build_leaves()
+                    sess.contract(scalar)
             use_graph = False
         else:
             use_graph = len(plan.steps) > 8

@@ -130,46 +130,65 @@ int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev,
                      double alpha_im, int32_t accumulate, int32_t dtype,
                      void* stream);
 
-/* (2c) launch-bound small networks (hundreds of leaves of <= 343 elements): whole
- * SUBTREES of tiny pairwise contractions in ONE launch, intermediates in SHARED
- * MEMORY.  One CTA per group (an independent subtree): it first copies the
- * group's leaf operands (`preload_dev[pre_start[g] .. pre_start[g+1])`) from the
- * arena into its shared-memory scratch, then runs the group's steps
- * (`steps_dev[group_start[g] .. group_start[g+1])`) back to back with a block
- * barrier between them.  An operand / result with `*_smem != 0` lives in the
- * scratch at byte offset `*_off`, otherwise at the absolute device address
- * `*_ptr` (+ `*_off` bytes).  Same contraction form as b2_modes, at most
- * B2_SMALL_MODES modes, alpha = 1, no accumulation.                          */
-#define B2_SMALL_MODES 16
+/* (2c) launch-bound small networks (hundreds of leaves of <= 343 elements; the
+ * reference pays one numpy call per tree node, backends.py:539-545): EVERY early tiny
+ * pairwise contraction of an eval -- or of a whole batch of evals -- in ONE persistent
+ * launch, intermediates in SHARED MEMORY, no launch per step.
+ *
+ * The plan's tiny steps are cut into TASKS (chains of steps one CTA executes back to
+ * back: leaves and hand-overs are imported from global memory into the CTA's scratch,
+ * every step reads and writes the scratch, a block barrier between steps, results that
+ * leave the task are exported to global memory).  Work items are (eval, task) pairs in
+ * topological order; persistent CTAs take them from a ticket counter, wait on the
+ * done-flags of the tasks they depend on (a dependency always holds a smaller ticket,
+ * so whoever holds it is already running: no deadlock, no co-residency requirement),
+ * and publish their own flag with release semantics.  Flags carry the launch EPOCH, so
+ * a CUDA-graph replay needs no reset: the last CTA to finish bumps the epoch and
+ * rewinds the ticket counter.
+ *
+ * A step is   C[oc(o)] = sum_r A[oa(o) + ra(r)] * B[ob(o) + rb(r)]   with the operand
+ * offsets of every output index o and every reduction index r TABULATED at plan time
+ * (element offsets inside the scratch, < 2^16): no index arithmetic on the device.    */
+typedef struct {
+    int32_t n_out, n_red;            /* output / reduction index values                 */
+    int32_t a_off, b_off, c_off;     /* scratch element offsets of A, B, C              */
+    int32_t rsplit;                  /* lanes sharing one output's reduction (2^k <= 32) */
+    int32_t out_tab, red_tab;        /* first row of this step in the two tables        */
+} b2_sp_step;
+
+typedef struct {                     /* import (global -> scratch) or export            */
+    int32_t space;                   /* 0 leaf arena, 1 workspace, 2 output             */
+    int32_t smem_off;                /* scratch element offset                          */
+    int64_t glob_off;                /* element offset inside that space                */
+    int64_t eval_stride;             /* + eval * eval_stride (batched plans)            */
+    int32_t n;                       /* elements                                        */
+    int32_t reserved;
+} b2_sp_copy;
 
 typedef struct {
-    int32_t n_out;
-    int32_t n_red;
-    int32_t n_out_elems;
-    int32_t n_red_elems;
-    int32_t dim[B2_SMALL_MODES];
-    uint32_t magic[B2_SMALL_MODES];     /* ceil(2^32 / dim): exact division of indices < 2^16 */
-    int64_t sa[B2_SMALL_MODES];
-    int64_t sb[B2_SMALL_MODES];
-    int64_t sc[B2_SMALL_MODES];
-    const void* a_ptr;
-    const void* b_ptr;
-    void* c_ptr;
-    int32_t a_off, b_off, c_off;        /* bytes */
-    int32_t a_smem, b_smem, c_smem;     /* 1 = in the CTA's shared-memory scratch */
-} b2_small_step;
+    int32_t step_begin, step_end;
+    int32_t imp_begin, imp_end;      /* rows of the copy table                          */
+    int32_t exp_begin, exp_end;
+    int32_t dep_begin, dep_end;      /* rows of the dependency list (task ids)          */
+} b2_sp_task;
 
 typedef struct {
-    const void* src;                    /* device address of a leaf (contiguous) */
-    int32_t dst_off;                    /* byte offset in the scratch           */
-    int32_t nbytes;
-} b2_small_preload;
+    const b2_sp_task* tasks_dev;
+    const b2_sp_step* steps_dev;
+    const b2_sp_copy* copies_dev;
+    const int32_t* deps_dev;
+    const uint32_t* out_tab_dev;     /* 2 words per row: oa | ob << 16, oc              */
+    const uint32_t* red_tab_dev;     /* ra | rb << 16                                   */
+    void* base_dev[3];               /* leaf arena, workspace, output                   */
+    int32_t* sync_dev;               /* [0] ticket [1] finished CTAs [2] epoch, then
+                                        batch * n_tasks done-flags; zero-filled ONCE    */
+    int32_t n_tasks;
+    int32_t batch;
+    int32_t scratch_elems;           /* complex elements of shared memory per CTA       */
+    int32_t reserved;
+} b2_small_program;
 
-int b2_contract_small_groups(const b2_small_step* steps_dev,
-                             const int32_t* group_start_dev,
-                             const b2_small_preload* preload_dev,
-                             const int32_t* pre_start_dev, int32_t n_groups,
-                             int32_t scratch_bytes, int32_t dtype, void* stream);
+int b2_run_small_program(const b2_small_program* prog, int32_t dtype, void* stream);
 
 /* (3) slice / Sum-term accumulation: y += alpha * x over n complex elements  */
 int b2_axpy(int64_t n, double alpha_re, double alpha_im, const void* x_dev,

@@ -93,70 +93,41 @@ class Session:
         self.params_stride = 0
         self.graph = None
         self.launches = 0
-        self._init_small_groups()
+        self._init_small_program()
 
-    # ---- small-subtree launch -------------------------------------------------
-    def _init_small_groups(self) -> None:
-        """Device tables of the single small-subtree launch (``plan.small_groups``):
-        compact mode descriptors, leaf preload lists, scratch offsets."""
+    # ---- small-step program ----------------------------------------------------
+    def _init_small_program(self) -> None:
+        """Device tables of the persistent small-step launch (``plan.small``)."""
         plan, torch = self.plan, self.torch
-        groups = plan.small_groups
-        self.small_n = len(groups)
-        if not self.small_n:
+        sp = plan.small
+        self.small_args = None
+        if sp is None:
             return
-        zeros = [0] * len(plan.sliced)
-        n_steps = sum(len(g.steps) for g in groups)
-        n_pre = sum(len(g.preload) for g in groups)
-        table = (rt.SmallStep * n_steps)()
-        pre = (rt.SmallPreload * max(1, n_pre))()
-        starts, pstarts, i, j = [0], [0], 0, 0
-        for g in groups:
-            for k in g.steps:
-                st, row = plan.steps[k], table[i]
-                d = st.desc
-                n = d.n_out + d.n_red
-                row.n_out, row.n_red = d.n_out, d.n_red
-                n_out = n_red = 1
-                for m in range(n):
-                    row.dim[m], row.sa[m], row.sb[m], row.sc[m] = d.dim[m], d.sa[m], d.sb[m], d.sc[m]
-                    assert d.dim[m] >= 2, "unit modes are merged away by the planner"
-                    row.magic[m] = ((1 << 32) + d.dim[m] - 1) // d.dim[m]
-                    if m < d.n_out:
-                        n_out *= d.dim[m]
-                    else:
-                        n_red *= d.dim[m]
-                row.n_out_elems, row.n_red_elems = n_out, n_red
-                a_off, b_off, c_off = g.place[k]
-                for name, lay, off in (("a", st.a, a_off), ("b", st.b, b_off), ("c", st.c, c_off)):
-                    if off is None:
-                        setattr(row, name + "_ptr", self._ptr(lay, zeros, ()))
-                        setattr(row, name + "_off", 0)
-                        setattr(row, name + "_smem", 0)
-                    else:
-                        setattr(row, name + "_ptr", None)
-                        setattr(row, name + "_off", off)
-                        setattr(row, name + "_smem", 1)
-                i += 1
-            for lay, off in g.preload:
-                pre[j].src = self._ptr(lay, zeros, ())
-                pre[j].dst_off, pre[j].nbytes = off, lay.size * self.esize
-                j += 1
-            starts.append(i)
-            pstarts.append(j)
-        self.small_scratch = max(g.scratch_bytes for g in groups)
-        self.small_steps_dev = torch.from_numpy(
-            np.frombuffer(bytes(table), dtype=np.uint8).copy()).to(self.device)
-        self.small_pre_dev = torch.from_numpy(
-            np.frombuffer(bytes(pre), dtype=np.uint8).copy()).to(self.device)
-        self.small_start_dev = torch.tensor(starts, dtype=torch.int32, device=self.device)
-        self.small_pstart_dev = torch.tensor(pstarts, dtype=torch.int32, device=self.device)
+
+        def up(arr):
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            if raw.size == 0:
+                raw = np.zeros(16, dtype=np.uint8)
+            return torch.from_numpy(raw.copy()).to(self.device)
+        self._sp_bufs = [up(sp.tasks), up(sp.steps), up(sp.copies), up(sp.deps),
+                         up(sp.out_tab), up(sp.red_tab)]
+        # [ticket, finished CTAs, epoch, pad] + one done-flag per (eval, task); zeroed once
+        self._sp_sync = torch.zeros(4 + plan.batch * len(sp.tasks), dtype=torch.int32,
+                                    device=self.device)
+        args = rt.SmallProgramArgs()
+        (args.tasks_dev, args.steps_dev, args.copies_dev, args.deps_dev, args.out_tab_dev,
+         args.red_tab_dev) = [b.data_ptr() for b in self._sp_bufs]
+        args.base_dev[ARENA] = self.arena.data_ptr()
+        args.base_dev[WS] = self.ws.data_ptr()
+        args.base_dev[OUT] = self.out.data_ptr()
+        args.sync_dev = self._sp_sync.data_ptr()
+        args.n_tasks, args.batch, args.scratch_elems = len(sp.tasks), plan.batch, sp.scratch_elems
+        self.small_args = args
 
     def _launch_small_groups(self, stream) -> None:
-        if self.small_n:
-            rt.check(self.lib.b2_contract_small_groups(
-                self.small_steps_dev.data_ptr(), self.small_start_dev.data_ptr(),
-                self.small_pre_dev.data_ptr(), self.small_pstart_dev.data_ptr(), self.small_n,
-                self.small_scratch, self.code, stream), "b2_contract_small_groups")
+        if self.small_args is not None:
+            rt.check(self.lib.b2_run_small_program(C.byref(self.small_args), self.code, stream),
+                     "b2_run_small_program")
             self.launches += 1
 
     # ---- leaves -------------------------------------------------------------

@@ -312,7 +312,8 @@ class Step:
     macs: float                  # complex MACs (incl. eval batch)
     bytes: float                 # algorithmic bytes: s * (|A| + |B| + |C|)
     mnk: Tuple[int, int, int, int]   # (batch, M, N, K) extents
-    grouped: bool = False        # runs inside the small-subtree launch (plan.small_groups)
+    grouped: bool = False        # runs inside the small-step program (plan.small)
+    small_modes: Optional[tuple] = None   # per-eval (out modes, red modes) [dim, sa, sb, sc]
 
 
 @dataclass
@@ -334,7 +335,7 @@ class Plan:
     total_macs: float = 0.0
     total_bytes: float = 0.0
     parallel_safe: bool = False   # no workspace recycling: branches may overlap
-    small_groups: list = field(default_factory=list)      # SmallGroup per tiny subtree
+    small: Optional[object] = None        # SmallProgram: every early tiny step, ONE launch
 
 
 class _Allocator:
@@ -568,12 +569,16 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
             for k, m in enumerate(allm):
                 desc.dim[k], desc.sa[k], desc.sb[k], desc.sc[k] = m
 
+        small_modes = None
+        if not final and max(la.size, lb.size, lc.size) <= SMALL_ELEMS:
+            small_modes = ([mode(q) for q in sorted(c_inds, key=lambda q: -lc.stride_of(q))],
+                           [mode(q) for q in red])
         a_slice = [(sliced.index(q), la.stride_of(q)) for q in la.inds if q in sl]
         b_slice = [(sliced.index(q), lb.stride_of(q)) for q in lb.inds if q in sl]
         per_slice = bool(da or db)
         steps.append(Step("gemm" if use_gemm else "direct", desc, la, lb, lc,
                           a_slice, b_slice, per_slice, final, macs, nbytes,
-                          (Bx, Mx, Nx, Kx)))
+                          (Bx, Mx, Nx, Kx), small_modes=small_modes))
         mult = info.nslices if per_slice else 1
         total_macs += macs * mult
         total_bytes += nbytes * mult
@@ -604,44 +609,68 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
             parallel_safe = True
     ws_elems = max([st.c.offset + st.c.size * batch for st in steps if st.c.space == WS] or [0])
 
-    small_groups = _group_small_steps(steps, esize, batch)
-    for group in small_groups:          # private, never recycled outputs (they run first)
-        for k in group.steps:
-            st = steps[k]
-            st.grouped = True
-            st.c.offset = int(ws_elems)
-            ws_elems += st.c.size * batch
+    # the small-step program runs before every other launch: what it hands over
+    # (task exports) lives in private, never recycled workspace
+    small, ws_elems = _build_small_program(steps, batch, arena_elems, int(ws_elems))
+    if small is not None:
+        for k in small.step_ids:
+            steps[k].grouped = True
 
     plan = Plan(steps, sliced, tuple(dims[q] for q in sliced), info.nslices, leaf_offsets,
                 arena_elems, unit_offset, int(ws_elems), out_shape, out_elems,
                 needs_zero or bool(sliced), batch, dtype, info, total_macs, total_bytes)
     plan.parallel_safe = parallel_safe
-    plan.small_groups = small_groups
+    plan.small = small
     return plan
 
 
-SMALL_MODES, SMALL_OUT, SMALL_WORK = 16, 4096, 1 << 16
-SMALL_SCRATCH = 144 * 1024          # shared-memory scratch of one subtree CTA (bytes)
-SMALL_MAX_STEPS = 32                # longest subtree that runs inside one CTA
+# --------------------------------------------------------------------------
+# the small-step program (csrc/contract_small.cu)
+# --------------------------------------------------------------------------
+SMALL_ELEMS = 4096                  # largest operand / result of a step the interpreter takes
+SMALL_WORK = 1 << 18                # ... and its multiply-adds
+SMALL_SCRATCH_ELEMS = 12288         # shared-memory scratch of one task (complex elements: 192 KB c128)
+SMALL_TASK_STEPS = 32               # single eval: steps per task (parallel subtrees run on
+                                    # different CTAs; a batch runs one task chain per eval)
+SMALL_MERGE_STEPS = 6               # a sibling subtree this short is absorbed, not exported
+SMALL_MIN_STEPS = 8                 # fewer small steps than this: not worth the launch
 
 
 @dataclass
-class SmallGroup:
-    """One leaf-rooted subtree of tiny steps, executed by one CTA with its leaves
-    and intermediates in shared memory (csrc/contract_small.cu)."""
-    steps: List[int]                                  # indices into plan.steps, in order
-    preload: List[Tuple[Layout, int]]                 # (leaf layout, scratch byte offset)
-    place: Dict[int, Tuple[Optional[int], Optional[int], Optional[int]]]
-    # step index -> scratch byte offsets of (a, b, c); None = global memory
-    scratch_bytes: int = 0
+class SmallProgram:
+    """Every early tiny step of a plan as ONE persistent launch: tasks (chains of
+    steps executed by one CTA out of shared memory), their global imports / exports,
+    the dependency lists between tasks, and per-step offset tables."""
+    tasks: np.ndarray               # runtime.SP_TASK_DTYPE
+    steps: np.ndarray               # runtime.SP_STEP_DTYPE
+    copies: np.ndarray              # runtime.SP_COPY_DTYPE (imports and exports)
+    deps: np.ndarray                # int32 task ids
+    out_tab: np.ndarray             # uint32 [n, 2]: (oa | ob << 16, oc)
+    red_tab: np.ndarray             # uint32: ra | rb << 16
+    scratch_elems: int
+    step_ids: List[int]             # indices into plan.steps, in execution order
+    task_of: Dict[int, int]         # plan step -> task
 
 
-def _group_small_steps(steps: List[Step], esize: int, batch: int) -> List[SmallGroup]:
-    """Leaf-rooted subtrees of tiny steps (each at most SMALL_OUT outputs and
-    SMALL_WORK multiply-adds, all operands leaves or tiny steps of the same
-    subtree).  Returns the subtrees with their shared-memory layout."""
-    if batch != 1:
-        return []
+def _mode_offsets(modes: List[List[int]]):
+    """(oa, ob, oc) of every index tuple of a mode list, C order (last fastest)."""
+    oa = np.zeros(1, dtype=np.int64)
+    ob, oc = oa.copy(), oa.copy()
+    for d, sa, sb, sc in modes:
+        idx = np.arange(d, dtype=np.int64)
+        oa = (oa[:, None] + idx[None, :] * sa).reshape(-1)
+        ob = (ob[:, None] + idx[None, :] * sb).reshape(-1)
+        oc = (oc[:, None] + idx[None, :] * sc).reshape(-1)
+    return oa, ob, oc
+
+
+def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
+                         ws_top: int) -> Tuple[Optional[SmallProgram], int]:
+    """Pick the EARLY tiny steps (operands are leaves or other early tiny steps), cut
+    them into tasks, lay every task out in shared memory and tabulate the operand
+    offsets of every output / reduction index (plan-time constants, shared by all
+    evals of a batch and by every replay)."""
+    from .runtime import SP_COPY_DTYPE, SP_STEP_DTYPE, SP_TASK_DTYPE
     producer = {id(st.c): k for k, st in enumerate(steps)}
     consumer: Dict[int, int] = {}
     for k, st in enumerate(steps):
@@ -650,84 +679,174 @@ def _group_small_steps(steps: List[Step], esize: int, batch: int) -> List[SmallG
             if p is not None:
                 consumer[p] = k
     early = [False] * len(steps)
-    parent = list(range(len(steps)))
-
-    def find(x):
-        while parent[x] != x:
-            parent[x] = parent[parent[x]]
-            x = parent[x]
-        return x
     for k, st in enumerate(steps):
-        if st.kernel != "direct" or st.final or st.per_slice or st.a_slice or st.b_slice:
+        if st.final or st.per_slice or st.a_slice or st.b_slice or st.small_modes is None:
             continue
-        d = st.desc
-        if d.n_out + d.n_red > SMALL_MODES:
+        if max(st.a.size, st.b.size, st.c.size) > SMALL_ELEMS:
             continue
-        n_out = n_red = 1
-        for m in range(d.n_out):
-            n_out *= d.dim[m]
-        for m in range(d.n_red):
-            n_red *= d.dim[d.n_out + m]
-        if n_out > SMALL_OUT or n_red >= (1 << 16) or n_out * n_red > SMALL_WORK:
+        outm, redm = st.small_modes
+        n_out = int(np.prod([m[0] for m in outm], dtype=np.int64)) if outm else 1
+        n_red = int(np.prod([m[0] for m in redm], dtype=np.int64)) if redm else 1
+        if n_out * n_red > SMALL_WORK or n_out > SMALL_ELEMS:
             continue
-        prods = [producer.get(id(lay)) for lay in (st.a, st.b)]
-        if any(p is not None and not early[p] for p in prods):
-            continue
-        if any(p is None and lay.space != ARENA for p, lay in zip(prods, (st.a, st.b))):
-            continue
-        early[k] = True
-        for p in prods:
-            if p is not None:
-                parent[find(p)] = find(k)
-    members: Dict[int, List[int]] = {}
-    for k in range(len(steps)):
-        if early[k]:
-            members.setdefault(find(k), []).append(k)
+        ok = True
+        for lay in (st.a, st.b):
+            p = producer.get(id(lay))
+            if (p is None and lay.space != ARENA) or (p is not None and not early[p]):
+                ok = False
+        early[k] = ok
+    ids = [k for k in range(len(steps)) if early[k]]
+    if len(ids) < SMALL_MIN_STEPS:
+        return None, ws_top
 
-    def align(x):
-        return (x + 15) & ~15
-    groups: List[SmallGroup] = []
-    for ks in members.values():
+    # ---- tasks: walk the steps in (topological) plan order; a step continues the task
+    # of its larger operand subtree; the other operand's task is absorbed when short,
+    # otherwise it stays a task of its own (runs in parallel, result handed over in
+    # global memory).  A batch gets one chain per eval as long as shared memory allows.
+    max_steps = SMALL_TASK_STEPS if batch == 1 else 1 << 30
+    merge_steps = SMALL_MERGE_STEPS if batch == 1 else 1 << 30
+    task_of: Dict[int, int] = {}
+    members: Dict[int, List[int]] = {}          # open or closed task id -> steps
+    footprint: Dict[int, int] = {}              # conservative scratch need (no reuse)
+
+    def leaf_need(st):
+        return sum(lay.size for lay in (st.a, st.b) if id(lay) not in producer)
+    nxt_task = 0
+    for k in ids:
+        st = steps[k]
+        ops = []
+        for lay in (st.a, st.b):
+            p = producer.get(id(lay))
+            if p is not None:
+                ops.append(task_of[p])
+        ops = sorted(set(ops), key=lambda t: -len(members[t]))
+        need = st.c.size + leaf_need(st)
+        home = None
+        if ops:
+            t0 = ops[0]
+            if len(members[t0]) < max_steps and footprint[t0] + need <= SMALL_SCRATCH_ELEMS:
+                home = t0
+        if home is None:
+            home = nxt_task
+            nxt_task += 1
+            members[home], footprint[home] = [], 0
+        for t in ops:
+            if t == home:
+                continue
+            if len(members[t]) <= merge_steps and len(members[home]) + len(members[t]) < max_steps \
+                    and footprint[home] + footprint[t] + need <= SMALL_SCRATCH_ELEMS:
+                for q in members[t]:
+                    task_of[q] = home
+                members[home] = sorted(members[home] + members.pop(t))
+                footprint[home] += footprint.pop(t)
+            else:
+                need += steps[[q for q in members[t] if consumer.get(q) == k][0]].c.size
+        members[home].append(k)
+        footprint[home] += need
+        task_of[k] = home
+    # renumber tasks in order of their LAST step: a task's dependencies then have
+    # smaller numbers (tickets are handed out in task order: no waiting on a later one)
+    order = sorted(members, key=lambda t: members[t][-1])
+    renum = {t: i for i, t in enumerate(order)}
+    task_of = {k: renum[t] for k, t in task_of.items()}
+    members = {renum[t]: ks for t, ks in members.items()}
+    n_tasks = len(members)
+    # what a task hands over (to another task or to a later launch) gets a private,
+    # never recycled workspace buffer: the program runs before every other launch
+    for k in ids:
+        st = steps[k]
+        c = consumer.get(k)
+        if (c is None or task_of.get(c) != task_of[k]) and st.c.space == WS:
+            st.c.offset = int(ws_top)
+            ws_top += st.c.size * batch
+
+    tasks = np.zeros(n_tasks, dtype=SP_TASK_DTYPE)
+    step_rows, copy_rows, dep_rows = [], [], []
+    out_rows: List[np.ndarray] = []
+    red_rows: List[np.ndarray] = []
+    out_cache: Dict[bytes, int] = {}
+    red_cache: Dict[bytes, int] = {}
+    n_out_tab = n_red_tab = 0
+    scratch = 0
+    step_ids: List[int] = []
+
+    def eval_stride(lay):
+        if batch == 1:
+            return 0
+        return arena_elems if lay.space == ARENA else lay.size
+    for t in range(n_tasks):
+        ks = members[t]
         inside = set(ks)
-        top = 0
-        leaf_off: Dict[int, int] = {}
-        preload: List[Tuple[Layout, int]] = []
-        for k in ks:                                  # leaves first, back to back
+        alloc = _Allocator()
+        where: Dict[int, int] = {}               # id(layout) -> scratch element offset
+        imports, exports, deps = [], [], []
+        for k in ks:                             # imports first: resident for the whole task
             for lay in (steps[k].a, steps[k].b):
-                if id(lay) not in producer and id(lay) not in leaf_off:
-                    leaf_off[id(lay)] = top
-                    preload.append((lay, top))
-                    top += align(lay.size * esize)
-        alloc = _Allocator()                          # intermediates, recycled (units of 16 B)
-        inter_off: Dict[int, int] = {}
-        place = {}
+                if id(lay) in where:
+                    continue
+                p = producer.get(id(lay))
+                if p is None or p not in inside:
+                    where[id(lay)] = alloc.alloc(lay.size)
+                    imports.append((lay.space, where[id(lay)], lay.offset, eval_stride(lay), lay.size))
+                    if p is not None:
+                        deps.append(task_of[p])
+        tasks[t]["step_begin"] = len(step_rows)
         for k in ks:
             st = steps[k]
-            offs = []
-            for lay in (st.a, st.b):
+            outm, redm = st.small_modes
+            c_off = alloc.alloc(st.c.size)
+            where[id(st.c)] = c_off
+            oa, ob, oc = _mode_offsets(outm)
+            ra, rb, _ = _mode_offsets(redm)
+            assert max(oa.max() + ra.max(), 0) < st.a.size and max(ob.max() + rb.max(), 0) < st.b.size
+            otab = np.stack([(oa | (ob << 16)), oc], axis=1).astype(np.uint32)
+            rtab = (ra | (rb << 16)).astype(np.uint32)
+            key = otab.tobytes()
+            o_at = out_cache.get(key)
+            if o_at is None:
+                o_at = out_cache[key] = n_out_tab
+                out_rows.append(otab)
+                n_out_tab += len(otab)
+            key = rtab.tobytes()
+            r_at = red_cache.get(key)
+            if r_at is None:
+                r_at = red_cache[key] = n_red_tab
+                red_rows.append(rtab)
+                n_red_tab += len(rtab)
+            n_out, n_red = len(otab), len(rtab)
+            rsplit = 1                            # lanes sharing one output's reduction
+            while rsplit < 32 and n_out * rsplit * 2 <= 256 and n_red >= 4 * rsplit:
+                rsplit *= 2
+            step_rows.append((n_out, n_red, where[id(st.a)], where[id(st.b)], c_off, rsplit, o_at, r_at))
+            step_ids.append(k)
+            if consumer.get(k) not in inside:     # leaves the task: a root or a hand-over
+                exports.append((st.c.space, c_off, st.c.offset, eval_stride(st.c), st.c.size))
+            for lay in (st.a, st.b):              # single consumer: operands die here
                 p = producer.get(id(lay))
-                offs.append(leaf_off[id(lay)] if p is None else inter_off[p])
-            if consumer.get(k) in inside:
-                units = align(st.c.size * esize) // 16
-                inter_off[k] = top + 16 * alloc.alloc(units)     # provisional: leaves end at `top`
-                c_off = inter_off[k]
-            else:
-                c_off = None                          # root of the subtree -> global memory
-            for lay in (st.a, st.b):                  # operands die here (single consumer)
-                p = producer.get(id(lay))
-                if p is not None:
-                    alloc.release((inter_off[p] - top) // 16, align(steps[p].c.size * esize) // 16)
-            place[k] = (offs[0], offs[1], c_off)
-        scratch = top + 16 * alloc.top
-        # measured (tools/small_nets.py): a CTA walks its steps at ~1.5 us per step,
-        # about what a dependent kernel node of a CUDA graph costs, so the launch pays
-        # for many short PARALLEL subtrees (cfg1: 21 subtrees, -9 %; HOM: -15 %), not
-        # for one long chain (cfg2: 170-step subtrees, +40 %): long subtrees keep
-        # their own launches
-        if scratch <= SMALL_SCRATCH and len(ks) <= SMALL_MAX_STEPS:
-            groups.append(SmallGroup(list(ks), preload, place, scratch))
-    # the extra launch only pays when it replaces a fair number of tiny launches
-    return groups if sum(len(g.steps) for g in groups) >= 8 else []
+                if p is not None and p in inside:
+                    alloc.release(where[id(lay)], lay.size)
+        tasks[t]["step_end"] = len(step_rows)
+        tasks[t]["imp_begin"] = len(copy_rows)
+        copy_rows.extend(imports)
+        tasks[t]["imp_end"] = tasks[t]["exp_begin"] = len(copy_rows)
+        copy_rows.extend(exports)
+        tasks[t]["exp_end"] = len(copy_rows)
+        tasks[t]["dep_begin"] = len(dep_rows)
+        dep_rows.extend(sorted(set(deps)))
+        tasks[t]["dep_end"] = len(dep_rows)
+        assert all(d < t for d in deps), "task order is not topological"
+        scratch = max(scratch, alloc.top)
+    assert scratch <= 14080, "small-step task exceeds the shared-memory scratch"
+    srows = np.array(step_rows, dtype=np.int32).reshape(-1, 8)
+    st_arr = np.zeros(len(step_rows), dtype=SP_STEP_DTYPE)
+    for j, name in enumerate(("n_out", "n_red", "a_off", "b_off", "c_off", "rsplit", "out_tab", "red_tab")):
+        st_arr[name] = srows[:, j]
+    cp_arr = np.zeros(len(copy_rows), dtype=SP_COPY_DTYPE)
+    for j, row in enumerate(copy_rows):
+        cp_arr[j] = tuple(row) + (0,)
+    return SmallProgram(tasks, st_arr, cp_arr, np.array(dep_rows, dtype=np.int32).reshape(-1),
+                        np.concatenate(out_rows).reshape(-1, 2), np.concatenate(red_rows).reshape(-1),
+                        int(scratch), step_ids, task_of), ws_top
 
 
 def plan_bound_seconds(plan: Plan, hbm_gbs: float, pipe_tflops: float) -> float:

@@ -19,7 +19,7 @@ MAX_RED_DIRECT = 16
 
 EXPORTS = [
     "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
-    "b2_contract_direct", "b2_contract_gemm", "b2_contract_small_groups", "b2_axpy", "b2_fill_zero",
+    "b2_contract_direct", "b2_contract_gemm", "b2_run_small_program", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
     "b2_fp64_peak_kernel",
 ]
@@ -63,26 +63,25 @@ class GemmModes(C.Structure):
     ]
 
 
-SMALL_MODES = 16
+SP_STEP_DTYPE = np.dtype([(n, "<i4") for n in
+                          ("n_out", "n_red", "a_off", "b_off", "c_off", "rsplit", "out_tab", "red_tab")])
+SP_COPY_DTYPE = np.dtype([("space", "<i4"), ("smem_off", "<i4"), ("glob_off", "<i8"),
+                          ("eval_stride", "<i8"), ("n", "<i4"), ("reserved", "<i4")])
+SP_TASK_DTYPE = np.dtype([(n, "<i4") for n in
+                          ("step_begin", "step_end", "imp_begin", "imp_end", "exp_begin", "exp_end",
+                           "dep_begin", "dep_end")])
+assert SP_STEP_DTYPE.itemsize == 32 and SP_COPY_DTYPE.itemsize == 32 and SP_TASK_DTYPE.itemsize == 32
 
 
-class SmallStep(C.Structure):
+class SmallProgramArgs(C.Structure):
+    """b2_small_program (include/optyx_b200.h)."""
     _fields_ = [
-        ("n_out", C.c_int32), ("n_red", C.c_int32),
-        ("n_out_elems", C.c_int32), ("n_red_elems", C.c_int32),
-        ("dim", C.c_int32 * SMALL_MODES),
-        ("magic", C.c_uint32 * SMALL_MODES),
-        ("sa", C.c_int64 * SMALL_MODES),
-        ("sb", C.c_int64 * SMALL_MODES),
-        ("sc", C.c_int64 * SMALL_MODES),
-        ("a_ptr", C.c_void_p), ("b_ptr", C.c_void_p), ("c_ptr", C.c_void_p),
-        ("a_off", C.c_int32), ("b_off", C.c_int32), ("c_off", C.c_int32),
-        ("a_smem", C.c_int32), ("b_smem", C.c_int32), ("c_smem", C.c_int32),
+        ("tasks_dev", C.c_void_p), ("steps_dev", C.c_void_p), ("copies_dev", C.c_void_p),
+        ("deps_dev", C.c_void_p), ("out_tab_dev", C.c_void_p), ("red_tab_dev", C.c_void_p),
+        ("base_dev", C.c_void_p * 3), ("sync_dev", C.c_void_p),
+        ("n_tasks", C.c_int32), ("batch", C.c_int32), ("scratch_elems", C.c_int32),
+        ("reserved", C.c_int32),
     ]
-
-
-class SmallPreload(C.Structure):
-    _fields_ = [("src", C.c_void_p), ("dst_off", C.c_int32), ("nbytes", C.c_int32)]
 
 
 class B2Error(RuntimeError):
@@ -118,7 +117,7 @@ def load():
     lib.b2_build_leaves.argtypes = [vp, i32, i64, vp, i64, vp, i64, i32, i32, vp]
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_contract_gemm.argtypes = [C.POINTER(GemmModes), vp, vp, vp, dbl, dbl, i32, i32, vp]
-    lib.b2_contract_small_groups.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.b2_run_small_program.argtypes = [C.POINTER(SmallProgramArgs), i32, vp]
     lib.b2_axpy.argtypes = [i64, dbl, dbl, vp, vp, i32, vp]
     lib.b2_fill_zero.argtypes = [i64, vp, i32, vp]
     lib.b2_probs_amp.argtypes = [i64, vp, vp, vp, i32, vp]

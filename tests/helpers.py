@@ -109,6 +109,39 @@ def emulate_gemm(desc: rt.GemmModes, A, a_off, B, b_off, Cbuf, c_off, alpha, acc
             Cbuf[idx] = res
 
 
+def emulate_small_program(sp, bufs, batch: int) -> None:
+    """numpy model of csrc/contract_small.cu: (eval, task) items in ticket order, every
+    task on a private NaN-filled scratch -- imports, the tabulated steps, exports; a
+    dependency that has not run yet, or a read of something never written, fails."""
+    done = set()
+    ot_all, rt_all = sp.out_tab.astype(np.int64), sp.red_tab.astype(np.int64)
+    for ev in range(batch):
+        for t, task in enumerate(sp.tasks):
+            for d in sp.deps[task["dep_begin"]:task["dep_end"]]:
+                assert (ev, int(d)) in done and int(d) < t, "dependency runs later"
+            S = np.full(sp.scratch_elems, np.nan + 0j, dtype=complex)
+            for c in sp.copies[task["imp_begin"]:task["imp_end"]]:
+                src = int(c["glob_off"]) + ev * int(c["eval_stride"])
+                chunk = bufs[int(c["space"])][src:src + int(c["n"])]
+                assert not np.isnan(chunk).any(), "import of an unwritten buffer"
+                S[int(c["smem_off"]):int(c["smem_off"]) + int(c["n"])] = chunk
+            for st in sp.steps[task["step_begin"]:task["step_end"]]:
+                ot = ot_all[st["out_tab"]:st["out_tab"] + st["n_out"]]
+                rt = rt_all[st["red_tab"]:st["red_tab"] + st["n_red"]]
+                oa, ob, oc = ot[:, 0] & 0xffff, ot[:, 0] >> 16, ot[:, 1]
+                ra, rb = rt & 0xffff, rt >> 16
+                assert st["rsplit"] in (1, 2, 4, 8, 16, 32)
+                vals = (S[st["a_off"] + oa[:, None] + ra[None, :]]
+                        * S[st["b_off"] + ob[:, None] + rb[None, :]]).sum(axis=1)
+                assert not np.isnan(vals).any(), "step reads scratch nobody wrote"
+                S[st["c_off"] + oc] = vals
+            for c in sp.copies[task["exp_begin"]:task["exp_end"]]:
+                dst = int(c["glob_off"]) + ev * int(c["eval_stride"])
+                bufs[int(c["space"])][dst:dst + int(c["n"])] = \
+                    S[int(c["smem_off"]):int(c["smem_off"]) + int(c["n"])]
+            done.add((ev, t))
+
+
 def emulate_plan(net: Network, plan: Plan, nets=None, slice_range=None) -> np.ndarray:
     """Run a plan on numpy buffers with the emulated kernels."""
     nets = nets or [net]
@@ -135,8 +168,10 @@ def emulate_plan(net: Network, plan: Plan, nets=None, slice_range=None) -> np.nd
 
     scalar = nets[0].scalar
     zeros = [0] * len(plan.sliced)
+    if plan.small is not None:            # the persistent small-step launch runs first
+        emulate_small_program(plan.small, bufs, b)
     for st in plan.steps:
-        if not st.per_slice:
+        if not st.per_slice and not st.grouped:
             launch(st, zeros, scalar if st.final else 1.0, 0)
     if plan.sliced:
         s0, s1 = slice_range or (0, plan.nslices)

@@ -25,8 +25,8 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(rt.LeafDesc) == 72
     assert ctypes.sizeof(rt.Modes) == 8 + 64 * 4 + 3 * 64 * 8
     assert ctypes.sizeof(rt.GemmModes) == 16 + 64 * 4 + 3 * 64 * 8
-    assert ctypes.sizeof(rt.SmallStep) == 16 + 2 * 16 * 4 + 3 * 16 * 8 + 3 * 8 + 6 * 4
-    assert ctypes.sizeof(rt.SmallPreload) == 16
+    assert rt.SP_STEP_DTYPE.itemsize == rt.SP_COPY_DTYPE.itemsize == rt.SP_TASK_DTYPE.itemsize == 32
+    assert ctypes.sizeof(rt.SmallProgramArgs) == 6 * 8 + 3 * 8 + 8 + 4 * 4
 
 
 def test_no_cpu_fallback_without_device():

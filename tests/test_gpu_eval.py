@@ -219,33 +219,56 @@ def test_complex64_eval_uses_tensor_core_gemm_and_meets_tolerance():
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
-def test_small_subtree_launch_matches_oracle(dtype):
-    """cfg1-like networks: the short leaf-rooted subtrees run in ONE launch with
-    shared-memory intermediates (b2_contract_small_groups); same tensor as the
-    oracle, and the same as the plan executed one launch per step."""
-    from cases import cfg1_interferometer, compile_channel
+@pytest.mark.parametrize("name", ["cfg1_4mode", "ghz8_noisy_measured", "fusion_ii", "clifford_t_8x6"])
+def test_small_step_program_matches_oracle(name, dtype):
+    """Every early tiny step of the plan in ONE persistent launch (b2_run_small_program:
+    tasks on shared memory, ticket order, done-flags): same tensor as the oracle and as
+    the same plan executed one launch per step; replays (CUDA graph) need no reset."""
+    from cases import EVAL_CASES, compile_channel
     from optyx_b200 import executor, planner
-    d = cfg1_interferometer(4, (1, 1, 0, 0), depth=4)
+    d = EVAL_CASES[name]()
     net = compile_channel(d)
     plan = planner.plan_network(net, dtype=dtype)
-    assert plan.small_groups and all(len(g.steps) <= planner.SMALL_MAX_STEPS for g in plan.small_groups)
+    assert plan.small is not None and len(plan.small.step_ids) >= planner.SMALL_MIN_STEPS
     sess = executor.Session(plan)
     got = sess.run([net])[0].cpu().numpy()
-    assert sess.lib.b2_last_kernel().decode() != "" and sess.small_n == len(plan.small_groups)
     want = oracle_eval(d)
     tol = TOL128 if dtype == np.complex128 else 1e-5
     assert _close(got, want, tol)
     plain = planner.plan_network(net, dtype=dtype)
-    for g in plain.small_groups:
-        for k in g.steps:
-            plain.steps[k].grouped = False
-    plain.small_groups = []
+    for k in plain.small.step_ids:
+        plain.steps[k].grouped = False
+    plain.small = None
     ref = executor.Session(plain).run([net])[0].cpu().numpy()
     assert _close(got, ref, tol)
-    # and through the captured graph (tree branches after the subtree launch)
-    sess.capture(net.scalar)
-    sess.replay()
-    assert _close(sess.out[0].cpu().numpy(), want, tol)
+    for _ in range(3):                       # plain relaunches: epoch flags, rewound tickets
+        sess.out.zero_()
+        sess.build_leaves()
+        sess.contract(net.scalar)
+        assert _close(sess.out[0].cpu().numpy(), want, tol)
+    sess.capture(net.scalar)                 # and as a node of the captured graph
+    for _ in range(3):
+        sess.out.zero_()
+        sess.replay()
+        assert _close(sess.out[0].cpu().numpy(), want, tol)
+
+
+def test_small_step_program_batched():
+    """A batch: (eval, task) work items, per-eval strides on imports / exports."""
+    from cases import compile_channel, fusion_teleport_input
+    from optyx_b200 import executor
+    from optyx_b200.core import network as nw
+    nets = [compile_channel(fusion_teleport_input(0.01 * j)) for j in range(40)]
+    wants = [contract_network(n) for n in nets]
+    for net in nets:
+        net.leaves.append(nw.Leaf(nw.K_DENSE, (), (), 0, np.array([net.scalar], dtype=complex), "scalar"))
+        net.scalar = 1.0 + 0j
+    plan = executor.get_plan(nets[0], batch=len(nets))
+    assert plan.small is not None
+    sess = executor.Session(plan)
+    out = sess.run(nets, scalar=1.0 + 0j).cpu().numpy()
+    for e, want in enumerate(wants):
+        assert _close(out[e], want, TOL128), e
 
 
 def test_cfg2_full_size_closed_form_on_device():

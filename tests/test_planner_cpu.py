@@ -312,3 +312,58 @@ def test_backend_takes_the_tree_the_optimiser_finds():
     class ReusableHyperCompressedOptimizer:
         pass
     assert B200Backend(hyperoptimiser=ReusableHyperCompressedOptimizer())._optimiser_kind() == "approx"
+
+
+# ---- the small-step program (csrc/contract_small.cu), emulated ----------------------------
+@pytest.mark.parametrize("name", ["lossy_hom", "cfg1_4mode", "ghz8_noisy_measured", "ghz5_noisy_open3",
+                                  "cfg3_small", "clifford_t_8x6", "fusion_ii", "hom_distinguishable"])
+def test_small_step_program_on_the_emulator(name):
+    """Tasks, imports / exports, dependency order, scratch layout and offset tables of
+    the persistent small-step launch: the numpy model of the kernel (NaN-poisoned
+    scratch and workspace) reproduces the oracle's tensor."""
+    import cases
+    from optyx_b200 import planner
+    d = cases.EVAL_CASES[name]()
+    net = cases.compile_channel(d)
+    plan = planner.plan_network(net)
+    sp = plan.small
+    assert sp is not None and len(sp.step_ids) >= planner.SMALL_MIN_STEPS
+    assert sum(st.grouped for st in plan.steps) == len(sp.step_ids)
+    assert all(int(t["dep_end"]) >= int(t["dep_begin"]) for t in sp.tasks)
+    assert sp.scratch_elems * 16 <= 220 * 1024
+    got = emulate_plan(net, plan)[0]
+    want = contract_network(net)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_small_step_program_batched_and_sliced():
+    import cases
+    from optyx_b200 import planner
+    from optyx_b200.core import network as nw
+    # a batch: one chain of tasks per eval, per-eval strides on every import / export
+    nets = [cases.compile_channel(cases.fusion_teleport_input(0.1 * (j + 1))) for j in range(3)]
+    for net in nets:
+        net.leaves.append(nw.Leaf(nw.K_DENSE, (), (), 0, np.array([net.scalar], dtype=complex), "scalar"))
+        net.scalar = 1.0 + 0j
+    assert nets[0].structure_key() == nets[1].structure_key()
+    plan = planner.plan_network(nets[0], batch=3)
+    assert plan.small is not None
+    got = emulate_plan(nets[0], plan, nets=nets)
+    for e, net in enumerate(nets):
+        assert np.allclose(got[e], contract_network(net), rtol=1e-12, atol=1e-12)
+    # a sliced plan: only slice-invariant steps enter the program
+    net = cases.compile_channel(cases.random_clifford_t(12, 10, seed=3))
+    plan = planner.plan_network(net, target_size=16.0)
+    assert plan.nslices > 1 and plan.small is not None
+    assert all(not plan.steps[k].per_slice for k in plan.small.step_ids)
+    assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)
+
+
+def test_small_step_tasks_run_in_parallel_for_one_eval_and_in_one_chain_per_batch_eval():
+    import cases
+    from optyx_b200 import planner
+    net = cases.compile_channel(cases.ghz(12, open_qubits=3, noise=0.9))
+    single = planner.plan_network(net).small
+    batched = planner.plan_network(net, batch=4).small
+    assert len(single.tasks) > len(batched.tasks) >= 1
+    assert max(int(t["step_end"] - t["step_begin"]) for t in single.tasks) <= planner.SMALL_TASK_STEPS

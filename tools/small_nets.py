@@ -19,10 +19,10 @@ for name, d in (("cfg2_k10", cases.ghz(20, open_qubits=10, noise=0.95)), ("cfg2_
         executor.BRANCH_STREAMS = n_streams
         plan = planner.plan_network(net)
         if not grouping:
-            for g in plan.small_groups:
-                for k in g.steps: plan.steps[k].grouped = False
-            plan.small_groups = []
+            for g in ([plan.small] if plan.small is not None else []):
+                for k in g.step_ids: plan.steps[k].grouped = False
+            plan.small = None
         sess = executor.Session(plan)
         sess.set_leaves([net]); sess.run([net])
         sess.capture(net.scalar)
-        print(name, "streams", n_streams, "grouping", grouping, "groups", len(plan.small_groups), "steps", len(plan.steps), "ms %.4f" % timed(sess.replay), flush=True)
+        print(name, "streams", n_streams, "grouping", grouping, "groups", (len(plan.small.tasks) if plan.small is not None else 0), "steps", len(plan.steps), "ms %.4f" % timed(sess.replay), flush=True)

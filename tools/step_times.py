@@ -19,10 +19,10 @@ if len(sys.argv) > 1 and sys.argv[1] in ("cfg3", "cfg1"):
     import numpy as np
     dtype = np.complex64 if os.environ.get("B2_DTYPE") == "c64" else np.complex128
     plan = executor.get_plan(net, dtype=dtype)
-    for g in plan.small_groups:                      # time every step on its own
-        for k in g.steps:
+    for g in ([plan.small] if plan.small is not None else []):                      # time every step on its own
+        for k in g.step_ids:
             plan.steps[k].grouped = False
-    plan.small_groups = []
+    plan.small = None
     for st in plan.steps:
         st.per_slice = True          # time every step
 else:
