@@ -190,6 +190,47 @@ typedef struct {
 
 int b2_run_small_program(const b2_small_program* prog, int32_t dtype, void* stream);
 
+/* (2d) a whole compiled plan in ONE call: the host-side loop of the reference
+ * (cotengra's contract_tree / gather_slices walking the tree node by node and slice by
+ * slice, reached from backends.py:539-545) as a C loop over a step table.  Order:
+ * optional zero-fill of the output, the small-step program, the slice-invariant steps,
+ * then for every slice id in [slice_begin, slice_end) the per-slice steps (operand base
+ * pointers offset by slice value x stride; the final step accumulates into the output).
+ * The table lives in HOST memory and holds no pointers: the three buffers are bound per
+ * call, so one table serves any number of buffer sets.                               */
+#define B2_STEP_DIRECT 0
+#define B2_STEP_GEMM 1
+#define B2_MAX_SLICED 16
+
+typedef struct {
+    int32_t kind;                       /* B2_STEP_DIRECT / B2_STEP_GEMM               */
+    int32_t per_slice;                  /* 1: runs once per slice id                   */
+    int32_t final;                      /* 1: scaled by alpha (and accumulated when sliced) */
+    int32_t a_space, b_space, c_space;  /* 0 leaf arena, 1 workspace, 2 output         */
+    int32_t n_a_slice, n_b_slice;
+    int64_t a_off, b_off, c_off;        /* element offsets inside the space            */
+    int64_t c_elems;                    /* extent of the result (all evals of a batch) */
+    int32_t a_slice_pos[B2_MAX_SLICED]; /* which sliced index ...                      */
+    int32_t b_slice_pos[B2_MAX_SLICED];
+    int64_t a_slice_stride[B2_MAX_SLICED]; /* ... times its element stride             */
+    int64_t b_slice_stride[B2_MAX_SLICED];
+    union { b2_modes direct; b2_gemm_modes gemm; } desc;
+} b2_plan_step;
+
+/* what to run: bit 0 zero-fill the output, bit 1 small-step program + invariant steps,
+ * bit 2 per-slice steps                                                              */
+#define B2_RUN_ZERO 1
+#define B2_RUN_INVARIANT 2
+#define B2_RUN_SLICES 4
+
+int b2_run_plan(const b2_plan_step* steps, int32_t n_steps, const int32_t* sliced_dims,
+                int32_t n_sliced, const b2_small_program* small, void* arena_dev,
+                void* ws_dev, void* out_dev, int64_t out_elems, int32_t what,
+                int64_t slice_begin, int64_t slice_end, double alpha_re, double alpha_im,
+                int32_t dtype, void* stream, int32_t* launches_out);
+/* workspace the table needs, in bytes (max over workspace results of offset + extent) */
+int64_t b2_workspace_bytes(const b2_plan_step* steps, int32_t n_steps, int32_t dtype);
+
 /* (3) slice / Sum-term accumulation: y += alpha * x over n complex elements  */
 int b2_axpy(int64_t n, double alpha_re, double alpha_im, const void* x_dev,
             void* y_dev, int32_t dtype, void* stream);

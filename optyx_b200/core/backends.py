@@ -36,11 +36,32 @@ class StateType(Enum):
 
 class ResultTensor:
     """Stand-in for ``discopy.tensor.Box("Result", dom, cod, array)``
-    (backends.py:485-491): ``array.shape == dom + cod``."""
+    (backends.py:485-491): ``array.shape == dom + cod``.  The host array may be LAZY:
+    given a ``loader`` instead of an array, the device -> host copy happens on the first
+    access of ``.array`` (``prob_dist`` / ``amplitudes`` of a device-resident result
+    never need it)."""
 
-    def __init__(self, dom, cod, array):
+    def __init__(self, dom, cod, array=None, loader=None):
         self.dom, self.cod = tuple(int(d) for d in dom), tuple(int(d) for d in cod)
-        self.array = np.asarray(array).reshape(self.dom + self.cod)
+        self._loader = loader
+        self._array = None if array is None else np.asarray(array).reshape(self.dom + self.cod)
+        if array is None and loader is None:
+            raise ValueError("ResultTensor needs an array or a loader")
+
+    @property
+    def shape(self):
+        return self.dom + self.cod
+
+    @property
+    def is_materialised(self) -> bool:
+        return self._array is not None
+
+    @property
+    def array(self) -> np.ndarray:
+        if self._array is None:
+            self._array = np.asarray(self._loader()).reshape(self.dom + self.cod)
+            self._loader = None
+        return self._array
 
     def dagger(self) -> "ResultTensor":
         n = len(self.dom)
@@ -160,7 +181,7 @@ class EvalResult:
             return {}
         # keys as tuples of Python ints (hash/compare equal to the reference's
         # tuples of numpy ints); .tolist() makes the dict build ~10x faster
-        return dict(zip(_index_tuples(flat, nz_h, self.tensor.array.shape), p_h[flat].tolist()))
+        return dict(zip(_index_tuples(flat, nz_h, self.tensor.shape), p_h[flat].tolist()))
 
     def _prob_dist_mixed(self) -> dict:
         """backends.py:306-356 with the diagonal partial trace on the device."""
@@ -172,7 +193,7 @@ class EvalResult:
         kinds = []
         for t in names:
             kinds.extend([1] if t in {"bit", "mode"} else [2, 3])
-        shape = self.tensor.array.shape
+        shape = self.tensor.shape
         assert len(kinds) == len(shape), "result axes do not match the output types"
         dev = self._resident()
         from .. import runtime as rt
@@ -294,7 +315,7 @@ class B200Backend(AbstractBackend):
     def __init__(self, hyperoptimiser=None, contraction_params: Optional[dict] = None,
                  dtype="complex128", target_size: Optional[int] = None, trials: int = 8,
                  seed: int = 0, distributed: bool = False, keep_on_device: bool = True,
-                 sparse_d2h: bool = True):
+                 sparse_d2h: bool = True, lazy_host: bool = True, cache_networks: bool = True):
         # backends.py:436-455: stored as given, checked when a term is contracted (526-534)
         self.hyperoptimiser = hyperoptimiser
         self.contraction_params = contraction_params or {}
@@ -306,7 +327,29 @@ class B200Backend(AbstractBackend):
         self.distributed = distributed
         self.keep_on_device = keep_on_device
         self.sparse_d2h = sparse_d2h
+        # the host array of a result is copied on first access of ``.tensor.array``
+        self.lazy_host = lazy_host and keep_on_device
+        # compiled networks are cached by a fingerprint of the diagram (same boxes, same
+        # parameters, same wiring): a re-built but identical diagram skips the host compile
+        self.cache_networks = cache_networks
+        self._networks: dict = {}
+        self._sessions: dict = {}         # id(plan) -> Session (device buffers, tables, graphs)
         self.last_plan = None
+        self.last_h2d_bytes = 0
+
+    def _get_network(self, diagram: channel.Diagram, nested_eval=None) -> nw.Network:
+        if not self.cache_networks:
+            return super()._get_network(diagram, nested_eval=nested_eval)
+        from .fingerprint import fingerprint
+        key = fingerprint(diagram)
+        net = self._networks.get(key) if key is not None else None
+        if net is None:
+            net = super()._get_network(diagram, nested_eval=nested_eval)
+            if key is not None:
+                if len(self._networks) >= 64:
+                    self._networks.pop(next(iter(self._networks)))
+                self._networks[key] = net
+        return net
 
     def _nested_eval(self, net: nw.Network) -> np.ndarray:
         """Contract a sub-network on the device (``BitControlledBox`` slabs,
@@ -385,22 +428,27 @@ class B200Backend(AbstractBackend):
         for net in nets[1:]:
             if net.structure_key() != key0:
                 raise ValueError("eval_batch needs structurally identical diagrams")
-        # per-eval scalars travel as a rank-0 leaf so the kernels apply them
-        for net in nets:
-            net.leaves.append(nw.Leaf(nw.K_DENSE, (), (), 0,
-                                      np.array([net.scalar], dtype=np.complex128), "scalar"))
-            net.scalar = 1.0 + 0j
+        # per-eval scalars travel as a rank-0 leaf so the kernels apply them (on copies:
+        # the compiled networks may be shared with the network cache)
+        import dataclasses
+        nets = [dataclasses.replace(
+            net, scalar=1.0 + 0j,
+            leaves=list(net.leaves) + [nw.Leaf(nw.K_DENSE, (), (), 0,
+                                               np.array([net.scalar], dtype=np.complex128), "scalar")])
+            for net in nets]
         plan = executor.get_plan(nets[0], dtype=self.dtype, batch=len(nets),
                                  trials=self.trials, seed=self.seed)
         self.last_plan = plan
-        sess = executor.Session(plan)
+        sess = self._session(plan)
         if len(plan.steps) > 8 and not plan.sliced:
             sess.set_leaves(nets)
-            sess.capture(1.0 + 0j)
+            if sess.graph is None:
+                sess.capture(1.0 + 0j)
             sess.replay()
-            dev = sess.out
         else:
-            dev = sess.run(nets, scalar=1.0 + 0j)
+            sess.run(nets, scalar=1.0 + 0j)
+        self.last_h2d_bytes = sess.h2d_bytes
+        dev = sess.take_out()
         host = self._to_host(dev)
         n, shape = nets[0].n_dom, nets[0].output_shape
         results = []
@@ -465,14 +513,28 @@ class B200Backend(AbstractBackend):
             plan = executor.get_plan(net, dtype=self.dtype, target_size=self.target_size,
                                      trials=self.trials, seed=self.seed)
         self.last_plan = plan
-        sess = executor.Session(plan)
+        sess = self._session(plan)
         if self.distributed:
             from .. import dist
-            out = dist.run_sliced(sess, net)
+            dist.run_sliced(sess, net)
         else:
-            out = sess.run([net])[0]
+            sess.run([net])
         self.last_h2d_bytes = sess.h2d_bytes
-        return out
+        return sess.take_out()[0]
+
+    MAX_SESSIONS = 4
+
+    def _session(self, plan):
+        """Device buffers, step tables and captured graphs of a plan are kept across
+        evals (the output buffer is handed to each result, ``Session.take_out``)."""
+        from .. import executor
+        sess = self._sessions.pop(id(plan), None)
+        if sess is None:
+            sess = executor.Session(plan)
+            while len(self._sessions) >= self.MAX_SESSIONS:
+                self._sessions.pop(next(iter(self._sessions)))
+        self._sessions[id(plan)] = sess          # most recently used last
+        return sess
 
     # results of at least this many bytes are scanned for sparsity before the copy
     SPARSE_MIN_BYTES = 32 << 20
@@ -551,12 +613,14 @@ class B200Backend(AbstractBackend):
             return self._eval_sum(diagram)
         net = self._get_network(diagram, nested_eval=self._nested_eval)
         dev = self.eval_network(net)
-        array = self._to_host(dev)
         n = net.n_dom
         shape = net.output_shape
         state_type = StateType.AMP if diagram.is_pure else StateType.DM
-        return EvalResult(ResultTensor(shape[:n], shape[n:], array),
-                          output_types=diagram.cod, state_type=state_type,
+        if self.lazy_host:
+            tensor = ResultTensor(shape[:n], shape[n:], loader=lambda: self._to_host(dev))
+        else:
+            tensor = ResultTensor(shape[:n], shape[n:], self._to_host(dev))
+        return EvalResult(tensor, output_types=diagram.cod, state_type=state_type,
                           _device=dev if self.keep_on_device else None)
 
 

@@ -206,7 +206,14 @@ class Channel(_CBox):
         super().__init__(name, dom, cod)
 
     def double(self) -> diagram.Diagram:
-        """The CP construction, channel.py:600-641."""
+        """The CP construction, channel.py:600-641 (memoised per instance: boxes are
+        immutable values and a circuit re-uses the same gate objects many times)."""
+        hit = self.__dict__.get("_doubled")
+        if hit is None:
+            hit = self.__dict__["_doubled"] = self._double()
+        return hit
+
+    def _double(self) -> diagram.Diagram:
         D = diagram.Diagram
 
         def get_spiders(ty: Ty) -> diagram.Diagram:

@@ -94,6 +94,7 @@ class Session:
         self.graph = None
         self.launches = 0
         self._init_small_program()
+        self._init_step_table()
 
     # ---- small-step program ----------------------------------------------------
     def _init_small_program(self) -> None:
@@ -123,6 +124,48 @@ class Session:
         args.sync_dev = self._sp_sync.data_ptr()
         args.n_tasks, args.batch, args.scratch_elems = len(sp.tasks), plan.batch, sp.scratch_elems
         self.small_args = args
+
+    def _init_step_table(self) -> None:
+        """Host table ``b2_run_plan`` walks: every step that is not part of the
+        small-step program, in plan order; no pointers (buffers are bound per call)."""
+        plan = self.plan
+        if len(plan.sliced) > rt.MAX_SLICED:
+            raise ValueError(f"{len(plan.sliced)} sliced indices: the step table holds {rt.MAX_SLICED}")
+        rows = [st for st in plan.steps if not st.grouped]
+        table = (rt.PlanStep * max(1, len(rows)))()
+        for row, st in zip(table, rows):
+            row.kind = rt.STEP_GEMM if st.kernel == "gemm" else rt.STEP_DIRECT
+            row.per_slice, row.final = int(st.per_slice), int(st.final)
+            row.a_space, row.b_space, row.c_space = st.a.space, st.b.space, st.c.space
+            row.a_off, row.b_off, row.c_off = st.a.offset, st.b.offset, st.c.offset
+            row.c_elems = st.c.size * plan.batch
+            row.n_a_slice, row.n_b_slice = len(st.a_slice), len(st.b_slice)
+            for i, (pos, stride) in enumerate(st.a_slice):
+                row.a_slice_pos[i], row.a_slice_stride[i] = pos, stride
+            for i, (pos, stride) in enumerate(st.b_slice):
+                row.b_slice_pos[i], row.b_slice_stride[i] = pos, stride
+            if st.kernel == "gemm":
+                row.desc.gemm = st.desc
+            else:
+                row.desc.direct = st.desc
+        self.step_table, self.n_table = table, len(rows)
+        self.sliced_dims = (C.c_int32 * max(1, len(plan.sliced)))(*plan.sliced_dims)
+        self.n_invariant = sum(1 for st in rows if not st.per_slice)
+        self._launch_count = C.c_int32(0)
+
+    def run_plan(self, what: int, scalar: complex, slice_range=(0, 0), stream=None) -> None:
+        """ONE call into the C plan interpreter (``b2_run_plan``)."""
+        plan = self.plan
+        if stream is None:
+            stream = self.torch.cuda.current_stream().cuda_stream
+        scalar = complex(scalar)
+        small = C.byref(self.small_args) if self.small_args is not None else None
+        rt.check(self.lib.b2_run_plan(
+            self.step_table, self.n_table, self.sliced_dims, len(plan.sliced), small,
+            self.arena.data_ptr(), self.ws.data_ptr(), self.out.data_ptr(), self.out.numel(),
+            what, slice_range[0], slice_range[1], scalar.real, scalar.imag, self.code, stream,
+            C.byref(self._launch_count)), "b2_run_plan")
+        self.launches += self._launch_count.value
 
     def _launch_small_groups(self, stream) -> None:
         if self.small_args is not None:
@@ -194,49 +237,28 @@ class Session:
         """Run the plan: invariant steps once, per-slice steps for every slice id
         in ``slice_range`` (default all), accumulating into ``self.out``."""
         plan = self.plan
-        stream = self.torch.cuda.current_stream().cuda_stream
-        scalar = complex(scalar)
         s0, s1 = slice_range if slice_range is not None else (0, plan.nslices)
-        if plan.needs_zero_out and zero_out:
-            rt.check(self.lib.b2_fill_zero(self.out.numel(), self.out.data_ptr(), self.code,
-                                           stream), "b2_fill_zero")
-        zeros = [0] * len(plan.sliced)
-        n_inv = sum(1 for st in plan.steps if not st.per_slice)
-        if plan.sliced and n_inv > 32 and not self.torch.cuda.is_current_stream_capturing():
-            # the slice-invariant subtrees of a sliced circuit are thousands of tiny
-            # steps: one CUDA graph (captured on first use) instead of one launch each
+        zero = rt.RUN_ZERO if plan.needs_zero_out and zero_out else 0
+        slices = rt.RUN_SLICES if plan.sliced else 0
+        if plan.sliced and self.n_invariant > 32 and not self.torch.cuda.is_current_stream_capturing():
+            # many slice-invariant launches left outside the small-step program: one CUDA
+            # graph (captured on first use) instead of one launch each
             if getattr(self, "inv_graph", None) is None:
                 self._capture_invariant()
+            if zero:
+                self.run_plan(rt.RUN_ZERO, scalar)
             self.inv_graph.replay()
+            self.run_plan(slices, scalar, (s0, s1))
         else:
-            self._launch_small_groups(stream)
-            for st in plan.steps:
-                if not st.per_slice and not st.grouped:
-                    self._launch(st, zeros, scalar if st.final else 1.0 + 0j, 0, stream)
-        if not plan.sliced:
-            return
-        for sid in range(s0, s1):
-            vals, rem = [0] * len(plan.sliced), sid
-            for k in range(len(plan.sliced) - 1, -1, -1):
-                vals[k] = rem % plan.sliced_dims[k]
-                rem //= plan.sliced_dims[k]
-            for st in plan.steps:
-                if st.per_slice:
-                    self._launch(st, vals, scalar if st.final else 1.0 + 0j,
-                                 1 if st.final else 0, stream)
+            self.run_plan(zero | rt.RUN_INVARIANT | slices, scalar, (s0, s1))
 
     def _capture_invariant(self) -> None:
         """CUDA graph of the slice-invariant steps (none of them is final: alpha = 1;
         their buffers are private, ``planner._reallocate_for_slices``)."""
-        torch, plan = self.torch, self.plan
-        zeros = [0] * len(plan.sliced)
+        torch = self.torch
 
         def body():
-            stream = torch.cuda.current_stream().cuda_stream
-            self._launch_small_groups(stream)
-            for st in plan.steps:
-                if not st.per_slice and not st.grouped:
-                    self._launch(st, zeros, 1.0 + 0j, 0, stream)
+            self.run_plan(rt.RUN_INVARIANT, 1.0 + 0j)
         launches = self.launches
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -249,6 +271,18 @@ class Session:
             body()
         self.launches = launches
         self.inv_graph = graph
+
+    def take_out(self):
+        """Hand the output buffer to the caller (a result object that may read it much
+        later): the session gets a fresh one before its next run.  With a captured graph
+        the buffer address is frozen into the graph, so the caller gets a copy."""
+        out = self.out
+        if self.graph is not None:
+            return out.clone()
+        self.out = self.torch.empty_like(out)
+        if self.small_args is not None:
+            self.small_args.base_dev[OUT] = self.out.data_ptr()
+        return out
 
     def run(self, nets: Sequence[Network], scalar: Optional[complex] = None):
         """Full device path for a batch of structurally identical networks."""

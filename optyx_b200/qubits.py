@@ -124,8 +124,20 @@ def Id(n):
 root2 = Scalar(2 ** 0.5)
 
 
+_GATES: dict = {}
+
+
 def gate(name: str) -> Diagram:
-    """The standard-gate -> spider table, qubits.py:575-592."""
+    """The standard-gate -> spider table, qubits.py:575-592.  Diagrams are immutable
+    values: one instance per gate name (a circuit of thousands of gates then holds a
+    dozen distinct boxes, which the compile caches recognise by identity)."""
+    hit = _GATES.get(name)
+    if hit is None:
+        hit = _GATES[name] = _make_gate(name)
+    return hit
+
+
+def _make_gate(name: str) -> Diagram:
     table = {
         "H": lambda: H(),
         "Z": lambda: Z(1, 1, 0.5),

@@ -21,7 +21,7 @@ EXPORTS = [
     "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
     "b2_contract_direct", "b2_contract_gemm", "b2_run_small_program", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
-    "b2_fp64_peak_kernel",
+    "b2_fp64_peak_kernel", "b2_run_plan", "b2_workspace_bytes",
 ]
 
 
@@ -84,6 +84,30 @@ class SmallProgramArgs(C.Structure):
     ]
 
 
+MAX_SLICED = 16
+
+
+class _StepDesc(C.Union):
+    _fields_ = [("direct", Modes), ("gemm", GemmModes)]
+
+
+class PlanStep(C.Structure):
+    """b2_plan_step (include/optyx_b200.h): one row of the step table b2_run_plan walks."""
+    _fields_ = [
+        ("kind", C.c_int32), ("per_slice", C.c_int32), ("final", C.c_int32),
+        ("a_space", C.c_int32), ("b_space", C.c_int32), ("c_space", C.c_int32),
+        ("n_a_slice", C.c_int32), ("n_b_slice", C.c_int32),
+        ("a_off", C.c_int64), ("b_off", C.c_int64), ("c_off", C.c_int64), ("c_elems", C.c_int64),
+        ("a_slice_pos", C.c_int32 * MAX_SLICED), ("b_slice_pos", C.c_int32 * MAX_SLICED),
+        ("a_slice_stride", C.c_int64 * MAX_SLICED), ("b_slice_stride", C.c_int64 * MAX_SLICED),
+        ("desc", _StepDesc),
+    ]
+
+
+STEP_DIRECT, STEP_GEMM = 0, 1
+RUN_ZERO, RUN_INVARIANT, RUN_SLICES = 1, 2, 4
+
+
 class B2Error(RuntimeError):
     pass
 
@@ -118,6 +142,10 @@ def load():
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_contract_gemm.argtypes = [C.POINTER(GemmModes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_run_small_program.argtypes = [C.POINTER(SmallProgramArgs), i32, vp]
+    lib.b2_run_plan.argtypes = [C.POINTER(PlanStep), i32, C.POINTER(i32), i32,
+                                C.POINTER(SmallProgramArgs), vp, vp, vp, i64, i32, i64, i64,
+                                dbl, dbl, i32, vp, C.POINTER(i32)]
+    lib.b2_workspace_bytes.argtypes = [C.POINTER(PlanStep), i32, i32]
     lib.b2_axpy.argtypes = [i64, dbl, dbl, vp, vp, i32, vp]
     lib.b2_fill_zero.argtypes = [i64, vp, i32, vp]
     lib.b2_probs_amp.argtypes = [i64, vp, vp, vp, i32, vp]
@@ -128,8 +156,10 @@ def load():
     lib.b2_fp64_peak_kernel.argtypes = [i32, i32, vp, C.POINTER(dbl), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms"):
+        if name not in ("b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms",
+                        "b2_workspace_bytes"):
             fn.restype = C.c_int
+    lib.b2_workspace_bytes.restype = C.c_int64
     if lib.b2_abi_version() != 1:
         raise B2Error("liboptyx_b200.so ABI version mismatch")
     _lib = lib
