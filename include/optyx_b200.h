@@ -148,43 +148,32 @@ int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev,
  *
  * A step is   C[oc(o)] = sum_r A[oa(o) + ra(r)] * B[ob(o) + rb(r)]   with the operand
  * offsets of every output index o and every reduction index r TABULATED at plan time
- * (element offsets inside the scratch, < 2^16): no index arithmetic on the device.    */
+ * (element offsets inside the scratch, < 2^16): no index arithmetic on the device.
+ *
+ * Per task ONE blob of 32-bit words, copied into shared memory in a single coalesced
+ * pass when the task starts (a step never begins with a global-memory round trip):
+ *   header   [n_dep, n_imp, n_exp, n_steps, staged, 0, 0, 0]
+ *   deps     n_dep task ids (padded to an even count)
+ *   copies   (n_imp + n_exp) x 8 words: space (0 leaf arena, 1 workspace, 2 output),
+ *            scratch element offset, elements, 0, global element offset (lo, hi),
+ *            eval stride (lo, hi): address = base[space] + offset + eval * stride
+ *   steps    n_steps x 8 words: n_out, n_red, a_off, b_off, c_off (scratch elements),
+ *            rsplit (lanes sharing one output's reduction, 2^k <= 32), out_tab, red_tab
+ *   tables   when staged: out_tab / red_tab are WORD offsets into this blob (out rows
+ *            are 2 words: oa | ob << 16, oc; red rows 1 word: ra | rb << 16); otherwise
+ *            they are ROW offsets into the global tables below.
+ * Shared memory of a CTA: [blob, 16-byte aligned][scratch].                           */
 typedef struct {
-    int32_t n_out, n_red;            /* output / reduction index values                 */
-    int32_t a_off, b_off, c_off;     /* scratch element offsets of A, B, C              */
-    int32_t rsplit;                  /* lanes sharing one output's reduction (2^k <= 32) */
-    int32_t out_tab, red_tab;        /* first row of this step in the two tables        */
-} b2_sp_step;
-
-typedef struct {                     /* import (global -> scratch) or export            */
-    int32_t space;                   /* 0 leaf arena, 1 workspace, 2 output             */
-    int32_t smem_off;                /* scratch element offset                          */
-    int64_t glob_off;                /* element offset inside that space                */
-    int64_t eval_stride;             /* + eval * eval_stride (batched plans)            */
-    int32_t n;                       /* elements                                        */
-    int32_t reserved;
-} b2_sp_copy;
-
-typedef struct {
-    int32_t step_begin, step_end;
-    int32_t imp_begin, imp_end;      /* rows of the copy table                          */
-    int32_t exp_begin, exp_end;
-    int32_t dep_begin, dep_end;      /* rows of the dependency list (task ids)          */
-} b2_sp_task;
-
-typedef struct {
-    const b2_sp_task* tasks_dev;
-    const b2_sp_step* steps_dev;
-    const b2_sp_copy* copies_dev;
-    const int32_t* deps_dev;
-    const uint32_t* out_tab_dev;     /* 2 words per row: oa | ob << 16, oc              */
-    const uint32_t* red_tab_dev;     /* ra | rb << 16                                   */
+    const uint32_t* blob_dev;        /* all task blobs, back to back                    */
+    const int32_t* blob_off_dev;     /* [n_tasks + 1] word offsets                      */
+    const uint32_t* out_tab_dev;     /* tables of the tasks that do not stage theirs    */
+    const uint32_t* red_tab_dev;
     void* base_dev[3];               /* leaf arena, workspace, output                   */
-    int32_t* sync_dev;               /* [0] ticket [1] finished CTAs [2] epoch, then
-                                        batch * n_tasks done-flags; zero-filled ONCE    */
+    int32_t* sync_dev;               /* [0] ticket [1] finished CTAs [2] epoch [3] pad,
+                                        then batch * n_tasks done-flags; zero-filled ONCE */
     int32_t n_tasks;
     int32_t batch;
-    int32_t scratch_elems;           /* complex elements of shared memory per CTA       */
+    int32_t smem_bytes;              /* dynamic shared memory of the launch (largest task) */
     int32_t reserved;
 } b2_small_program;
 

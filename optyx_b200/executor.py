@@ -110,19 +110,19 @@ class Session:
             if raw.size == 0:
                 raw = np.zeros(16, dtype=np.uint8)
             return torch.from_numpy(raw.copy()).to(self.device)
-        self._sp_bufs = [up(sp.tasks), up(sp.steps), up(sp.copies), up(sp.deps),
-                         up(sp.out_tab), up(sp.red_tab)]
+        self._sp_bufs = [up(sp.blob), up(sp.blob_off), up(sp.out_tab), up(sp.red_tab)]
         # [ticket, finished CTAs, epoch, pad] + one done-flag per (eval, task); zeroed once
-        self._sp_sync = torch.zeros(4 + plan.batch * len(sp.tasks), dtype=torch.int32,
+        self._sp_sync = torch.zeros(4 + plan.batch * sp.n_tasks, dtype=torch.int32,
                                     device=self.device)
         args = rt.SmallProgramArgs()
-        (args.tasks_dev, args.steps_dev, args.copies_dev, args.deps_dev, args.out_tab_dev,
-         args.red_tab_dev) = [b.data_ptr() for b in self._sp_bufs]
+        args.blob_dev, args.blob_off_dev, args.out_tab_dev, args.red_tab_dev = \
+            [b.data_ptr() for b in self._sp_bufs]
         args.base_dev[ARENA] = self.arena.data_ptr()
         args.base_dev[WS] = self.ws.data_ptr()
         args.base_dev[OUT] = self.out.data_ptr()
         args.sync_dev = self._sp_sync.data_ptr()
-        args.n_tasks, args.batch, args.scratch_elems = len(sp.tasks), plan.batch, sp.scratch_elems
+        args.n_tasks, args.batch = sp.n_tasks, plan.batch
+        args.smem_bytes = sp.smem_bytes(self.esize)
         self.small_args = args
 
     def _init_step_table(self) -> None:

@@ -629,27 +629,45 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
 # --------------------------------------------------------------------------
 SMALL_ELEMS = 4096                  # largest operand / result of a step the interpreter takes
 SMALL_WORK = 1 << 18                # ... and its multiply-adds
-SMALL_SCRATCH_ELEMS = 12288         # shared-memory scratch of one task (complex elements: 192 KB c128)
+SMALL_SCRATCH_ELEMS = 11264         # scratch budget of one task (complex elements: 176 KB c128;
+                                    # the task blob -- records + staged tables -- rides beside it)
 SMALL_TASK_STEPS = 32               # single eval: steps per task (parallel subtrees run on
                                     # different CTAs; a batch runs one task chain per eval)
 SMALL_MERGE_STEPS = 6               # a sibling subtree this short is absorbed, not exported
 SMALL_MIN_STEPS = 8                 # fewer small steps than this: not worth the launch
 
 
+SMALL_STAGE_WORDS = 6144             # a task's offset tables up to this size ride in shared memory
+SP_HDR, SP_COPY_WORDS, SP_STEP_WORDS = 8, 8, 8
+
+
 @dataclass
 class SmallProgram:
-    """Every early tiny step of a plan as ONE persistent launch: tasks (chains of
-    steps executed by one CTA out of shared memory), their global imports / exports,
-    the dependency lists between tasks, and per-step offset tables."""
-    tasks: np.ndarray               # runtime.SP_TASK_DTYPE
-    steps: np.ndarray               # runtime.SP_STEP_DTYPE
-    copies: np.ndarray              # runtime.SP_COPY_DTYPE (imports and exports)
-    deps: np.ndarray                # int32 task ids
-    out_tab: np.ndarray             # uint32 [n, 2]: (oa | ob << 16, oc)
+    """Every early tiny step of a plan as ONE persistent launch.  Per task one BLOB of
+    32-bit words (what the CTA copies into shared memory in a single coalesced pass):
+    header [n_dep, n_imp, n_exp, n_steps, staged, 0, 0, 0] | dependency task ids |
+    copy records (imports, then exports; 8 words: space, scratch offset, n, 0,
+    global offset lo/hi, eval stride lo/hi) | step records (8 words: n_out, n_red,
+    a_off, b_off, c_off, rsplit, out_tab, red_tab) | the task's offset tables when they
+    are small enough to be staged (then out_tab / red_tab are word offsets into this
+    part, else row offsets into the global tables)."""
+    blob: np.ndarray                # uint32
+    blob_off: np.ndarray            # int32 [n_tasks + 1] word offsets
+    out_tab: np.ndarray             # uint32 [n, 2]: (oa | ob << 16, oc)  (unstaged tasks)
     red_tab: np.ndarray             # uint32: ra | rb << 16
-    scratch_elems: int
+    task_scratch: np.ndarray        # int32 [n_tasks]: scratch elements of each task
     step_ids: List[int]             # indices into plan.steps, in execution order
     task_of: Dict[int, int]         # plan step -> task
+
+    @property
+    def n_tasks(self) -> int:
+        return len(self.blob_off) - 1
+
+    def smem_bytes(self, esize: int) -> int:
+        """Dynamic shared memory of the launch: per task its blob (16-byte aligned),
+        then its scratch; the largest task decides."""
+        words = np.diff(self.blob_off).astype(np.int64)
+        return int((((words * 4 + 15) // 16) * 16 + self.task_scratch.astype(np.int64) * esize).max())
 
 
 def _mode_offsets(modes: List[List[int]]):
@@ -670,7 +688,6 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
     them into tasks, lay every task out in shared memory and tabulate the operand
     offsets of every output / reduction index (plan-time constants, shared by all
     evals of a batch and by every replay)."""
-    from .runtime import SP_COPY_DTYPE, SP_STEP_DTYPE, SP_TASK_DTYPE
     producer = {id(st.c): k for k, st in enumerate(steps)}
     consumer: Dict[int, int] = {}
     for k, st in enumerate(steps):
@@ -700,50 +717,71 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
         return None, ws_top
 
     # ---- tasks: walk the steps in (topological) plan order; a step continues the task
-    # of its larger operand subtree; the other operand's task is absorbed when short,
-    # otherwise it stays a task of its own (runs in parallel, result handed over in
-    # global memory).  A batch gets one chain per eval as long as shared memory allows.
+    # of its larger operand subtree; the other operand's task is absorbed when short
+    # (or whenever it fits, for a batch: parallelism comes from the evals), otherwise it
+    # stays a task of its own (runs in parallel, result handed over in global memory).
+    # Scratch need of a task = what it imports (resident throughout) + the peak of its
+    # live intermediates (an operand dies at its single consumer).
     max_steps = SMALL_TASK_STEPS if batch == 1 else 1 << 30
     merge_steps = SMALL_MERGE_STEPS if batch == 1 else 1 << 30
     task_of: Dict[int, int] = {}
-    members: Dict[int, List[int]] = {}          # open or closed task id -> steps
-    footprint: Dict[int, int] = {}              # conservative scratch need (no reuse)
+    members: Dict[int, List[int]] = {}
+    resident: Dict[int, int] = {}               # imports of the task (elements)
+    live: Dict[int, int] = {}                   # live intermediates right now
+    peak: Dict[int, int] = {}                   # peak of resident + live
 
     def leaf_need(st):
-        return sum(lay.size for lay in (st.a, st.b) if id(lay) not in producer)
+        seen, tot = set(), 0
+        for lay in (st.a, st.b):
+            if id(lay) not in producer and id(lay) not in seen:
+                seen.add(id(lay))
+                tot += lay.size
+        return tot
     nxt_task = 0
     for k in ids:
         st = steps[k]
-        ops = []
+        ops = {}
         for lay in (st.a, st.b):
             p = producer.get(id(lay))
             if p is not None:
-                ops.append(task_of[p])
-        ops = sorted(set(ops), key=lambda t: -len(members[t]))
-        need = st.c.size + leaf_need(st)
+                ops[task_of[p]] = lay.size
+        order = sorted(ops, key=lambda t: -len(members[t]))
         home = None
-        if ops:
-            t0 = ops[0]
-            if len(members[t0]) < max_steps and footprint[t0] + need <= SMALL_SCRATCH_ELEMS:
+        if order:
+            t0 = order[0]
+            if len(members[t0]) < max_steps and \
+                    resident[t0] + live[t0] + st.c.size + leaf_need(st) <= SMALL_SCRATCH_ELEMS:
                 home = t0
         if home is None:
             home = nxt_task
             nxt_task += 1
-            members[home], footprint[home] = [], 0
-        for t in ops:
+            members[home], resident[home], live[home], peak[home] = [], 0, 0, 0
+        resident[home] += leaf_need(st)
+        for t in order:
             if t == home:
                 continue
+            fits = max(peak[t] + resident[home] + live[home],
+                       resident[t] + live[t] + resident[home] + live[home] + st.c.size) \
+                <= SMALL_SCRATCH_ELEMS
             if len(members[t]) <= merge_steps and len(members[home]) + len(members[t]) < max_steps \
-                    and footprint[home] + footprint[t] + need <= SMALL_SCRATCH_ELEMS:
+                    and fits:
                 for q in members[t]:
                     task_of[q] = home
+                peak[home] = max(peak[home], peak[t] + resident[home] + live[home])
                 members[home] = sorted(members[home] + members.pop(t))
-                footprint[home] += footprint.pop(t)
+                resident[home] += resident.pop(t)
+                live[home] += live.pop(t)
+                peak.pop(t)
             else:
-                need += steps[[q for q in members[t] if consumer.get(q) == k][0]].c.size
+                resident[home] += ops[t]          # imported hand-over
         members[home].append(k)
-        footprint[home] += need
         task_of[k] = home
+        live[home] += st.c.size
+        peak[home] = max(peak[home], resident[home] + live[home])
+        for lay in (st.a, st.b):                  # in-task operands die here
+            p = producer.get(id(lay))
+            if p is not None and task_of[p] == home:
+                live[home] -= lay.size
     # renumber tasks in order of their LAST step: a task's dependencies then have
     # smaller numbers (tickets are handed out in task order: no waiting on a later one)
     order = sorted(members, key=lambda t: members[t][-1])
@@ -760,20 +798,24 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
             st.c.offset = int(ws_top)
             ws_top += st.c.size * batch
 
-    tasks = np.zeros(n_tasks, dtype=SP_TASK_DTYPE)
-    step_rows, copy_rows, dep_rows = [], [], []
     out_rows: List[np.ndarray] = []
     red_rows: List[np.ndarray] = []
     out_cache: Dict[bytes, int] = {}
     red_cache: Dict[bytes, int] = {}
     n_out_tab = n_red_tab = 0
-    scratch = 0
+    task_scratch: List[int] = []
     step_ids: List[int] = []
+    blobs: List[np.ndarray] = []
+    blob_off = [0]
 
     def eval_stride(lay):
         if batch == 1:
             return 0
         return arena_elems if lay.space == ARENA else lay.size
+
+    def copy_words(space, smem_off, glob_off, stride, n):
+        return [space, smem_off, n, 0, glob_off & 0xffffffff, glob_off >> 32,
+                stride & 0xffffffff, stride >> 32]
     for t in range(n_tasks):
         ks = members[t]
         inside = set(ks)
@@ -787,10 +829,12 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
                 p = producer.get(id(lay))
                 if p is None or p not in inside:
                     where[id(lay)] = alloc.alloc(lay.size)
-                    imports.append((lay.space, where[id(lay)], lay.offset, eval_stride(lay), lay.size))
+                    imports.append(copy_words(lay.space, where[id(lay)], lay.offset,
+                                              eval_stride(lay), lay.size))
                     if p is not None:
                         deps.append(task_of[p])
-        tasks[t]["step_begin"] = len(step_rows)
+        tabs = []                                # (otab, rtab) per step
+        rows = []
         for k in ks:
             st = steps[k]
             outm, redm = st.small_modes
@@ -798,55 +842,71 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
             where[id(st.c)] = c_off
             oa, ob, oc = _mode_offsets(outm)
             ra, rb, _ = _mode_offsets(redm)
-            assert max(oa.max() + ra.max(), 0) < st.a.size and max(ob.max() + rb.max(), 0) < st.b.size
+            assert oa.max() + ra.max() < st.a.size and ob.max() + rb.max() < st.b.size
             otab = np.stack([(oa | (ob << 16)), oc], axis=1).astype(np.uint32)
             rtab = (ra | (rb << 16)).astype(np.uint32)
-            key = otab.tobytes()
-            o_at = out_cache.get(key)
-            if o_at is None:
-                o_at = out_cache[key] = n_out_tab
-                out_rows.append(otab)
-                n_out_tab += len(otab)
-            key = rtab.tobytes()
-            r_at = red_cache.get(key)
-            if r_at is None:
-                r_at = red_cache[key] = n_red_tab
-                red_rows.append(rtab)
-                n_red_tab += len(rtab)
             n_out, n_red = len(otab), len(rtab)
             rsplit = 1                            # lanes sharing one output's reduction
             while rsplit < 32 and n_out * rsplit * 2 <= 256 and n_red >= 4 * rsplit:
                 rsplit *= 2
-            step_rows.append((n_out, n_red, where[id(st.a)], where[id(st.b)], c_off, rsplit, o_at, r_at))
+            rows.append([n_out, n_red, where[id(st.a)], where[id(st.b)], c_off, rsplit, 0, 0])
+            tabs.append((otab, rtab))
             step_ids.append(k)
             if consumer.get(k) not in inside:     # leaves the task: a root or a hand-over
-                exports.append((st.c.space, c_off, st.c.offset, eval_stride(st.c), st.c.size))
+                exports.append(copy_words(st.c.space, c_off, st.c.offset, eval_stride(st.c),
+                                          st.c.size))
             for lay in (st.a, st.b):              # single consumer: operands die here
                 p = producer.get(id(lay))
-                if p is not None and p in inside:
-                    alloc.release(where[id(lay)], lay.size)
-        tasks[t]["step_end"] = len(step_rows)
-        tasks[t]["imp_begin"] = len(copy_rows)
-        copy_rows.extend(imports)
-        tasks[t]["imp_end"] = tasks[t]["exp_begin"] = len(copy_rows)
-        copy_rows.extend(exports)
-        tasks[t]["exp_end"] = len(copy_rows)
-        tasks[t]["dep_begin"] = len(dep_rows)
-        dep_rows.extend(sorted(set(deps)))
-        tasks[t]["dep_end"] = len(dep_rows)
+                if p is not None and p in inside and id(lay) in where:
+                    alloc.release(where.pop(id(lay)), lay.size)
+        deps = sorted(set(deps))
         assert all(d < t for d in deps), "task order is not topological"
-        scratch = max(scratch, alloc.top)
-    assert scratch <= 14080, "small-step task exceeds the shared-memory scratch"
-    srows = np.array(step_rows, dtype=np.int32).reshape(-1, 8)
-    st_arr = np.zeros(len(step_rows), dtype=SP_STEP_DTYPE)
-    for j, name in enumerate(("n_out", "n_red", "a_off", "b_off", "c_off", "rsplit", "out_tab", "red_tab")):
-        st_arr[name] = srows[:, j]
-    cp_arr = np.zeros(len(copy_rows), dtype=SP_COPY_DTYPE)
-    for j, row in enumerate(copy_rows):
-        cp_arr[j] = tuple(row) + (0,)
-    return SmallProgram(tasks, st_arr, cp_arr, np.array(dep_rows, dtype=np.int32).reshape(-1),
-                        np.concatenate(out_rows).reshape(-1, 2), np.concatenate(red_rows).reshape(-1),
-                        int(scratch), step_ids, task_of), ws_top
+        tab_words = sum(2 * len(o) + len(r) + (len(r) & 1) for o, r in tabs)
+        staged = tab_words <= SMALL_STAGE_WORDS
+        head_words = SP_HDR + len(deps) + (len(deps) & 1) + \
+            SP_COPY_WORDS * (len(imports) + len(exports)) + SP_STEP_WORDS * len(rows)
+        tail: List[np.ndarray] = []
+        at = head_words                           # word offset of the staged tables in the blob
+        for row, (otab, rtab) in zip(rows, tabs):
+            if staged:
+                row[6], row[7] = at, at + 2 * len(otab)
+                tail.append(otab.reshape(-1))
+                tail.append(rtab)
+                if len(rtab) & 1:
+                    tail.append(np.zeros(1, dtype=np.uint32))
+                at += 2 * len(otab) + len(rtab) + (len(rtab) & 1)
+            else:
+                key = otab.tobytes()
+                o_at = out_cache.get(key)
+                if o_at is None:
+                    o_at = out_cache[key] = n_out_tab
+                    out_rows.append(otab)
+                    n_out_tab += len(otab)
+                key = rtab.tobytes()
+                r_at = red_cache.get(key)
+                if r_at is None:
+                    r_at = red_cache[key] = n_red_tab
+                    red_rows.append(rtab)
+                    n_red_tab += len(rtab)
+                row[6], row[7] = o_at, r_at
+        head = [len(deps), len(imports), len(exports), len(rows), int(staged), 0, 0, 0]
+        head += deps + ([0] if len(deps) & 1 else [])
+        for c in imports + exports:
+            head += c
+        for row in rows:
+            head += row
+        assert len(head) == head_words
+        blob = np.concatenate([np.array(head, dtype=np.int64).astype(np.uint32)] + tail)
+        blobs.append(blob)
+        blob_off.append(blob_off[-1] + len(blob))
+        task_scratch.append(int(alloc.top))
+        assert ((len(blob) * 4 + 15) // 16) * 16 + alloc.top * 16 <= 226 * 1024, \
+            "small-step task exceeds the shared memory of an SM"
+    return SmallProgram(
+        np.concatenate(blobs), np.array(blob_off, dtype=np.int32),
+        np.concatenate(out_rows).reshape(-1, 2) if out_rows else np.zeros((1, 2), dtype=np.uint32),
+        np.concatenate(red_rows).reshape(-1) if red_rows else np.zeros(1, dtype=np.uint32),
+        np.array(task_scratch, dtype=np.int32), step_ids, task_of), ws_top
 
 
 def plan_bound_seconds(plan: Plan, hbm_gbs: float, pipe_tflops: float) -> float:

@@ -63,23 +63,13 @@ class GemmModes(C.Structure):
     ]
 
 
-SP_STEP_DTYPE = np.dtype([(n, "<i4") for n in
-                          ("n_out", "n_red", "a_off", "b_off", "c_off", "rsplit", "out_tab", "red_tab")])
-SP_COPY_DTYPE = np.dtype([("space", "<i4"), ("smem_off", "<i4"), ("glob_off", "<i8"),
-                          ("eval_stride", "<i8"), ("n", "<i4"), ("reserved", "<i4")])
-SP_TASK_DTYPE = np.dtype([(n, "<i4") for n in
-                          ("step_begin", "step_end", "imp_begin", "imp_end", "exp_begin", "exp_end",
-                           "dep_begin", "dep_end")])
-assert SP_STEP_DTYPE.itemsize == 32 and SP_COPY_DTYPE.itemsize == 32 and SP_TASK_DTYPE.itemsize == 32
-
-
 class SmallProgramArgs(C.Structure):
     """b2_small_program (include/optyx_b200.h)."""
     _fields_ = [
-        ("tasks_dev", C.c_void_p), ("steps_dev", C.c_void_p), ("copies_dev", C.c_void_p),
-        ("deps_dev", C.c_void_p), ("out_tab_dev", C.c_void_p), ("red_tab_dev", C.c_void_p),
+        ("blob_dev", C.c_void_p), ("blob_off_dev", C.c_void_p),
+        ("out_tab_dev", C.c_void_p), ("red_tab_dev", C.c_void_p),
         ("base_dev", C.c_void_p * 3), ("sync_dev", C.c_void_p),
-        ("n_tasks", C.c_int32), ("batch", C.c_int32), ("scratch_elems", C.c_int32),
+        ("n_tasks", C.c_int32), ("batch", C.c_int32), ("smem_bytes", C.c_int32),
         ("reserved", C.c_int32),
     ]
 

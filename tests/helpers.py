@@ -110,35 +110,50 @@ def emulate_gemm(desc: rt.GemmModes, A, a_off, B, b_off, Cbuf, c_off, alpha, acc
 
 
 def emulate_small_program(sp, bufs, batch: int) -> None:
-    """numpy model of csrc/contract_small.cu: (eval, task) items in ticket order, every
-    task on a private NaN-filled scratch -- imports, the tabulated steps, exports; a
-    dependency that has not run yet, or a read of something never written, fails."""
+    """numpy model of csrc/contract_small.cu, parsing the same task BLOBS the kernel
+    copies into shared memory: (eval, task) items in ticket order, every task on a
+    private NaN-filled scratch -- imports, the tabulated steps, exports; a dependency
+    that has not run yet, or a read of something never written, fails."""
     done = set()
     ot_all, rt_all = sp.out_tab.astype(np.int64), sp.red_tab.astype(np.int64)
+    assert sp.smem_bytes(16) <= 226 * 1024
     for ev in range(batch):
-        for t, task in enumerate(sp.tasks):
-            for d in sp.deps[task["dep_begin"]:task["dep_end"]]:
+        for t in range(sp.n_tasks):
+            H = sp.blob[sp.blob_off[t]:sp.blob_off[t + 1]].astype(np.int64)
+            n_dep, n_imp, n_exp, n_steps, staged = (int(x) for x in H[:5])
+            at = 8
+            deps = H[at:at + n_dep]
+            at += n_dep + (n_dep & 1)
+            copies = H[at:at + 8 * (n_imp + n_exp)].reshape(-1, 8)
+            at += 8 * (n_imp + n_exp)
+            steps = H[at:at + 8 * n_steps].reshape(-1, 8)
+            for d in deps:
                 assert (ev, int(d)) in done and int(d) < t, "dependency runs later"
-            S = np.full(sp.scratch_elems, np.nan + 0j, dtype=complex)
-            for c in sp.copies[task["imp_begin"]:task["imp_end"]]:
-                src = int(c["glob_off"]) + ev * int(c["eval_stride"])
-                chunk = bufs[int(c["space"])][src:src + int(c["n"])]
+            S = np.full(int(sp.task_scratch[t]), np.nan + 0j, dtype=complex)
+
+            def glob(c):
+                return int(c[4] | (c[5] << 32)) + ev * int(c[6] | (c[7] << 32))
+            for c in copies[:n_imp]:
+                chunk = bufs[int(c[0])][glob(c):glob(c) + int(c[2])]
                 assert not np.isnan(chunk).any(), "import of an unwritten buffer"
-                S[int(c["smem_off"]):int(c["smem_off"]) + int(c["n"])] = chunk
-            for st in sp.steps[task["step_begin"]:task["step_end"]]:
-                ot = ot_all[st["out_tab"]:st["out_tab"] + st["n_out"]]
-                rt = rt_all[st["red_tab"]:st["red_tab"] + st["n_red"]]
+                S[int(c[1]):int(c[1]) + int(c[2])] = chunk
+            for st in steps:
+                n_out, n_red, a_off, b_off, c_off, rsplit, o_at, r_at = (int(x) for x in st)
+                if staged:
+                    assert o_at % 2 == 0
+                    ot = H[o_at:o_at + 2 * n_out].reshape(-1, 2)
+                    rt = H[r_at:r_at + n_red]
+                else:
+                    ot, rt = ot_all[o_at:o_at + n_out], rt_all[r_at:r_at + n_red]
                 oa, ob, oc = ot[:, 0] & 0xffff, ot[:, 0] >> 16, ot[:, 1]
                 ra, rb = rt & 0xffff, rt >> 16
-                assert st["rsplit"] in (1, 2, 4, 8, 16, 32)
-                vals = (S[st["a_off"] + oa[:, None] + ra[None, :]]
-                        * S[st["b_off"] + ob[:, None] + rb[None, :]]).sum(axis=1)
+                assert rsplit in (1, 2, 4, 8, 16, 32)
+                vals = (S[a_off + oa[:, None] + ra[None, :]]
+                        * S[b_off + ob[:, None] + rb[None, :]]).sum(axis=1)
                 assert not np.isnan(vals).any(), "step reads scratch nobody wrote"
-                S[st["c_off"] + oc] = vals
-            for c in sp.copies[task["exp_begin"]:task["exp_end"]]:
-                dst = int(c["glob_off"]) + ev * int(c["eval_stride"])
-                bufs[int(c["space"])][dst:dst + int(c["n"])] = \
-                    S[int(c["smem_off"]):int(c["smem_off"]) + int(c["n"])]
+                S[c_off + oc] = vals
+            for c in copies[n_imp:]:
+                bufs[int(c[0])][glob(c):glob(c) + int(c[2])] = S[int(c[1]):int(c[1]) + int(c[2])]
             done.add((ev, t))
 
 

@@ -57,9 +57,10 @@ if plan.small is not None:
     t_small = timed(lambda: sess._launch_small_groups(stream))
     macs = sum(plan.steps[k].macs for k in sp.step_ids)
     nbytes = sum(plan.steps[k].bytes for k in sp.step_ids)
-    longest = max(int(t["step_end"] - t["step_begin"]) for t in sp.tasks)
-    print(f"small-step program   {t_small*1e6:9.1f} us   {len(sp.step_ids)} steps in {len(sp.tasks)} tasks "
-          f"(longest {longest}), scratch {sp.scratch_elems*16/1024:.0f} KB, {macs:.3g} MACs, "
+    longest = max(int(sp.blob[sp.blob_off[t] + 3]) for t in range(sp.n_tasks))
+    staged = sum(int(sp.blob[sp.blob_off[t] + 4]) for t in range(sp.n_tasks))
+    print(f"small-step program   {t_small*1e6:9.1f} us   {len(sp.step_ids)} steps in {sp.n_tasks} tasks "
+          f"(longest {longest}, {staged} with staged tables), smem {sp.smem_bytes(16)/1024:.0f} KB, {macs:.3g} MACs, "
           f"{nbytes/t_small/1e9:.0f} GB/s algorithmic")
 vals = [0] * len(plan.sliced)
 rows = []
