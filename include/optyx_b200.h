@@ -113,6 +113,15 @@ int b2_build_leaves(const b2_leaf_desc* desc_dev, int32_t n_leaves,
                     int64_t arena_stride, int32_t batch, int32_t dtype,
                     void* stream);
 
+/* the same with a plan-time index: block_leaf_dev[b] = leaf holding arena element
+ * 256 * b (one trailing entry: the leaf holding the last element), so that a thread
+ * searches only the leaves of its own 256-element block                              */
+int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_leaves,
+                            const int32_t* block_leaf_dev, int64_t arena_elems,
+                            const void* params_dev, int64_t params_stride,
+                            void* arena_dev, int64_t arena_stride, int32_t batch,
+                            int32_t dtype, void* stream);
+
 /* (2a) thin / bandwidth-bound pairs: one thread per output element.
  * accumulate != 0: C += alpha * (...)                                        */
 int b2_contract_direct(const b2_modes* modes, const void* a_dev,

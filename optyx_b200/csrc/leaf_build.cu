@@ -62,70 +62,113 @@ __device__ __forceinline__ double leaf_value(const b2_leaf_desc& d, const int* i
     }
 }
 
+// One thread owns one arena ELEMENT and writes it for a whole group of evals: the leaf
+// lookup (a bounded binary search between the first and last leaf of the thread's
+// 256-element block, `block_leaf`, tabulated at plan time), the 32-bit multi-index decode
+// and the closed-form value are computed once and amortised over the evals of the
+// group; consecutive threads write consecutive addresses of one eval (coalesced 16-byte
+// stores).  Host-valued leaves (VEC / DENSE) read their per-eval value instead.
 template <typename T>
 __global__ void __launch_bounds__(256)
-leaf_build_kernel(const b2_leaf_desc* __restrict__ descs, int n_leaves, long long arena_elems,
+leaf_build_kernel(const b2_leaf_desc* __restrict__ descs, int n_leaves,
+                  const int* __restrict__ block_leaf, long long arena_elems,
                   const double2* __restrict__ params, long long params_stride,
-                  typename cplx<T>::type* __restrict__ arena, long long arena_stride) {
+                  typename cplx<T>::type* __restrict__ arena, long long arena_stride,
+                  int batch, int ev_per) {
     using C = typename cplx<T>::type;
-    const int ev = blockIdx.y;
-    C* out = arena + (long long)ev * arena_stride;
-    const double2* par = params ? params + (long long)ev * params_stride : nullptr;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < arena_elems;
-         e += (long long)gridDim.x * blockDim.x) {
-        // largest leaf with offset <= e
-        int lo = 0, hi = n_leaves - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (descs[mid].offset <= e) lo = mid; else hi = mid - 1;
-        }
-        const b2_leaf_desc d = descs[lo];
-        long long local = e - d.offset;
-        int idx[B2_MAX_LEAF_RANK];
-        long long rem = local;
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= arena_elems) return;
+    int lo, hi;
+    if (block_leaf) { lo = block_leaf[blockIdx.x]; hi = block_leaf[blockIdx.x + 1]; }
+    else { lo = 0; hi = n_leaves - 1; }
+    while (lo < hi) {                    // largest leaf with offset <= e
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&descs[mid].offset) <= e) lo = mid; else hi = mid - 1;
+    }
+    const b2_leaf_desc& dref = descs[lo];
+    b2_leaf_desc d;
+    d.kind = __ldg(&dref.kind);
+    d.ndim = __ldg(&dref.ndim);
+    d.ipar = __ldg(&dref.ipar);
+    const unsigned local = (unsigned)(e - __ldg(&dref.offset));
+    int idx[B2_MAX_LEAF_RANK];
+    bool from_params = d.kind == B2_K_VEC || d.kind == B2_K_DENSE;
+    double v = 0.0;
+    if (!from_params) {
+        unsigned rem = local;
         #pragma unroll
         for (int a = B2_MAX_LEAF_RANK - 1; a >= 0; --a) {
-            if (a < d.ndim) { idx[a] = (int)(rem % d.dims[a]); rem /= d.dims[a]; }
-            else idx[a] = 0;
+            if (a < d.ndim) {
+                const unsigned dim = (unsigned)__ldg(&dref.dims[a]);
+                d.dims[a] = (int)dim;
+                const unsigned q = rem / dim;
+                idx[a] = (int)(rem - q * dim);
+                rem = q;
+            } else idx[a] = 0;
         }
-        bool from_params;
-        double v = leaf_value(d, idx, from_params);
-        C val;
+        v = leaf_value(d, idx, from_params);
+    }
+    const long long poff = from_params ? __ldg(&dref.poff) + (long long)local : 0;
+    for (int g = blockIdx.y; (long long)g * ev_per < batch; g += gridDim.y) {
+        const int ev0 = g * ev_per, ev1 = min(batch, ev0 + ev_per);
+        C* out = arena + (long long)ev0 * arena_stride + e;
         if (from_params) {
-            double2 p = par[d.poff + local];
-            val.x = (T)p.x; val.y = (T)p.y;
+            const double2* par = params + (long long)ev0 * params_stride + poff;
+            for (int ev = ev0; ev < ev1; ++ev) {
+                const double2 pv = *par;
+                C val; val.x = (T)pv.x; val.y = (T)pv.y;
+                *out = val;
+                out += arena_stride; par += params_stride;
+            }
         } else {
-            val.x = (T)v; val.y = (T)0;
+            C val; val.x = (T)v; val.y = (T)0;
+            for (int ev = ev0; ev < ev1; ++ev) { *out = val; out += arena_stride; }
         }
-        out[e] = val;
     }
 }
 
 }  // namespace b2
+
+// block_leaf_dev: for every 256-element block of the arena the index of the leaf that
+// holds its first element, plus one trailing entry (= index of the leaf holding the last
+// element); may be null (then every thread searches the whole table).
+extern "C" int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_leaves,
+                                       const int32_t* block_leaf_dev, int64_t arena_elems,
+                                       const void* params_dev, int64_t params_stride,
+                                       void* arena_dev, int64_t arena_stride, int32_t batch,
+                                       int32_t dtype, void* stream) {
+    if (n_leaves <= 0 || arena_elems <= 0 || batch <= 0) return 0;
+    if (!desc_dev || !arena_dev) { b2::set_error("b2_build_leaves: null pointer"); return 1; }
+    int sms = b2::num_sms();
+    if (sms <= 0) return 1;
+    const long long blocks = (arena_elems + 255) / 256;
+    if (blocks > 2147483647ll) { b2::set_error("b2_build_leaves: arena too large"); return 1; }
+    // evals per thread: enough CTAs to fill the GPU a few times over, long enough store
+    // runs to amortise the decode
+    long long ev_per = (long long)batch * blocks / ((long long)sms * 16);
+    if (ev_per < 1) ev_per = 1;
+    if (ev_per > 64) ev_per = 64;
+    long long gy = (batch + ev_per - 1) / ev_per;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)blocks, (unsigned)gy);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == B2_C128)
+        b2::leaf_build_kernel<double><<<grid, 256, 0, s>>>(
+            desc_dev, n_leaves, block_leaf_dev, arena_elems, (const double2*)params_dev,
+            params_stride, (double2*)arena_dev, arena_stride, batch, (int)ev_per);
+    else if (dtype == B2_C64)
+        b2::leaf_build_kernel<float><<<grid, 256, 0, s>>>(
+            desc_dev, n_leaves, block_leaf_dev, arena_elems, (const double2*)params_dev,
+            params_stride, (float2*)arena_dev, arena_stride, batch, (int)ev_per);
+    else { b2::set_error("b2_build_leaves: bad dtype %d", dtype); return 1; }
+    return b2::check_launch("b2_build_leaves");
+}
 
 extern "C" int b2_build_leaves(const b2_leaf_desc* desc_dev, int32_t n_leaves,
                                int64_t arena_elems, const void* params_dev,
                                int64_t params_stride, void* arena_dev,
                                int64_t arena_stride, int32_t batch, int32_t dtype,
                                void* stream) {
-    if (n_leaves <= 0 || arena_elems <= 0 || batch <= 0) return 0;
-    if (!desc_dev || !arena_dev) { b2::set_error("b2_build_leaves: null pointer"); return 1; }
-    const int threads = 256;
-    long long blocks = (arena_elems + threads - 1) / threads;
-    int sms = b2::num_sms();
-    if (sms <= 0) return 1;
-    long long cap = (long long)sms * 8;
-    if (blocks > cap) blocks = cap;
-    dim3 grid((unsigned)blocks, (unsigned)batch);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == B2_C128)
-        b2::leaf_build_kernel<double><<<grid, threads, 0, s>>>(
-            desc_dev, n_leaves, arena_elems, (const double2*)params_dev, params_stride,
-            (double2*)arena_dev, arena_stride);
-    else if (dtype == B2_C64)
-        b2::leaf_build_kernel<float><<<grid, threads, 0, s>>>(
-            desc_dev, n_leaves, arena_elems, (const double2*)params_dev, params_stride,
-            (float2*)arena_dev, arena_stride);
-    else { b2::set_error("b2_build_leaves: bad dtype %d", dtype); return 1; }
-    return b2::check_launch("b2_build_leaves");
+    return b2_build_leaves_indexed(desc_dev, n_leaves, nullptr, arena_elems, params_dev,
+                                   params_stride, arena_dev, arena_stride, batch, dtype, stream);
 }

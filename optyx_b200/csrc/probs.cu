@@ -27,70 +27,138 @@ struct dm_layout {
     int kind[B2_MAX_MODES];   // 1 measured, 2 ket, 3 bra
 };
 
-// pass 1 (elementwise, coalesced): seen[meas] = 1 for every non-zero entry
-// (backends.py:339-341: every measured key that occurs is kept, 353-354)
+// pass 1 (streaming, coalesced): seen[meas] = 1 for every non-zero entry
+// (backends.py:339-341: every measured key that occurs is kept, 353-354).
+// The axes are split into a SLOW group (decoded once per tile with div/mod) and a FAST
+// group of `fast` elements (contiguous in memory) whose contribution to the measured
+// key is tabulated once per CTA in shared memory: per element one 16-byte load, one
+// table lookup, one compare.  A key is stored only while it still reads 0 (benign race:
+// every writer stores 1), so a dense tensor does not hammer a handful of addresses.
+constexpr int DM_FAST_MAX = 4096;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-probs_dm_seen_kernel(const __grid_constant__ dm_layout L, long long n,
+probs_dm_seen_kernel(const __grid_constant__ dm_layout L, int n_slow_axes, int fast,
+                     long long n_tiles, long long fast_key_mul,
                      const typename cplx<T>::type* __restrict__ t,
                      uint8_t* __restrict__ seen) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x) {
-        const auto v = t[e];
-        if (v.x == (T)0 && v.y == (T)0) continue;
-        long long rem = e, meas = 0, mul = 1;
-        for (int a = L.ndim - 1; a >= 0; --a) {
+    __shared__ unsigned tab[DM_FAST_MAX];
+    // key contribution of every position inside the fast block (axes n_slow_axes..ndim)
+    for (int f = threadIdx.x; f < fast; f += blockDim.x) {
+        int rem = f;
+        unsigned key = 0, mul = 1;
+        for (int a = L.ndim - 1; a >= n_slow_axes; --a) {
             const int d = L.dims[a];
-            const int i = (int)(rem % d);
+            const int i = rem % d;
             rem /= d;
-            if (L.kind[a] == 1) { meas += i * mul; mul *= d; }
+            if (L.kind[a] == 1) { key += (unsigned)i * mul; mul *= (unsigned)d; }
         }
-        seen[meas] = 1;
+        tab[f] = key;
+    }
+    __syncthreads();
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // measured key of the slow axes of this tile
+        long long rem = tile, key_slow = 0, mul = fast_key_mul;
+        for (int a = n_slow_axes - 1; a >= 0; --a) {
+            const int d = L.dims[a];
+            const long long i = rem % d;
+            rem /= d;
+            if (L.kind[a] == 1) { key_slow += i * mul; mul *= d; }
+        }
+        const typename cplx<T>::type* row = t + tile * (long long)fast;
+        for (int f = threadIdx.x; f < fast; f += blockDim.x) {
+            const auto v = row[f];
+            if (v.x != (T)0 || v.y != (T)0) {
+                uint8_t* s = seen + key_slow + tab[f];
+                if (*s == 0) *s = 1;
+            }
+        }
     }
 }
 
-// pass 2: one thread per measured key walks the unmeasured diagonal in C order
-// (the order in which the reference's dict loop adds them, 339-351), so the
-// floating-point sum is deterministic and ordered like the reference's.
+// pass 2: the diagonal of the unmeasured (ket, bra) pairs of every measured key.
+// `lanes` threads (a power of two <= 1024: a whole CTA, a sub-warp group, or one
+// thread) share one key: lane l sums diagonal entries l, l + lanes, ... in increasing
+// order and the partial sums are combined by a fixed butterfly, so the result is
+// deterministic.  The loads are strided by construction (the diagonal of a C-ordered
+// tensor); what matters is that all of them are in flight at once.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 probs_dm_sum_kernel(const __grid_constant__ dm_layout L, long long n_meas, long long n_diag,
-                    const typename cplx<T>::type* __restrict__ t, double* __restrict__ p,
-                    double* __restrict__ max_imag) {
-    double local_max = 0.0;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_meas;
-         k += (long long)gridDim.x * blockDim.x) {
-        // strides of every axis
-        long long stride[B2_MAX_MODES];
+                    int lanes, const typename cplx<T>::type* __restrict__ t,
+                    double* __restrict__ p, double* __restrict__ max_imag) {
+    __shared__ double red[8], redm[8];
+    long long stride[B2_MAX_MODES];
+    {
         long long s = 1;
         for (int a = L.ndim - 1; a >= 0; --a) { stride[a] = s; s *= L.dims[a]; }
-        // base offset from the measured key (C order over measured axes)
-        long long base = 0, rem = k;
+    }
+    const int keys_per_cta = lanes >= 256 ? 1 : 256 / lanes;
+    const int lane = lanes >= 256 ? threadIdx.x : threadIdx.x % lanes;
+    const int step = lanes >= 256 ? 256 : lanes;
+    double cta_max = 0.0;
+    for (long long k0 = (long long)blockIdx.x * keys_per_cta; k0 < n_meas;
+         k0 += (long long)gridDim.x * keys_per_cta) {
+        const long long k = k0 + (lanes >= 256 ? 0 : threadIdx.x / lanes);
+        const bool valid = k < n_meas;
+        long long base = 0, rem = valid ? k : 0;
         for (int a = L.ndim - 1; a >= 0; --a)
             if (L.kind[a] == 1) { base += (rem % L.dims[a]) * stride[a]; rem /= L.dims[a]; }
-        double acc = 0.0;
-        for (long long u = 0; u < n_diag; ++u) {
-            long long off = base, r = u;
-            for (int a = L.ndim - 1; a >= 0; --a)
-                if (L.kind[a] == 3) {   // bra half; its ket twin is axis a-1
-                    const long long i = r % L.dims[a];
-                    r /= L.dims[a];
-                    off += i * (stride[a] + stride[a - 1]);
-                }
-            const auto v = t[off];
-            if (v.x == (T)0 && v.y == (T)0) continue;   // not a dict entry
-            double val = (double)v.x;
-            const double im = fabs((double)v.y);
-            if (im > local_max) local_max = im;
-            if (val < 0 && fabs(val) < 1e-12) val = 0.0;   // backends.py:349-350
-            acc += val;
+        double acc = 0.0, mx = 0.0;
+        if (valid)
+            for (long long u = lane; u < n_diag; u += step) {
+                long long off = base, r = u;
+                for (int a = L.ndim - 1; a >= 0; --a)
+                    if (L.kind[a] == 3) {   // bra half; its ket twin is axis a-1
+                        const long long i = r % L.dims[a];
+                        r /= L.dims[a];
+                        off += i * (stride[a] + stride[a - 1]);
+                    }
+                const auto v = t[off];
+                if (v.x == (T)0 && v.y == (T)0) continue;   // not a dict entry
+                double val = (double)v.x;
+                const double im = fabs((double)v.y);
+                if (im > mx) mx = im;
+                if (val < 0 && fabs(val) < 1e-12) val = 0.0;   // backends.py:349-350
+                acc += val;
+            }
+        // combine the lanes of one key
+        const int width = lanes >= 32 ? 32 : lanes;
+        for (int m = width >> 1; m > 0; m >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, m);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
         }
-        p[k] = acc;
+        if (lanes >= 256) {                    // one key per CTA: 8 warps
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redm[threadIdx.x >> 5] = mx; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double a8 = 0.0, m8 = 0.0;
+                for (int w = 0; w < 8; ++w) { a8 += red[w]; m8 = fmax(m8, redm[w]); }
+                p[k] = a8;
+                if (m8 > cta_max) cta_max = m8;
+            }
+        } else if (lanes > 32) {               // 64 or 128 lanes: 2 or 4 warps per key
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redm[threadIdx.x >> 5] = mx; }
+            __syncthreads();
+            const int wpk = lanes / 32;
+            if (valid && lane == 0) {
+                const int w0 = (threadIdx.x >> 5);
+                double a8 = 0.0, m8 = 0.0;
+                for (int w = 0; w < wpk; ++w) { a8 += red[w0 + w]; m8 = fmax(m8, redm[w0 + w]); }
+                p[k] = a8;
+                if (m8 > cta_max) cta_max = m8;
+            }
+        } else if (valid && lane == 0) {
+            p[k] = acc;
+            if (mx > cta_max) cta_max = mx;
+        }
     }
     // max |Im| (np.real_if_close guard, backends.py:348): non-negative doubles
     // order like their bit patterns
-    if (local_max > 0.0)
-        atomicMax((unsigned long long*)max_imag, (unsigned long long)__double_as_longlong(local_max));
+    if (cta_max > 0.0)
+        atomicMax((unsigned long long*)max_imag, (unsigned long long)__double_as_longlong(cta_max));
 }
 
 template <typename T>
@@ -155,14 +223,38 @@ extern "C" int b2_probs_dm(int32_t ndim, const int32_t* dims, const int32_t* axi
     cudaStream_t s = (cudaStream_t)stream;
     cudaMemsetAsync(seen_dev, 0, (size_t)n_meas, s);
     cudaMemsetAsync(max_imag_dev, 0, sizeof(double), s);
-    unsigned g1 = b2::grid_for(n, 256, 8), g2 = b2::grid_for(n_meas, 128, 8);
+    // pass 1 split: trailing axes whose extents multiply to <= DM_FAST_MAX form the
+    // fast block (at least one axis, unless it alone is larger: then no fast axes)
+    int n_slow = ndim;
+    long long fast = 1, fast_key_mul = 1;
+    while (n_slow > 0 && fast * dims[n_slow - 1] <= b2::DM_FAST_MAX) {
+        --n_slow;
+        fast *= dims[n_slow];
+        if (axis_kind[n_slow] == 1) fast_key_mul *= dims[n_slow];
+    }
+    const long long n_tiles = n / fast;
+    // pass 2 parallelism: as many lanes per key as its diagonal has entries
+    int lanes = 1;
+    while (lanes < 256 && lanes < n_diag) lanes <<= 1;
+    const long long keys_per_cta = lanes >= 256 ? 1 : 256 / lanes;
+    long long g2l = (n_meas + keys_per_cta - 1) / keys_per_cta;
+    const long long cap2 = (long long)b2::num_sms() * 8;
+    if (g2l > cap2) g2l = cap2;
+    if (g2l < 1) g2l = 1;
+    long long g1l = n_tiles;
+    const long long cap1 = (long long)b2::num_sms() * 8;
+    if (g1l > cap1) g1l = cap1;
+    if (g1l < 1) g1l = 1;
+    const unsigned g1 = (unsigned)g1l, g2 = (unsigned)g2l;
     if (dtype == B2_C128) {
-        b2::probs_dm_seen_kernel<double><<<g1, 256, 0, s>>>(L, n, (const double2*)t_dev, seen_dev);
-        b2::probs_dm_sum_kernel<double><<<g2, 128, 0, s>>>(L, n_meas, n_diag,
+        b2::probs_dm_seen_kernel<double><<<g1, 256, 0, s>>>(L, n_slow, (int)fast, n_tiles, fast_key_mul,
+                                                          (const double2*)t_dev, seen_dev);
+        b2::probs_dm_sum_kernel<double><<<g2, 256, 0, s>>>(L, n_meas, n_diag, lanes,
                                                          (const double2*)t_dev, p_dev, max_imag_dev);
     } else if (dtype == B2_C64) {
-        b2::probs_dm_seen_kernel<float><<<g1, 256, 0, s>>>(L, n, (const float2*)t_dev, seen_dev);
-        b2::probs_dm_sum_kernel<float><<<g2, 128, 0, s>>>(L, n_meas, n_diag,
+        b2::probs_dm_seen_kernel<float><<<g1, 256, 0, s>>>(L, n_slow, (int)fast, n_tiles, fast_key_mul,
+                                                         (const float2*)t_dev, seen_dev);
+        b2::probs_dm_sum_kernel<float><<<g2, 256, 0, s>>>(L, n_meas, n_diag, lanes,
                                                         (const float2*)t_dev, p_dev, max_imag_dev);
     } else { b2::set_error("b2_probs_dm: bad dtype"); return 1; }
     return b2::check_launch("b2_probs_dm");

@@ -184,6 +184,11 @@ class Session:
         if self.desc_dev is None:
             self.n_leaves = len(table)
             self.desc_dev = torch.from_numpy(table.view(np.uint8).copy()).to(self.device)
+            # leaf holding the first element of every 256-element block of the arena
+            firsts = np.arange(0, plan.arena_elems, 256, dtype=np.int64)
+            firsts = np.append(firsts, plan.arena_elems - 1)
+            block_leaf = np.searchsorted(table["offset"], firsts, side="right") - 1
+            self.block_leaf_dev = torch.from_numpy(block_leaf.astype(np.int32)).to(self.device)
             self.params_stride = len(p0)
             self.params_host = torch.empty((plan.batch, len(p0)), dtype=torch.complex128,
                                            pin_memory=True)
@@ -205,8 +210,8 @@ class Session:
     def build_leaves(self) -> None:
         plan = self.plan
         stream = self.torch.cuda.current_stream().cuda_stream
-        rt.check(self.lib.b2_build_leaves(
-            self.desc_dev.data_ptr(), self.n_leaves, plan.arena_elems,
+        rt.check(self.lib.b2_build_leaves_indexed(
+            self.desc_dev.data_ptr(), self.n_leaves, self.block_leaf_dev.data_ptr(), plan.arena_elems,
             self.params_dev.data_ptr(), self.params_stride, self.arena.data_ptr(),
             plan.arena_elems, plan.batch, self.code, stream), "b2_build_leaves")
         self.launches += 1

@@ -21,7 +21,7 @@ EXPORTS = [
     "b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms", "b2_build_leaves",
     "b2_contract_direct", "b2_contract_gemm", "b2_run_small_program", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
-    "b2_fp64_peak_kernel", "b2_run_plan", "b2_workspace_bytes",
+    "b2_fp64_peak_kernel", "b2_run_plan", "b2_workspace_bytes", "b2_build_leaves_indexed",
 ]
 
 
@@ -129,6 +129,7 @@ def load():
     lib.b2_last_kernel.restype = C.c_char_p
     lib.b2_device_sms.restype = C.c_int
     lib.b2_build_leaves.argtypes = [vp, i32, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.b2_build_leaves_indexed.argtypes = [vp, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_contract_gemm.argtypes = [C.POINTER(GemmModes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_run_small_program.argtypes = [C.POINTER(SmallProgramArgs), i32, vp]
