@@ -38,7 +38,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC, UNIT = "eval_diagrams_per_sec", "diagrams/s"
 FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profiles/r01_probe.json)
-CFG4_TARGET = float(2 ** 26)
+CFG4_TARGET = float(2 ** 27)       # <= 2^27 elements (2 GiB complex128) per slice
+CFG4_MIN_SLICES = 32               # ... and >= 32 slices, so that 8 GPUs get >= 4 each
 
 
 def peaks():
@@ -58,11 +59,12 @@ def workload(name: str):
     diagrams per step)."""
     from optyx_b200 import workloads as cases
     if name == "cfg4":
-        n, depth = 30, 41
+        n, depth = 30, 44
         return dict(kind="sliced", factory=lambda: cases.random_clifford_t(n, depth, seed=0),
-                    target=CFG4_TARGET, trials=16,
+                    target=CFG4_TARGET, trials=16, min_slices=CFG4_MIN_SLICES,
                     desc=f"cfg4: {n}-qubit brickwork Clifford+T depth {depth} amplitude <0|C|0>, "
-                         f"sliced to <= 2^{int(math.log2(CFG4_TARGET))} elements per slice")
+                         f"sliced to <= 2^{int(math.log2(CFG4_TARGET))} elements per slice, "
+                         f">= {CFG4_MIN_SLICES} slices")
     if name == "cfg2":
         n, k = 20, 14
         return dict(kind="single", factory=lambda: cases.ghz(n, open_qubits=k, noise=0.95),
@@ -199,7 +201,8 @@ def cpu_reference(name: str, budget_s: float = 25.0, max_evals: int = 3):
         # the tree: found on the product's network (hyper-indices) -- the numpy port
         # contracts that same network so that it does the same arithmetic per slice
         net = B200Backend()._get_network(d)
-        plan = executor.get_plan(net, target_size=w["target"], trials=w["trials"])
+        plan = executor.get_plan(net, target_size=w["target"], trials=w["trials"],
+                                 min_slices=w.get("min_slices", 1))
         from oracle import leaves as ol
         arrays = ol.build_all(net.leaves)
         inds = [list(l.inds) for l in net.leaves]
@@ -313,7 +316,8 @@ class Bench:
         from optyx_b200.planner import plan_bound_seconds
         w = workload(name)
         world = self.world if sharded else 1
-        backend_kw = dict(target_size=w["target"], trials=w["trials"])
+        backend_kw = dict(target_size=w["target"], trials=w["trials"],
+                          min_slices=w.get("min_slices", 1))
         compile_backend = B200Backend(**backend_kw)
         t0 = time.perf_counter()
         if w["kind"] == "batch":

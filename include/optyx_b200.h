@@ -291,6 +291,21 @@ int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
                            int64_t n_configs, int32_t n_bins, double* hist_dev,
                            void* stream);
 
+/* (6) host side of the planner (CPU only, no kernels): the randomised greedy pair-order
+ * search and the cost of a pair order under slicing, for networks of thousands of
+ * tensors (the reference hands this to cotengra, backends.py:436-455).  Tensors are index
+ * lists in CSR form over index ids 0..n_inds-1; hyper-indices and open indices allowed.
+ * b2_plan_greedy writes the SSA pair order (2 * (n - 1) ids, step k creates id n + k);
+ * b2_plan_cost writes [multiply-adds per slice, largest intermediate (elements),
+ * number of slices, roofline time estimate in seconds] and, optionally, log2 of every
+ * step's result size.                                                                */
+int b2_plan_greedy(int32_t n, const int32_t* ind_ptr, const int32_t* inds, int32_t n_inds,
+                   const int32_t* dims, const uint8_t* is_output, uint64_t seed,
+                   double temperature, double costmod, int32_t* path_out);
+int b2_plan_cost(int32_t n, const int32_t* ind_ptr, const int32_t* inds, int32_t n_inds,
+                 const int32_t* dims, const uint8_t* is_output, const int32_t* path,
+                 const uint8_t* is_sliced, double* out, double* step_sizes_out);
+
 /* micro-benchmarks used by bench.py to measure the FP64 pipes of this GPU:
  * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = DMMA m16n8k16 (falls back to 1 if the
  * shape is unavailable).  Launches `iters` dependent-chain iterations on a

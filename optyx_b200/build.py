@@ -25,7 +25,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["abi.cu", "leaf_build.cu", "contract_direct.cu", "contract_gemm.cu", "contract_gemm_c64.cu",
            "contract_ctile.cu", "contract_fma.cu", "contract_small.cu", "permanent.cu", "probs.cu",
-           "compact.cu", "plan_runner.cu", "compress.cu"]
+           "compact.cu", "plan_runner.cu", "planner_native.cu", "compress.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

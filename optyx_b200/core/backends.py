@@ -313,7 +313,8 @@ class B200Backend(AbstractBackend):
     """
 
     def __init__(self, hyperoptimiser=None, contraction_params: Optional[dict] = None,
-                 dtype="complex128", target_size: Optional[int] = None, trials: int = 8,
+                 dtype="complex128", target_size: Optional[int] = None, min_slices: int = 1,
+                 trials: int = 8,
                  seed: int = 0, distributed: bool = False, keep_on_device: bool = True,
                  sparse_d2h: bool = True, lazy_host: bool = True, cache_networks: bool = True):
         # backends.py:436-455: stored as given, checked when a term is contracted (526-534)
@@ -323,6 +324,7 @@ class B200Backend(AbstractBackend):
         if self.dtype not in (np.dtype(np.complex128), np.dtype(np.complex64)):
             raise ValueError(f"Unsupported dtype {dtype}: use complex128 or complex64")
         self.target_size = target_size
+        self.min_slices = min_slices      # at least this many slices (units that shard over GPUs)
         self.trials, self.seed = trials, seed
         self.distributed = distributed
         self.keep_on_device = keep_on_device
@@ -511,7 +513,7 @@ class B200Backend(AbstractBackend):
             plan = executor.get_plan(net, dtype=self.dtype, ssa_path=ssa_path, sliced_inds=sliced)
         else:
             plan = executor.get_plan(net, dtype=self.dtype, target_size=self.target_size,
-                                     trials=self.trials, seed=self.seed)
+                                     trials=self.trials, seed=self.seed, min_slices=self.min_slices)
         self.last_plan = plan
         sess = self._session(plan)
         if self.distributed:

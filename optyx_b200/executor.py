@@ -397,7 +397,7 @@ _PLAN_CACHE: Dict[tuple, Plan] = {}
 
 def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None,
              trials: int = 8, seed: int = 0, gemm_threshold=(32, 16, 8, 4.0),
-             ssa_path=None, sliced_inds=()) -> Plan:
+             ssa_path=None, sliced_inds=(), min_slices: int = 1) -> Plan:
     """Plan cache keyed by network *structure* (the counterpart of cotengra's
     ReusableHyperOptimizer the reference accepts, backends.py:49-56, 436-455).
     ``ssa_path`` (+ ``sliced_inds``): execute that contraction tree instead of
@@ -405,7 +405,7 @@ def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None
     tree_key = None if ssa_path is None else (tuple(tuple(int(i) for i in e) for e in ssa_path),
                                               tuple(int(q) for q in sliced_inds))
     key = (net.structure_key(), np.dtype(dtype).str, batch, target_size, trials, seed,
-           tuple(gemm_threshold), tree_key)
+           tuple(gemm_threshold), tree_key, min_slices)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         if ssa_path is not None:
@@ -413,7 +413,8 @@ def get_plan(net: Network, dtype=np.complex128, batch: int = 1, target_size=None
                                       gemm_threshold=gemm_threshold)
         else:
             plan = plan_network(net, dtype=dtype, batch=batch, trials=trials, seed=seed,
-                                target_size=target_size, gemm_threshold=gemm_threshold)
+                                target_size=target_size, gemm_threshold=gemm_threshold,
+                                min_slices=min_slices)
         _PLAN_CACHE[key] = plan
     return plan
 

@@ -186,14 +186,25 @@ def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: froz
                     t_inv + nslices * t_dep)
 
 
+NATIVE_MIN_TENSORS = 64        # from here on the search runs in C++ (csrc/planner_native.cu)
+NATIVE_TRIALS_PER_TRIAL = 16   # ... and affords this many more randomised trials
+
+
 def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
               minimize: str = "flops", target_size: Optional[float] = None,
-              slice_candidates: int = 4) -> PathInfo:
+              slice_candidates: int = 4, min_slices: int = 1) -> PathInfo:
     """Best of a deterministic greedy plus ``trials-1`` noisy ones.  With a
     ``target_size`` the candidates are compared AFTER slicing, by the roofline
     estimate of the whole sliced contraction (a tree that is cheapest unsliced can
     be far from the cheapest once its widest tensors must be cut): the
-    ``slice_candidates`` cheapest trees are sliced and the best sliced one wins."""
+    ``slice_candidates`` cheapest trees are sliced and the best sliced one wins.
+    ``min_slices``: keep slicing (cheapest index first) until there are at least that
+    many slices -- the units that shard over GPUs.  Networks of ``NATIVE_MIN_TENSORS``
+    tensors or more are searched by the C++ implementation with 16x the trials."""
+    need_slicing = target_size is not None or min_slices > 1
+    if len(inputs) >= NATIVE_MIN_TENSORS:
+        return _find_path_native(inputs, dims, output, max(1, trials) * NATIVE_TRIALS_PER_TRIAL,
+                                 seed, minimize, target_size, max(slice_candidates, 12), min_slices)
     cands = []
     rng = random.Random(seed)
     for t in range(max(1, trials)):
@@ -207,18 +218,52 @@ def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
         key = (info.macs, info.peak) if minimize == "flops" else (info.peak, info.macs)
         cands.append((key, t, info))
     cands.sort(key=lambda c: (c[0], c[1]))
-    if target_size is None or cands[0][2].peak <= target_size:
+    if not need_slicing or (min_slices <= 1 and cands[0][2].peak <= target_size):
         return cands[0][2]
     best = None
     for _, _, info in cands[:max(1, slice_candidates)]:
-        sl = slice_path(inputs, dims, output, info, target_size) if info.peak > target_size else info
+        sl = slice_path(inputs, dims, output, info, target_size, min_slices=min_slices)
         if best is None or sl.time_est < best.time_est:
             best = sl
     return best
 
 
-def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
-               max_slices: int = 1 << 24) -> PathInfo:
+def _find_path_native(inputs, dims, output, trials, seed, minimize, target_size,
+                      slice_candidates, min_slices) -> PathInfo:
+    nn = NativeNetwork(inputs, dims, output)
+    rng = random.Random(seed)
+    cands = []
+    for t in range(trials):
+        if t == 0:
+            p = nn.greedy(seed=seed)
+        else:
+            p = nn.greedy(seed=seed * 7919 + t, temperature=0.3 + 0.7 * rng.random(),
+                          costmod=rng.choice([0.5, 1.0, 1.0, 2.0]))
+        macs, peak, _, _ = nn.cost(p)
+        cands.append((macs, peak, t, p))
+    need_slicing = target_size is not None or min_slices > 1
+
+    def info_of(p):
+        return analyse_path(inputs, dims, output, [tuple(x) for x in p.tolist()])
+    if not need_slicing:
+        cands.sort(key=lambda c: (c[0], c[1], c[2]) if minimize == "flops" else (c[1], c[0], c[2]))
+        return info_of(cands[0][3])
+    tgt = target_size if target_size is not None else float("inf")
+    # rank by work x how far the widest tensor overshoots (each factor of two over the
+    # target costs at least one sliced index), slice the best few, compare by time
+    cands.sort(key=lambda c: (c[0] * max(1.0, c[1] / tgt), c[2]))
+    best = None
+    for macs, peak, _, p in cands[:max(1, slice_candidates)]:
+        info = info_of(p)
+        if info.peak > tgt or min_slices > 1:
+            info = slice_path(inputs, dims, output, info, target_size, min_slices=min_slices)
+        if best is None or info.time_est < best.time_est:
+            best = info
+    return best
+
+
+def slice_path(inputs, dims, output, info: PathInfo, target_size: Optional[float],
+               max_slices: int = 1 << 24, min_slices: int = 1) -> PathInfo:
     """Greedy index slicing until the largest intermediate fits ``target_size``
     elements.  Works on step x index incidence matrices (numpy): each round
     scores every candidate index by (bits of oversize removed over all oversized
@@ -248,12 +293,19 @@ def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
             allowed[col[q]] = False
     allowed &= logd > 0
     cur_u, cur_r = Uf @ logd, Rf @ logd
-    log_target = math.log2(target_size)
+    log_target = math.log2(target_size) if target_size is not None else float("inf")
+    log_min = math.log2(max(1, min_slices))
     sliced: List[int] = []
     log_slices = 0.0
-    while cur_r.max() > log_target + 1e-9 and log_slices < math.log2(max_slices):
+    while (cur_r.max() > log_target + 1e-9 or log_slices < log_min - 1e-9) \
+            and log_slices < math.log2(max_slices):
         over = cur_r > log_target + 1e-9
-        cand = np.flatnonzero(allowed & R[over].any(axis=0))
+        if over.any():
+            cand = np.flatnonzero(allowed & R[over].any(axis=0))
+        else:
+            # everything fits already: more slices are wanted as units of parallel
+            # work -- any index will do, the cheapest (least extra work) wins
+            cand = np.flatnonzero(allowed & U.any(axis=0))
         if cand.size == 0:
             break
         excess_now = np.maximum(cur_r - log_target, 0.0).sum()
@@ -265,10 +317,13 @@ def slice_path(inputs, dims, output, info: PathInfo, target_size: float,
         macs = np.logaddexp2.reduce(new_u, axis=0) + log_slices + logd[cand]
         gain = excess_now - excess
         overhead = np.maximum(macs - macs_now, 0.0)
-        score = gain / (overhead + 0.05)
-        j = int(np.argmax(score))
-        if gain[j] <= 0:
-            break
+        if over.any():
+            score = gain / (overhead + 0.05)
+            j = int(np.argmax(score))
+            if gain[j] <= 0:
+                break
+        else:
+            j = int(np.argmin(overhead))
         c = int(cand[j])
         sliced.append(ids[c])
         allowed[c] = False
@@ -1004,13 +1059,67 @@ def plan_from_ssa_path(net: Network, ssa_path: Sequence[Sequence[int]],
 
 def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int = 8,
                  seed: int = 0, target_size: Optional[float] = None,
-                 gemm_threshold: Tuple = (32, 16, 8, 4.0)) -> Plan:
-    """Path search (+ slicing to ``target_size`` elements) + compilation."""
+                 gemm_threshold: Tuple = (32, 16, 8, 4.0), min_slices: int = 1) -> Plan:
+    """Path search (+ slicing to ``target_size`` elements / ``min_slices`` slices) +
+    compilation."""
     inputs = [frozenset(l.inds) for l in net.leaves]
     output = frozenset(net.output_inds)
     if len(inputs) >= 2:
         info = find_path(inputs, net.dims, output, trials=trials, seed=seed,
-                         target_size=target_size)
+                         target_size=target_size, min_slices=min_slices)
     else:
         info = PathInfo([], (), 0.0, 0.0, 1, [])
     return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)
+
+
+# --------------------------------------------------------------------------
+# native (C++) path search: csrc/planner_native.cu behind the C ABI
+# --------------------------------------------------------------------------
+class NativeNetwork:
+    """A network in the CSR form ``b2_plan_greedy`` / ``b2_plan_cost`` take: compact
+    index ids, extents, open-index flags.  Built once per search."""
+
+    def __init__(self, inputs: Sequence[frozenset], dims: Dict[int, int], output: frozenset):
+        from . import runtime as rt
+        self.lib = rt.load()
+        ids = sorted({q for s in inputs for q in s} | set(output))
+        self.ids = ids
+        self.col = {q: k for k, q in enumerate(ids)}
+        self.n = len(inputs)
+        ptr = np.zeros(self.n + 1, dtype=np.int32)
+        flat: List[int] = []
+        for k, s in enumerate(inputs):
+            flat.extend(self.col[q] for q in s)
+            ptr[k + 1] = len(flat)
+        self.ptr = ptr
+        self.flat = np.array(flat, dtype=np.int32) if flat else np.zeros(1, dtype=np.int32)
+        self.dims = np.array([dims[q] for q in ids], dtype=np.int32) if ids else np.zeros(1, dtype=np.int32)
+        out = np.zeros(max(1, len(ids)), dtype=np.uint8)
+        for q in output:
+            out[self.col[q]] = 1
+        self.is_output = out
+
+    def greedy(self, seed: int = 0, temperature: float = 0.0, costmod: float = 1.0) -> np.ndarray:
+        """SSA pair order as an int32 array [n - 1, 2]."""
+        from . import runtime as rt
+        path = np.zeros(max(1, 2 * (self.n - 1)), dtype=np.int32)
+        rt.check(self.lib.b2_plan_greedy(
+            self.n, self.ptr.ctypes.data, self.flat.ctypes.data, len(self.ids), self.dims.ctypes.data,
+            self.is_output.ctypes.data, seed, temperature, costmod, path.ctypes.data), "b2_plan_greedy")
+        return path[:2 * (self.n - 1)].reshape(-1, 2)
+
+    def cost(self, path: np.ndarray, sliced: Sequence[int] = (), want_sizes: bool = False):
+        """(macs per slice, peak elements, nslices, time estimate[, log2 step sizes])."""
+        from . import runtime as rt
+        path = np.ascontiguousarray(path, dtype=np.int32)
+        flags = np.zeros(max(1, len(self.ids)), dtype=np.uint8)
+        for q in sliced:
+            flags[self.col[q]] = 1
+        out = np.zeros(4, dtype=np.float64)
+        sizes = np.zeros(max(1, self.n - 1), dtype=np.float64) if want_sizes else None
+        rt.check(self.lib.b2_plan_cost(
+            self.n, self.ptr.ctypes.data, self.flat.ctypes.data, len(self.ids), self.dims.ctypes.data,
+            self.is_output.ctypes.data, path.ctypes.data, flags.ctypes.data, out.ctypes.data,
+            sizes.ctypes.data if want_sizes else None), "b2_plan_cost")
+        res = (float(out[0]), float(out[1]), int(round(out[2])), float(out[3]))
+        return res + (sizes,) if want_sizes else res

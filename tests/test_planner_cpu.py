@@ -367,3 +367,50 @@ def test_small_step_tasks_run_in_parallel_for_one_eval_and_in_one_chain_per_batc
     assert single.n_tasks > batched.n_tasks >= 1
     steps_of = [int(single.blob[single.blob_off[t] + 3]) for t in range(single.n_tasks)]
     assert max(steps_of) <= planner.SMALL_TASK_STEPS
+
+
+# ---- native (C++) path search behind the C ABI ---------------------------------------------
+def test_native_greedy_and_cost_agree_with_the_python_planner():
+    """b2_plan_greedy gives a valid SSA pair order; b2_plan_cost == analyse_path on it
+    (MACs, widest intermediate, slice count and roofline estimate), sliced or not."""
+    import cases
+    from optyx_b200 import planner
+    net = cases.compile_channel(cases.random_clifford_t(12, 10, seed=4))
+    inputs = [frozenset(l.inds) for l in net.leaves]
+    output = frozenset(net.output_inds)
+    nn = planner.NativeNetwork(inputs, net.dims, output)
+    n = len(inputs)
+    for seed, temp in ((0, 0.0), (1, 0.5), (2, 1.0)):
+        p = nn.greedy(seed=seed, temperature=temp, costmod=1.0)
+        assert p.shape == (n - 1, 2)
+        used = set()
+        for k, (a, b) in enumerate(p.tolist()):
+            assert a != b and a < n + k and b < n + k and a not in used and b not in used
+            used.update((a, b))
+        path = [tuple(x) for x in p.tolist()]
+        closed = sorted({q for s in inputs for q in s} - output)
+        for sliced in ((), tuple(closed[:3])):
+            info = planner.analyse_path(inputs, net.dims, output, path, sliced)
+            macs, peak, nslices, est = nn.cost(p, sliced)
+            assert (macs, peak, nslices) == (info.macs, info.peak, info.nslices)
+            assert abs(est - info.time_est) <= 1e-12 * max(1.0, est)
+    # same seed, same tree (every rank of a job must find the same plan)
+    assert np.array_equal(nn.greedy(seed=5, temperature=0.7), nn.greedy(seed=5, temperature=0.7))
+    # a plan built from the native search contracts to the oracle's tensor
+    plan = planner.plan_network(net, target_size=64.0, min_slices=8)
+    assert plan.nslices >= 8 and plan.info.peak <= 64
+    assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)
+
+
+def test_min_slices_keeps_slicing_with_the_cheapest_indices():
+    from optyx_b200 import planner
+    rng = np.random.default_rng(11)
+    net = random_network(rng, n_leaves=9, n_inds=12, n_out=1, dims=(2,))
+    inputs = [frozenset(l.inds) for l in net.leaves]
+    output = frozenset(net.output_inds)
+    base = planner.find_path(inputs, net.dims, output, trials=4)
+    more = planner.find_path(inputs, net.dims, output, trials=4, min_slices=4)
+    assert base.nslices == 1 and more.nslices >= 4
+    assert not (set(more.sliced) & output)
+    plan = planner.plan_network(net, min_slices=4)
+    assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)

@@ -18,7 +18,7 @@ from optyx_b200.core.backends import B200Backend  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w = bench.workload(name)
-backend = B200Backend(target_size=w["target"], trials=w["trials"])
+backend = B200Backend(target_size=w["target"], trials=w["trials"], min_slices=w.get("min_slices", 1))
 if w["kind"] == "batch":
     nets, _ = backend.compile_batch(w["make"], w["batch"])
     for net in nets:
@@ -28,7 +28,8 @@ if w["kind"] == "batch":
 else:
     nets = [backend._get_network(w["factory"](), nested_eval=backend._nested_eval)]
     batch = 1
-plan = executor.get_plan(nets[0], batch=batch, target_size=w["target"], trials=w["trials"])
+plan = executor.get_plan(nets[0], batch=batch, target_size=w["target"], trials=w["trials"],
+                         min_slices=w.get("min_slices", 1))
 sess = executor.Session(plan)
 sess.set_leaves(nets)
 sess.build_leaves()
