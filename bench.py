@@ -88,11 +88,18 @@ def workload(name: str):
                 th = j * (math.pi / 2) / (batch - 1)
                 return cases.fusion_link((math.cos(th), math.sin(th)), "bell")
             desc = "cfg5a: heralded fusion link (README.md:230-280), inflate(2), 1024 internal-state angles"
+            params = (np.arange(batch) * (math.pi / 2) / (batch - 1),)
+
+            def make_arr(th):                 # ONE diagram with array-valued amplitudes
+                return cases.fusion_link((np.cos(th), np.sin(th)), "bell")
         else:
             def make(j):
                 return cases.fusion_teleport_input(j / batch)
             desc = "cfg5b: fusion-II teleportation with classical feed-forward, 1024 input phases"
-        return dict(kind="batch", make=make, batch=batch, target=None, trials=8, desc=desc)
+            params = (np.arange(batch) / batch,)
+            make_arr = cases.fusion_teleport_input
+        return dict(kind="batch", make=make, make_arr=make_arr, params=params, batch=batch,
+                    target=None, trials=8, desc=desc)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -468,8 +475,8 @@ class Bench:
         world = self.world if sharded else 1
         backend = B200Backend(distributed=(sharded and self.world > 1), **backend_kw)
         if w["kind"] == "batch":
-            def call():
-                return backend.eval_batch(make=w["make"], count=w["batch"])
+            def call():                      # one compile with array-valued parameters
+                return backend.eval_params(w["make_arr"], *w["params"])
             units = w["batch"]
         else:
             def call():

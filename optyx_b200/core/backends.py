@@ -358,6 +358,9 @@ class B200Backend(AbstractBackend):
         control.py:164-191).  Cached by structure + values: a batch of evals that
         differ only outside the controlled box pays for it once."""
         from .. import executor
+        if net.batch is not None:
+            raise NotImplementedError("array-valued parameters inside a controlled box: "
+                                      "use eval_batch for this circuit")
         key = (net.structure_key(), complex(net.scalar),
                tuple(l.params.tobytes() for l in net.leaves if l.params is not None))
         cache = self.__dict__.setdefault("_nested_cache", {})
@@ -408,6 +411,48 @@ class B200Backend(AbstractBackend):
             if nets[j] is None:
                 nets[j] = self._get_network(make(j), nested_eval=self._nested_eval)
         return nets, first
+
+    def eval_params(self, make, *params) -> list:
+        """A batch of evals that differ only in numeric parameters, compiled ONCE:
+        ``make(*params)`` is called with the parameter ARRAYS (one entry per eval) and
+        builds a single diagram whose boxes carry array-valued phases / amplitudes /
+        scalars; the host compile then produces the whole ``[batch, P]`` matrix of leaf
+        values in one pass of numpy (the reference -- and ``eval_batch`` -- re-run
+        ``double()`` + ``to_tensor()`` per parameter set, channel.py:277-285,
+        diagram.py:301-375).  ``make`` must use numpy functions on its arguments
+        (``np.cos``, not ``math.cos``)."""
+        import dataclasses
+        from .. import executor
+        if self.target_size is not None or self.distributed:
+            raise ValueError("eval_params runs one unsliced plan per batch on one device")
+        d = make(*[np.asarray(p) for p in params])
+        net = self._get_network(d, nested_eval=self._nested_eval)
+        batch = net.batch
+        if batch is None:
+            return [self.eval(d)]
+        scal = np.asarray(net.scalar, dtype=np.complex128).reshape(-1)
+        scal = scal[None, :] if scal.size > 1 else scal
+        net = dataclasses.replace(net, scalar=1.0 + 0j, leaves=list(net.leaves) + [
+            nw.Leaf(nw.K_DENSE, (), (), 0, scal.reshape(1, -1) if scal.size > 1 else scal, "scalar")])
+        plan = executor.get_plan(net, dtype=self.dtype, batch=batch, trials=self.trials, seed=self.seed)
+        self.last_plan = plan
+        sess = self._session(plan)
+        sess.set_leaves_batched(net)
+        if len(plan.steps) > 8:
+            if sess.graph is None:
+                sess.capture(1.0 + 0j)
+            sess.replay()
+        else:
+            sess.build_leaves()
+            sess.contract(1.0 + 0j)
+        self.last_h2d_bytes = sess.h2d_bytes
+        dev = sess.take_out()
+        host = self._to_host(dev)
+        n, shape = net.n_dom, net.output_shape
+        state_type = StateType.AMP if d.is_pure else StateType.DM
+        return [EvalResult(ResultTensor(shape[:n], shape[n:], host[e]), output_types=d.cod,
+                           state_type=state_type, _device=dev[e] if self.keep_on_device else None)
+                for e in range(batch)]
 
     def eval_batch(self, diagrams=None, make=None, count: Optional[int] = None,
                    workers: Optional[int] = None) -> list:

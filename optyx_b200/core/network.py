@@ -90,7 +90,9 @@ def closed_form_values(kind: int, shape: Tuple[int, ...], ipar: int = 0) -> np.n
 class Leaf:
     """One dense leaf: ``kind`` + ``shape`` say what to build, ``inds`` how
     it is wired.  ``ipar`` is an integer parameter (one-hot position);
-    ``params`` complex values for VEC/DENSE kinds (C order)."""
+    ``params`` complex values for VEC/DENSE kinds (C order): shape ``(size,)``, or
+    ``(size, batch)`` when the diagram was built with ARRAY-valued parameters (one
+    compile for a whole batch of evals: column e belongs to eval e)."""
     kind: int
     shape: Tuple[int, ...]
     inds: Tuple[int, ...]
@@ -120,6 +122,30 @@ class Network:
     def output_shape(self) -> Tuple[int, ...]:
         return tuple(self.dims[i] for i in self.output_inds)
 
+    @property
+    def batch(self):
+        """Number of evals this network stands for (array-valued parameters), or None."""
+        sizes = {l.params.shape[1] for l in self.leaves
+                 if l.params is not None and l.params.ndim == 2}
+        if np.ndim(self.scalar) > 0 and np.size(self.scalar) > 1:
+            sizes.add(int(np.size(self.scalar)))
+        if not sizes:
+            return None
+        if len(sizes) > 1:
+            raise ValueError(f"array-valued parameters of different lengths: {sorted(sizes)}")
+        return sizes.pop()
+
+    def params_matrix(self, batch: int) -> np.ndarray:
+        """Host values of every VEC / DENSE leaf for ``batch`` evals: ``[batch, P]``."""
+        cols = []
+        for l in self.leaves:
+            if l.kind in (K_VEC, K_DENSE):
+                p = l.params
+                cols.append(np.broadcast_to(p[:, None], (l.size, batch)) if p.ndim == 1 else p)
+        if not cols:
+            return np.zeros((batch, 1), dtype=np.complex128)
+        return np.ascontiguousarray(np.concatenate(cols, axis=0).T)
+
     def structure_key(self) -> tuple:
         """Hashable description of everything except VEC/DENSE values and the
         scalar: two networks with equal keys share a contraction plan."""
@@ -146,7 +172,7 @@ class Network:
                     raise ValueError(f"leaf {leaf.name!r}: index {i} has extent {self.dims.get(i)}, "
                                      f"axis has {d}")
             if leaf.kind in (K_VEC, K_DENSE):
-                if leaf.params is None or leaf.params.size != leaf.size:
+                if leaf.params is None or leaf.params.shape[0] != leaf.size or leaf.params.ndim > 2:
                     raise ValueError(f"leaf {leaf.name!r}: host values missing or of the wrong size")
         for i in self.output_inds:
             if i not in self.dims:
@@ -203,11 +229,23 @@ class NetworkBuilder:
         if params is None and kind not in (K_VEC, K_DENSE) and len(shape) > MAX_LEAF_RANK:
             kind, params, ipar = K_DENSE, closed_form_values(kind, shape, ipar), 0
         if params is not None:
-            params = np.ascontiguousarray(params, dtype=np.complex128).reshape(-1)
+            params = np.ascontiguousarray(params, dtype=np.complex128)
+            size = math.prod(shape)
+            if params.size == size:
+                params = params.reshape(-1)
+            elif params.ndim >= 1 and params.size == size * params.shape[-1]:
+                # array-valued parameters: the last axis runs over the evals of a batch
+                params = params.reshape(size, params.shape[-1])
+            else:
+                raise ValueError(f"leaf {name!r}: {params.size} host values for {size} elements")
         self.leaves.append(Leaf(kind, shape, tuple(inds), ipar, params, name))
 
-    def mul_scalar(self, value: complex) -> None:
-        self.scalar = self.scalar * complex(value)
+    def mul_scalar(self, value) -> None:
+        if np.ndim(value) > 0 and np.size(value) > 1:
+            self.scalar = self.scalar * np.asarray(value, dtype=np.complex128).reshape(-1)
+        else:
+            self.scalar = self.scalar * complex(np.asarray(value).reshape(-1)[0]
+                                                if np.ndim(value) > 0 else value)
 
     # -- finish ---------------------------------------------------------------
     def finish(self, dom_inds: Sequence[int], cod_inds: Sequence[int]) -> Network:

@@ -43,8 +43,10 @@ class Spider(ZXBox):
     """zx.py:323-374"""
 
     def __init__(self, n_legs_in, n_legs_out, phase=0):
-        super().__init__(f"{type(self).__name__}({n_legs_in}, {n_legs_out}"
-                         f"{', ' + str(phase) if phase else ''})", n_legs_in, n_legs_out)
+        shown = "" if np.ndim(phase) == 0 and not phase else \
+            (f", {phase}" if np.ndim(phase) == 0 else f", <{np.size(phase)} phases>")
+        super().__init__(f"{type(self).__name__}({n_legs_in}, {n_legs_out}{shown})",
+                         n_legs_in, n_legs_out)
         self.phase = phase
         self.n_legs_in, self.n_legs_out = n_legs_in, n_legs_out
 
@@ -58,10 +60,11 @@ class Spider(ZXBox):
 def _emit_z(b, ins, n_out, amplitudes) -> List[int]:
     """``zw.ZBox(n, m, [1, a]).truncation([2] * n)`` (zx.py:382-397).  The
     vector is skipped when it is exactly [1, 1] (identity diagonal)."""
-    amps = np.asarray(amplitudes, dtype=complex)
+    # array-valued phases (one compile for a batch of evals): [2, batch]
+    amps = np.stack([np.asarray(x, dtype=complex) for x in np.broadcast_arrays(*amplitudes)])
     # a 1 -> 1 spider is a phase GATE: keep its vector even at phase 0 so that a
     # batch of evals over the phase has one network structure (eval_batch)
-    trivial = amps[0] == 1 and amps[1] == 1 and not (len(ins) == 1 and n_out == 1)
+    trivial = amps.ndim == 1 and amps[0] == 1 and amps[1] == 1 and not (len(ins) == 1 and n_out == 1)
     return diagram.emit_spider(b, ins, [2] * len(ins), n_out, 2,
                                amplitudes=None if trivial else amps)
 

@@ -6,6 +6,7 @@ PyTorch is used only for device memory, streams, CUDA graphs and (in
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -201,6 +202,30 @@ class Session:
         ph[0] = p0
         for e in range(1, plan.batch):
             ph[e] = params_vector(nets[e])
+        self.params_dev.copy_(self.params_host, non_blocking=True)
+        self.h2d_bytes = int(self.params_host.numel() * 16 + self.desc_dev.numel())
+        if self._params_copied is None:
+            self._params_copied = torch.cuda.Event()
+        self._params_copied.record()
+
+    def set_leaves_batched(self, net: Network) -> None:
+        """The same for ONE network whose parameters are array-valued (``net.batch``
+        evals compiled in one pass): the parameter matrix is assembled with numpy, no
+        per-eval Python work."""
+        torch, plan = self.torch, self.plan
+        batch = net.batch or 1
+        assert batch == plan.batch, (batch, plan.batch)
+        pm = net.params_matrix(batch)
+        if self.desc_dev is None:
+            flat = [l if l.params is None or l.params.ndim == 1 else
+                    dataclasses.replace(l, params=l.params[:, 0]) for l in net.leaves]
+            table, p0 = leaf_table(dataclasses.replace(net, leaves=flat), plan)
+            assert len(p0) == pm.shape[1] or (pm.shape[1] == 1 and len(p0) == 1)
+            self.set_leaves([dataclasses.replace(net, leaves=flat)] * 1 if batch == 1 else
+                            [dataclasses.replace(net, leaves=flat)] * batch)
+        if self._params_copied is not None:
+            self._params_copied.synchronize()
+        self.params_host.numpy()[:] = pm
         self.params_dev.copy_(self.params_host, non_blocking=True)
         self.h2d_bytes = int(self.params_host.numel() * 16 + self.desc_dev.numel())
         if self._params_copied is None:

@@ -86,3 +86,38 @@ def statevector_clifford_t(n, depth, seed=0):
             sub = psi[tuple(idx)]
             psi[tuple(idx)] = np.flip(sub, axis=t - 1 if t > c else t)
     return psi[(0,) * n]
+
+
+def statevector_clifford_t_torch(n, depth, seed=0, device="cuda"):
+    """The same independent gate-by-gate statevector simulation for the BENCH-size
+    circuit (30 qubits: a 2^30-entry complex128 state, 17 GB) with plain torch ops on
+    the GPU -- a TEST-ONLY checker: no kernel, planner or compiler of optyx_b200 is
+    involved.  Qubit 0 = most significant axis; returns <0..0|C|0..0> as a Python complex."""
+    import math
+    import torch
+    rnd = random.Random(seed)
+    psi = torch.zeros(1 << n, dtype=torch.complex128, device=device)
+    psi[0] = 1.0
+    r = 1.0 / math.sqrt(2.0)
+    phase = {"S": 1j, "T": complex(math.cos(math.pi / 4), math.sin(math.pi / 4))}
+    for layer in range(depth):
+        for q in range(n):
+            g = rnd.choice("HST")
+            v = psi.view(1 << q, 2, 1 << (n - q - 1))
+            if g == "H":
+                a = v[:, 0, :].clone()
+                b = v[:, 1, :]
+                v[:, 0, :] = (a + b) * r
+                v[:, 1, :] = (a - b) * r          # b is read before it is overwritten
+                del a
+            else:
+                v[:, 1, :] *= phase[g]
+        start = layer % 2
+        for p in range((n - start) // 2):
+            c = start + 2 * p                     # control c, target c + 1: swap |10> and |11>
+            v = psi.view(1 << c, 2, 2, 1 << (n - c - 2))
+            tmp = v[:, 1, 0, :].clone()
+            v[:, 1, 0, :] = v[:, 1, 1, :]
+            v[:, 1, 1, :] = tmp
+            del tmp
+    return complex(psi[0].item())

@@ -554,3 +554,27 @@ def test_permanent_histogram_with_discards_before_later_boxes(name):
     total = sum(want.values())
     keys = set(want) | set(got)
     assert max(abs(got.get(k, 0.0) - want.get(k, 0.0) / total) for k in keys) <= 1e-10
+
+
+def test_eval_params_matches_per_diagram_evals_and_oracle():
+    """One compile with array-valued parameters (eval_params) == eval_batch == oracle."""
+    import math
+    from cases import fusion_link, fusion_teleport_input
+    backend = B200Backend()
+    phis = np.arange(24) / 24
+    got = backend.eval_params(fusion_teleport_input, phis)
+    ref = backend.eval_batch(make=lambda j: fusion_teleport_input(phis[j]), count=24, workers=1)
+    assert len(got) == 24
+    for j in (0, 5, 23):
+        want = oracle_eval(fusion_teleport_input(phis[j]))
+        assert _close(got[j].tensor.array, want, TOL128)
+    for a, b in zip(got, ref):
+        assert _close(a.tensor.array, b.tensor.array, 1e-12)
+    th = np.linspace(0, math.pi / 2, 16)
+    got = backend.eval_params(lambda t: fusion_link((np.cos(t), np.sin(t)), "bell"), th)
+    for j in (0, 7, 15):
+        want = oracle_eval(fusion_link((math.cos(th[j]), math.sin(th[j])), "bell"))
+        assert _close(got[j].tensor.array, want, TOL128)
+    # second call: cached session + captured graph, new parameters
+    got2 = backend.eval_params(fusion_teleport_input, phis[::-1].copy())
+    assert _close(got2[0].tensor.array, oracle_eval(fusion_teleport_input(phis[-1])), TOL128)

@@ -414,3 +414,27 @@ def test_min_slices_keeps_slicing_with_the_cheapest_indices():
     assert not (set(more.sliced) & output)
     plan = planner.plan_network(net, min_slices=4)
     assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)
+
+
+def test_array_valued_parameters_compile_a_whole_batch_in_one_pass():
+    """eval_params: a diagram built with ARRAY phases / amplitudes compiles once into
+    the [batch, P] matrix of leaf values -- identical to compiling every eval on its own."""
+    import math
+    import cases
+    from optyx_b200.executor import params_vector
+    th = np.linspace(0.0, math.pi / 2, 6)
+    both = [
+        (lambda: cases.fusion_link((np.cos(th), np.sin(th)), "bell"),
+         lambda j: cases.fusion_link((math.cos(th[j]), math.sin(th[j])), "bell")),
+        (lambda: cases.fusion_teleport_input(np.arange(6) / 6), lambda j: cases.fusion_teleport_input(j / 6)),
+    ]
+    for batched, single in both:
+        net = cases.compile_channel(batched())
+        assert net.batch == 6
+        pm = net.params_matrix(6)
+        for j in range(6):
+            one = cases.compile_channel(single(j))
+            assert one.structure_key() == net.structure_key() and one.batch is None
+            assert np.abs(pm[j] - params_vector(one)).max() <= 1e-15
+            sc = net.scalar[j] if np.ndim(net.scalar) else net.scalar
+            assert abs(sc - one.scalar) <= 1e-15
