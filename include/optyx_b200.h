@@ -291,6 +291,24 @@ int b2_permanent_histogram(const void* v_dev, int32_t n, int32_t m,
                            int64_t n_configs, int32_t n_bins, double* hist_dev,
                            void* stream);
 
+/* (7) compressed (approximate) contraction, SURVEY.md 8(f) row f4: what quimb's
+ * contract_compressed does for the reference when QuimbBackend holds a
+ * HyperCompressedOptimizer (backends.py:516-545).  The reductions over everything but the
+ * bond (Gram matrices G_A = A^H A, G_B = B B^H) and the application of the projectors are
+ * ordinary pairwise contractions (entry points (2a) / (2b)); b2_conj provides conj(A);
+ * b2_bond_compress is the small dense part, one CTA per bond: from the two bond x bond
+ * Gram matrices (row-major complex128) it writes the oblique projectors P_A [bond][bond]
+ * (columns 0..k-1 valid) and P_B [bond][bond] (rows 0..k-1 valid) with
+ * A P_A P_B B = the rank-k truncation of A B, k = number of singular values of the bond
+ * matrix that exceed cutoff * largest, at most max_bond (<= 0: no cap), at least 1;
+ * *k_dev receives k, sv_dev[0..k) the kept singular values in descending order.
+ * Factorisations: one-sided Jacobi (round-robin pair order, one warp per column pair). */
+int b2_conj(int64_t n, const void* x_dev, void* y_dev, int32_t dtype, void* stream);
+int64_t b2_bond_compress_scratch_bytes(int32_t bond);
+int b2_bond_compress(const void* ga_dev, const void* gb_dev, int32_t bond, int32_t max_bond,
+                     double cutoff, void* pa_dev, void* pb_dev, int32_t* k_dev, double* sv_dev,
+                     void* scratch_dev, void* stream);
+
 /* (6) host side of the planner (CPU only, no kernels): the randomised greedy pair-order
  * search and the cost of a pair order under slicing, for networks of thousands of
  * tensors (the reference hands this to cotengra, backends.py:436-455).  Tensors are index

@@ -24,8 +24,7 @@
 
 namespace b2 {
 
-constexpr int SP_THREADS = 256;
-constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_MAX_THREADS = 1024;               // blockDim is chosen per launch (256 .. 1024)
 constexpr int SP_SMEM_MAX_BYTES = 226 * 1024;
 constexpr int SP_HDR = 8, SP_COPY_WORDS = 8, SP_STEP_WORDS = 8;
 
@@ -50,6 +49,7 @@ template <typename T, typename C>
 __device__ __forceinline__ void sp_step(const uint32_t* __restrict__ st, C* __restrict__ S,
                                         const uint2* __restrict__ ot,
                                         const uint32_t* __restrict__ rt, int tid) {
+    const int SP_THREADS = (int)blockDim.x;
     const int n_out = (int)st[0], n_red = (int)st[1], rs = (int)st[5];
     const C* A = S + st[2];
     const C* B = S + st[3];
@@ -113,13 +113,14 @@ __device__ __forceinline__ void sp_step(const uint32_t* __restrict__ st, C* __re
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SP_THREADS)
+__global__ void __launch_bounds__(SP_MAX_THREADS)
 small_program_kernel(const __grid_constant__ b2_small_program P) {
     using C = typename cplx<T>::type;
     extern __shared__ __align__(16) unsigned char sp_raw[];
     uint32_t* H = reinterpret_cast<uint32_t*>(sp_raw);          // the task's blob
     __shared__ int s_item;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int SP_THREADS = (int)blockDim.x, SP_WARPS = SP_THREADS >> 5;
     int* sync = P.sync_dev;
     int* flags = sync + 4;
     const int n_tasks = P.n_tasks;
@@ -240,19 +241,25 @@ extern "C" int b2_run_small_program(const b2_small_program* prog, int32_t dtype,
         }
         mark_done(attr_done);
     }
-    int occ = 0;
-    cudaError_t e = dtype == B2_C128
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_program_kernel<double>, SP_THREADS, smem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_program_kernel<float>, SP_THREADS, smem);
-    if (e != cudaSuccess || occ < 1) occ = 1;
+    // threads per CTA: shared memory decides how many CTAs fit an SM; with few CTAs
+    // per SM the CTA itself must bring the warps that hide the latencies (>= 32 per SM)
+    int threads = 256, occ = 0;
+    for (;;) {
+        cudaError_t e = dtype == B2_C128
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_program_kernel<double>, threads, smem)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_program_kernel<float>, threads, smem);
+        if (e != cudaSuccess || occ < 1) occ = 1;
+        if (occ * threads >= 1024 || threads >= SP_MAX_THREADS) break;
+        threads *= 2;
+    }
     if (occ > 8) occ = 8;
     long long grid = (long long)P.n_tasks * P.batch;
     if (grid > (long long)sms * occ) grid = (long long)sms * occ;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == B2_C128)
-        small_program_kernel<double><<<(unsigned)grid, SP_THREADS, smem, s>>>(P);
+        small_program_kernel<double><<<(unsigned)grid, threads, smem, s>>>(P);
     else
-        small_program_kernel<float><<<(unsigned)grid, SP_THREADS, smem, s>>>(P);
+        small_program_kernel<float><<<(unsigned)grid, threads, smem, s>>>(P);
     set_last_kernel("small_program");
     return check_launch("b2_run_small_program");
 }

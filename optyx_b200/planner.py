@@ -682,7 +682,8 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
 # --------------------------------------------------------------------------
 # the small-step program (csrc/contract_small.cu)
 # --------------------------------------------------------------------------
-SMALL_ELEMS = 4096                  # largest operand / result of a step the interpreter takes
+SMALL_ELEMS = 8192                  # largest operand / result of a step the interpreter takes
+                                    # (128 KB of complex128; offsets stay below 2^16)
 SMALL_WORK = 1 << 18                # ... and its multiply-adds
 SMALL_SCRATCH_ELEMS = 11264         # scratch budget of one task (complex elements: 176 KB c128;
                                     # the task blob -- records + staged tables -- rides beside it)
@@ -737,8 +738,29 @@ def _mode_offsets(modes: List[List[int]]):
     return oa, ob, oc
 
 
+class _ScratchOverflow(Exception):
+    pass
+
+
 def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
                          ws_top: int) -> Tuple[Optional[SmallProgram], int]:
+    """``_build_small_program_once`` with the scratch budget lowered until the real
+    shared-memory layout of every task (first-fit allocation fragments) fits an SM."""
+    budget = SMALL_SCRATCH_ELEMS
+    saved = [(st.c.offset, st.grouped) for st in steps]
+    while True:
+        try:
+            return _build_small_program_once(steps, batch, arena_elems, ws_top, budget)
+        except _ScratchOverflow:
+            for st, (off, grouped) in zip(steps, saved):
+                st.c.offset, st.grouped = off, grouped
+            budget = int(budget * 0.8)
+            if budget < 1024:
+                return None, ws_top
+
+
+def _build_small_program_once(steps: List[Step], batch: int, arena_elems: int, ws_top: int,
+                              budget: int) -> Tuple[Optional[SmallProgram], int]:
     """Pick the EARLY tiny steps (operands are leaves or other early tiny steps), cut
     them into tasks, lay every task out in shared memory and tabulate the operand
     offsets of every output / reduction index (plan-time constants, shared by all
@@ -754,7 +776,8 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
     for k, st in enumerate(steps):
         if st.final or st.per_slice or st.a_slice or st.b_slice or st.small_modes is None:
             continue
-        if max(st.a.size, st.b.size, st.c.size) > SMALL_ELEMS:
+        if max(st.a.size, st.b.size, st.c.size) > SMALL_ELEMS or \
+                st.a.size + st.b.size + st.c.size > budget:     # all three sit in the scratch
             continue
         outm, redm = st.small_modes
         n_out = int(np.prod([m[0] for m in outm], dtype=np.int64)) if outm else 1
@@ -805,7 +828,7 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
         if order:
             t0 = order[0]
             if len(members[t0]) < max_steps and \
-                    resident[t0] + live[t0] + st.c.size + leaf_need(st) <= SMALL_SCRATCH_ELEMS:
+                    resident[t0] + live[t0] + st.c.size + leaf_need(st) <= budget:
                 home = t0
         if home is None:
             home = nxt_task
@@ -817,7 +840,7 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
                 continue
             fits = max(peak[t] + resident[home] + live[home],
                        resident[t] + live[t] + resident[home] + live[home] + st.c.size) \
-                <= SMALL_SCRATCH_ELEMS
+                <= budget
             if len(members[t]) <= merge_steps and len(members[home]) + len(members[t]) < max_steps \
                     and fits:
                 for q in members[t]:
@@ -955,8 +978,8 @@ def _build_small_program(steps: List[Step], batch: int, arena_elems: int,
         blobs.append(blob)
         blob_off.append(blob_off[-1] + len(blob))
         task_scratch.append(int(alloc.top))
-        assert ((len(blob) * 4 + 15) // 16) * 16 + alloc.top * 16 <= 226 * 1024, \
-            "small-step task exceeds the shared memory of an SM"
+        if ((len(blob) * 4 + 15) // 16) * 16 + alloc.top * 16 > 226 * 1024:
+            raise _ScratchOverflow()
     return SmallProgram(
         np.concatenate(blobs), np.array(blob_off, dtype=np.int32),
         np.concatenate(out_rows).reshape(-1, 2) if out_rows else np.zeros((1, 2), dtype=np.uint32),
@@ -1067,6 +1090,13 @@ def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int 
     if len(inputs) >= 2:
         info = find_path(inputs, net.dims, output, trials=trials, seed=seed,
                          target_size=target_size, min_slices=min_slices)
+        if batch > 1 and target_size is None and min_slices <= 1 and info.peak > SMALL_ELEMS:
+            # a batch of small evals: a tree whose every intermediate fits the small-step
+            # interpreter runs each eval entirely out of shared memory (one CTA per eval,
+            # no HBM round trip per step) -- worth some extra multiply-adds
+            narrow = find_path(inputs, net.dims, output, trials=trials, seed=seed, minimize="size")
+            if narrow.peak <= SMALL_ELEMS and narrow.macs <= 4.0 * info.macs:
+                info = narrow
     else:
         info = PathInfo([], (), 0.0, 0.0, 1, [])
     return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)

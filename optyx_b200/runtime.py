@@ -22,7 +22,7 @@ EXPORTS = [
     "b2_contract_direct", "b2_contract_gemm", "b2_run_small_program", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
     "b2_fp64_peak_kernel", "b2_run_plan", "b2_workspace_bytes", "b2_build_leaves_indexed",
-    "b2_plan_greedy", "b2_plan_cost",
+    "b2_plan_greedy", "b2_plan_cost", "b2_conj", "b2_bond_compress", "b2_bond_compress_scratch_bytes",
 ]
 
 
@@ -138,6 +138,9 @@ def load():
                                 C.POINTER(SmallProgramArgs), vp, vp, vp, i64, i32, i64, i64,
                                 dbl, dbl, i32, vp, C.POINTER(i32)]
     lib.b2_workspace_bytes.argtypes = [C.POINTER(PlanStep), i32, i32]
+    lib.b2_conj.argtypes = [i64, vp, vp, i32, vp]
+    lib.b2_bond_compress.argtypes = [vp, vp, i32, i32, dbl, vp, vp, vp, vp, vp, vp]
+    lib.b2_bond_compress_scratch_bytes.argtypes = [i32]
     lib.b2_plan_greedy.argtypes = [i32, vp, vp, i32, vp, vp, C.c_uint64, dbl, dbl, vp]
     lib.b2_plan_cost.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.b2_axpy.argtypes = [i64, dbl, dbl, vp, vp, i32, vp]
@@ -151,9 +154,10 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("b2_abi_version", "b2_last_error", "b2_last_kernel", "b2_device_sms",
-                        "b2_workspace_bytes"):
+                        "b2_workspace_bytes", "b2_bond_compress_scratch_bytes"):
             fn.restype = C.c_int
     lib.b2_workspace_bytes.restype = C.c_int64
+    lib.b2_bond_compress_scratch_bytes.restype = C.c_int64
     if lib.b2_abi_version() != 1:
         raise B2Error("liboptyx_b200.so ABI version mismatch")
     _lib = lib
