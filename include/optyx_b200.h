@@ -58,7 +58,8 @@ typedef struct {
     int32_t ndim;
     int32_t dims[B2_MAX_LEAF_RANK];
     int32_t ipar;
-    int32_t reserved;
+    int32_t shared;     /* VEC / DENSE: 1 = poff indexes the SHARED values (same for every
+                           eval of a batch), 0 = the per-eval params buffer               */
     int64_t offset;
     int64_t nelem;
     int64_t poff;
@@ -115,12 +116,13 @@ int b2_build_leaves(const b2_leaf_desc* desc_dev, int32_t n_leaves,
 
 /* the same with a plan-time index: block_leaf_dev[b] = leaf holding arena element
  * 256 * b (one trailing entry: the leaf holding the last element), so that a thread
- * searches only the leaves of its own 256-element block                              */
+ * searches only the leaves of its own 256-element block; shared_params_dev holds the
+ * host values of the leaves flagged `shared` (one copy for the whole batch)           */
 int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_leaves,
                             const int32_t* block_leaf_dev, int64_t arena_elems,
                             const void* params_dev, int64_t params_stride,
-                            void* arena_dev, int64_t arena_stride, int32_t batch,
-                            int32_t dtype, void* stream);
+                            const void* shared_params_dev, void* arena_dev,
+                            int64_t arena_stride, int32_t batch, int32_t dtype, void* stream);
 
 /* (2a) thin / bandwidth-bound pairs: one thread per output element.
  * accumulate != 0: C += alpha * (...)                                        */

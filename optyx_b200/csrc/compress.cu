@@ -182,7 +182,13 @@ bond_compress_kernel(const double2* __restrict__ GA, const double2* __restrict__
         const int i = idx % n, j = idx / n;
         if (lamB[j] < 0.0) continue;
         const int rank = (int)lamB[j];
-        const double s = sv[j], rs = 1.0 / sqrt(s);
+        const double s = sv[j];
+        if (!(s > 0.0)) {                                  // a zero bond matrix: zero projectors
+            PA[(size_t)i * n + rank] = make_double2(0.0, 0.0);
+            PB[(size_t)rank * n + i] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const double rs = 1.0 / sqrt(s);
         double2 pa = make_double2(0.0, 0.0), pb = make_double2(0.0, 0.0);
         for (int l = 0; l < n; ++l) {
             cfma(pa, XB[(size_t)l * n + i], W[(size_t)j * n + l]);

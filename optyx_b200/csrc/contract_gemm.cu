@@ -17,6 +17,7 @@
 // CTA tile 64 x 64 x 8 (complex), 4 warps as 2 x 2, warp tile 32 x 32:
 // per k4 step a warp issues 64 DMMAs for 16 LDS.128 -> the math pipe is the
 // only busy unit.  Shared pitch 66 (x16 B) makes fragment loads conflict-free.
+#include <stdlib.h>
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -224,6 +225,111 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     }
 }
 
+// ---- few outputs, very long reduction with many modes (the last pair of a sliced
+// amplitude network: <psi_left | psi_right> over 2^20 index values spread over 20
+// binary modes).  A tile of the DMMA kernel would be 1/4096 full; here every CTA takes a
+// contiguous range of the flat reduction index, decodes it once (mixed radix) and then
+// walks it with an odometer, one complex FMA per element; block-reduce, one atomic per
+// output and CTA.  C must hold zeros (or the running sum when accumulating).
+constexpr int DOT_THREADS = 256;
+constexpr int DOT_MAX_OUT = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(DOT_THREADS)
+contract_dot_kernel(const __grid_constant__ b2_gemm_modes g, long long n_out, long long K,
+                    const typename cplx<T>::type* __restrict__ A,
+                    const typename cplx<T>::type* __restrict__ B,
+                    typename cplx<T>::type* __restrict__ Cout, T alpha_re, T alpha_im) {
+    using C = typename cplx<T>::type;
+    __shared__ double red_re[DOT_THREADS / 32], red_im[DOT_THREADS / 32];
+    const int f_k = g.n_batch + g.n_m + g.n_n, n_free = f_k;
+    const long long per_cta = (K + gridDim.x - 1) / gridDim.x;
+    const long long k0 = (long long)blockIdx.x * per_cta;
+    const long long k1 = k0 + per_cta < K ? k0 + per_cta : K;
+    for (long long o = 0; o < n_out; ++o) {
+        long long oa = 0, ob = 0, oc = 0, rem = o;
+        for (int m = 0; m < n_free; ++m) {               // mode 0 of every group is fastest
+            const int d = g.dim[m];
+            const long long i = rem % d;
+            rem /= d;
+            oa += i * g.sa[m]; ob += i * g.sb[m]; oc += i * g.sc[m];
+        }
+        double acc_re = 0.0, acc_im = 0.0;
+        // thread t takes k0 + t, k0 + t + 256, ...: decode, then step the odometer by 256
+        long long k = k0 + threadIdx.x;
+        if (k < k1) {
+            int idx[B2_MAX_MODES];
+            long long ra = 0, rb = 0, r = k;
+            for (int m = 0; m < g.n_k; ++m) {
+                const int d = g.dim[f_k + m];
+                idx[m] = (int)(r % d);
+                r /= d;
+                ra += idx[m] * g.sa[f_k + m]; rb += idx[m] * g.sb[f_k + m];
+            }
+            for (; k < k1; k += DOT_THREADS) {
+                const C x = A[oa + ra], y = B[ob + rb];
+                acc_re += (double)x.x * (double)y.x - (double)x.y * (double)y.y;
+                acc_im += (double)x.x * (double)y.y + (double)x.y * (double)y.x;
+                // advance the mixed-radix counter by DOT_THREADS
+                long long carry = DOT_THREADS;
+                for (int m = 0; m < g.n_k && carry; ++m) {
+                    const int d = g.dim[f_k + m];
+                    const long long v = idx[m] + carry;
+                    const int nv = (int)(v % d);
+                    carry = v / d;
+                    ra += (long long)(nv - idx[m]) * g.sa[f_k + m];
+                    rb += (long long)(nv - idx[m]) * g.sb[f_k + m];
+                    idx[m] = nv;
+                }
+            }
+        }
+        for (int m = 16; m > 0; m >>= 1) {
+            acc_re += __shfl_xor_sync(0xffffffffu, acc_re, m);
+            acc_im += __shfl_xor_sync(0xffffffffu, acc_im, m);
+        }
+        if ((threadIdx.x & 31) == 0) { red_re[threadIdx.x >> 5] = acc_re; red_im[threadIdx.x >> 5] = acc_im; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sr = 0.0, si = 0.0;
+            for (int w = 0; w < DOT_THREADS / 32; ++w) { sr += red_re[w]; si += red_im[w]; }
+            C* dst = Cout + oc;
+            atomicAdd(&dst->x, (T)(alpha_re * sr - alpha_im * si));
+            atomicAdd(&dst->y, (T)(alpha_re * si + alpha_im * sr));
+        }
+        __syncthreads();
+    }
+}
+
+// returns handled = true when the pair was a tiny-output / long-reduction one
+static int launch_dot(const b2_gemm_modes& g, const void* a, const void* b, void* c, double ar,
+                      double ai, int accumulate, int dtype, cudaStream_t s, bool& handled) {
+    handled = false;
+    const int f_k = g.n_batch + g.n_m + g.n_n;
+    long long n_out = 1, K = 1, span = 0;
+    for (int i = 0; i < f_k; ++i) { n_out *= g.dim[i]; span += (long long)(g.dim[i] - 1) * g.sc[i]; }
+    for (int i = 0; i < g.n_k; ++i) K *= g.dim[f_k + i];
+    if (n_out > DOT_MAX_OUT || K < 4096) return 0;
+    const int sms = num_sms();
+    if (sms <= 0) return 1;
+    const size_t esize = dtype == B2_C128 ? 16 : 8;
+    if (!accumulate) {                                   // the CTAs add into C
+        if (span + 1 != n_out) return 0;                 // C is not one dense block
+        cudaError_t e = cudaMemsetAsync(c, 0, (size_t)n_out * esize, s);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(dot): memset: %s", cudaGetErrorString(e)); return 1; }
+    }
+    long long blocks = (K + 4 * DOT_THREADS - 1) / (4 * DOT_THREADS);
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    if (dtype == B2_C128)
+        contract_dot_kernel<double><<<(unsigned)blocks, DOT_THREADS, 0, s>>>(
+            g, n_out, K, (const double2*)a, (const double2*)b, (double2*)c, ar, ai);
+    else
+        contract_dot_kernel<float><<<(unsigned)blocks, DOT_THREADS, 0, s>>>(
+            g, n_out, K, (const float2*)a, (const float2*)b, (float2*)c, (float)ar, (float)ai);
+    handled = true;
+    set_last_kernel("dot");
+    return check_launch("b2_contract_gemm(dot)");
+}
+
 int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, double ar,
                  double ai, int accumulate, cudaStream_t s, bool& handled);
 int launch_gemm_c64(const b2_gemm_modes& g, const void* a_dev, const void* b_dev, void* c_dev,
@@ -254,6 +360,12 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         set_error("b2_contract_gemm: reduction extent %lld too large (slice the network)", k_total);
         return 1;
     }
+    {   // a handful of outputs over a very long reduction: neither tensor-core tiling fits
+        bool handled = false;
+        int st = launch_dot(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate, dtype,
+                            (cudaStream_t)stream, handled);
+        if (st != 0 || handled) return st;
+    }
     if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
         return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
                                (cudaStream_t)stream);
@@ -262,7 +374,9 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     for (int i = 0; i < g.n_batch; ++i) b_total *= g.dim[i];
     const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
                                  2ll * num_sms() && k_total >= 256;
-    if ((k_total <= 32 || n_total < 64) && !underfilled) {
+    // (B2_CTILE_KMAX: experiment knob, reductions up to this length take the ctile kernel)
+    static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 32;
+    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
         // classic 64x64 tiling below (4x4 register blocking per warp).

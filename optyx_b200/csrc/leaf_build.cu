@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256)
 leaf_build_kernel(const b2_leaf_desc* __restrict__ descs, int n_leaves,
                   const int* __restrict__ block_leaf, long long arena_elems,
                   const double2* __restrict__ params, long long params_stride,
+                  const double2* __restrict__ shared_params,
                   typename cplx<T>::type* __restrict__ arena, long long arena_stride,
                   int batch, int ev_per) {
     using C = typename cplx<T>::type;
@@ -109,10 +110,16 @@ leaf_build_kernel(const b2_leaf_desc* __restrict__ descs, int n_leaves,
         v = leaf_value(d, idx, from_params);
     }
     const long long poff = from_params ? __ldg(&dref.poff) + (long long)local : 0;
+    // host values that are the same for every eval of the batch live in one shared vector
+    const bool shared_vals = from_params && __ldg(&dref.shared) != 0;
     for (int g = blockIdx.y; (long long)g * ev_per < batch; g += gridDim.y) {
         const int ev0 = g * ev_per, ev1 = min(batch, ev0 + ev_per);
         C* out = arena + (long long)ev0 * arena_stride + e;
-        if (from_params) {
+        if (shared_vals) {
+            const double2 pv = shared_params[poff];
+            C val; val.x = (T)pv.x; val.y = (T)pv.y;
+            for (int ev = ev0; ev < ev1; ++ev) { *out = val; out += arena_stride; }
+        } else if (from_params) {
             const double2* par = params + (long long)ev0 * params_stride + poff;
             for (int ev = ev0; ev < ev1; ++ev) {
                 const double2 pv = *par;
@@ -135,8 +142,9 @@ leaf_build_kernel(const b2_leaf_desc* __restrict__ descs, int n_leaves,
 extern "C" int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_leaves,
                                        const int32_t* block_leaf_dev, int64_t arena_elems,
                                        const void* params_dev, int64_t params_stride,
-                                       void* arena_dev, int64_t arena_stride, int32_t batch,
-                                       int32_t dtype, void* stream) {
+                                       const void* shared_params_dev, void* arena_dev,
+                                       int64_t arena_stride, int32_t batch, int32_t dtype,
+                                       void* stream) {
     if (n_leaves <= 0 || arena_elems <= 0 || batch <= 0) return 0;
     if (!desc_dev || !arena_dev) { b2::set_error("b2_build_leaves: null pointer"); return 1; }
     int sms = b2::num_sms();
@@ -155,11 +163,13 @@ extern "C" int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_l
     if (dtype == B2_C128)
         b2::leaf_build_kernel<double><<<grid, 256, 0, s>>>(
             desc_dev, n_leaves, block_leaf_dev, arena_elems, (const double2*)params_dev,
-            params_stride, (double2*)arena_dev, arena_stride, batch, (int)ev_per);
+            params_stride, (const double2*)shared_params_dev, (double2*)arena_dev, arena_stride,
+            batch, (int)ev_per);
     else if (dtype == B2_C64)
         b2::leaf_build_kernel<float><<<grid, 256, 0, s>>>(
             desc_dev, n_leaves, block_leaf_dev, arena_elems, (const double2*)params_dev,
-            params_stride, (float2*)arena_dev, arena_stride, batch, (int)ev_per);
+            params_stride, (const double2*)shared_params_dev, (float2*)arena_dev, arena_stride,
+            batch, (int)ev_per);
     else { b2::set_error("b2_build_leaves: bad dtype %d", dtype); return 1; }
     return b2::check_launch("b2_build_leaves");
 }
@@ -170,5 +180,6 @@ extern "C" int b2_build_leaves(const b2_leaf_desc* desc_dev, int32_t n_leaves,
                                int64_t arena_stride, int32_t batch, int32_t dtype,
                                void* stream) {
     return b2_build_leaves_indexed(desc_dev, n_leaves, nullptr, arena_elems, params_dev,
-                                   params_stride, arena_dev, arena_stride, batch, dtype, stream);
+                                   params_stride, nullptr, arena_dev, arena_stride, batch, dtype,
+                                   stream);
 }

@@ -29,12 +29,16 @@ def require_cuda():
     return torch
 
 
-def leaf_table(net: Network, plan: Plan) -> Tuple[np.ndarray, np.ndarray]:
-    """Descriptor table (+ the unit leaf) and the flat params vector of one eval."""
+def leaf_table(net: Network, plan: Plan, varying=None) -> Tuple[np.ndarray, np.ndarray]:
+    """Descriptor table (+ the unit leaf) and the flat params vector of one eval.
+    ``varying``: indices of the host-valued leaves whose values differ per eval of a batch
+    (they index the per-eval params buffer); the others are flagged ``shared`` and index
+    one vector for the whole batch.  ``None``: every host-valued leaf is per-eval, and the
+    returned vector holds them all."""
     n = len(net.leaves)
     table = np.zeros(n + 1, dtype=rt.LEAF_DESC_DTYPE)
     params: List[np.ndarray] = []
-    poff = 0
+    poff = soff = 0
     for k, leaf in enumerate(net.leaves):
         row = table[k]
         row["kind"], row["ipar"] = leaf.kind, leaf.ipar
@@ -44,9 +48,14 @@ def leaf_table(net: Network, plan: Plan) -> Tuple[np.ndarray, np.ndarray]:
             # rank (the planner alone knows their shape and indices)
             row["ndim"] = 1
             row["dims"][0] = min(leaf.size, 2 ** 31 - 1)
-            row["poff"] = poff
-            params.append(np.asarray(leaf.params, dtype=np.complex128).reshape(-1))
-            poff += leaf.size
+            if varying is None or k in varying:
+                row["poff"] = poff
+                if varying is None:
+                    params.append(np.asarray(leaf.params, dtype=np.complex128).reshape(-1))
+                poff += leaf.size
+            else:
+                row["shared"], row["poff"] = 1, soff
+                soff += leaf.size
         else:
             row["ndim"] = len(leaf.shape)
             row["dims"][:len(leaf.shape)] = leaf.shape
@@ -89,6 +98,7 @@ class Session:
         self.desc_dev = None
         self.params_dev = None
         self.params_host = None
+        self.shared_dev = None
         self._params_copied = None
         self.n_leaves = 0
         self.params_stride = 0
@@ -182,14 +192,11 @@ class Session:
         plan = self.plan
         assert len(nets) == plan.batch
         table, p0 = leaf_table(nets[0], plan)
-        if self.desc_dev is None:
-            self.n_leaves = len(table)
-            self.desc_dev = torch.from_numpy(table.view(np.uint8).copy()).to(self.device)
-            # leaf holding the first element of every 256-element block of the arena
-            firsts = np.arange(0, plan.arena_elems, 256, dtype=np.int64)
-            firsts = np.append(firsts, plan.arena_elems - 1)
-            block_leaf = np.searchsorted(table["offset"], firsts, side="right") - 1
-            self.block_leaf_dev = torch.from_numpy(block_leaf.astype(np.int32)).to(self.device)
+        if self.desc_dev is None or getattr(self, "_varying", None) is not None:
+            self._upload_table(table)
+            self._varying = None
+            self.shared_dev = None
+            self.graph = None            # a captured graph holds the old buffers
             self.params_stride = len(p0)
             self.params_host = torch.empty((plan.batch, len(p0)), dtype=torch.complex128,
                                            pin_memory=True)
@@ -210,35 +217,66 @@ class Session:
 
     def set_leaves_batched(self, net: Network) -> None:
         """The same for ONE network whose parameters are array-valued (``net.batch``
-        evals compiled in one pass): the parameter matrix is assembled with numpy, no
-        per-eval Python work."""
+        evals compiled in one pass).  Only the leaves that really vary get a per-eval
+        column block ``[batch, P_var]``; every other host value is uploaded once, in one
+        vector the array-build kernel shares between the evals."""
         torch, plan = self.torch, self.plan
         batch = net.batch or 1
         assert batch == plan.batch, (batch, plan.batch)
-        pm = net.params_matrix(batch)
-        if self.desc_dev is None:
-            flat = [l if l.params is None or l.params.ndim == 1 else
-                    dataclasses.replace(l, params=l.params[:, 0]) for l in net.leaves]
-            table, p0 = leaf_table(dataclasses.replace(net, leaves=flat), plan)
-            assert len(p0) == pm.shape[1] or (pm.shape[1] == 1 and len(p0) == 1)
-            self.set_leaves([dataclasses.replace(net, leaves=flat)] * 1 if batch == 1 else
-                            [dataclasses.replace(net, leaves=flat)] * batch)
+        varying = frozenset(k for k, l in enumerate(net.leaves)
+                            if l.params is not None and l.params.ndim == 2)
+        if self.desc_dev is None or getattr(self, "_varying", None) != varying:
+            table, _ = leaf_table(net, plan, varying=varying)
+            self._upload_table(table)
+            self._varying = varying
+            self.graph = None            # a captured graph holds the old buffers
+            p_var = max(1, sum(net.leaves[k].size for k in varying))
+            p_sh = max(1, sum(l.size for k, l in enumerate(net.leaves)
+                              if l.params is not None and k not in varying))
+            self.params_stride = p_var
+            self.params_host = torch.empty((batch, p_var), dtype=torch.complex128, pin_memory=True)
+            self.params_dev = torch.empty((batch, p_var), dtype=torch.complex128, device=self.device)
+            self.shared_host = torch.empty(p_sh, dtype=torch.complex128, pin_memory=True)
+            self.shared_dev = torch.empty(p_sh, dtype=torch.complex128, device=self.device)
         if self._params_copied is not None:
             self._params_copied.synchronize()
-        self.params_host.numpy()[:] = pm
+        ph, sh = self.params_host.numpy(), self.shared_host.numpy()
+        pv = ps = 0
+        for k, l in enumerate(net.leaves):
+            if l.params is None:
+                continue
+            if k in varying:
+                ph[:, pv:pv + l.size] = l.params.T
+                pv += l.size
+            else:
+                sh[ps:ps + l.size] = l.params
+                ps += l.size
         self.params_dev.copy_(self.params_host, non_blocking=True)
-        self.h2d_bytes = int(self.params_host.numel() * 16 + self.desc_dev.numel())
+        self.shared_dev.copy_(self.shared_host, non_blocking=True)
+        self.h2d_bytes = int((self.params_host.numel() + self.shared_host.numel()) * 16
+                             + self.desc_dev.numel())
         if self._params_copied is None:
             self._params_copied = torch.cuda.Event()
         self._params_copied.record()
+
+    def _upload_table(self, table: np.ndarray) -> None:
+        torch, plan = self.torch, self.plan
+        self.n_leaves = len(table)
+        self.desc_dev = torch.from_numpy(table.view(np.uint8).copy()).to(self.device)
+        # leaf holding the first element of every 256-element block of the arena
+        firsts = np.arange(0, plan.arena_elems, 256, dtype=np.int64)
+        firsts = np.append(firsts, plan.arena_elems - 1)
+        block_leaf = np.searchsorted(table["offset"], firsts, side="right") - 1
+        self.block_leaf_dev = torch.from_numpy(block_leaf.astype(np.int32)).to(self.device)
 
     def build_leaves(self) -> None:
         plan = self.plan
         stream = self.torch.cuda.current_stream().cuda_stream
         rt.check(self.lib.b2_build_leaves_indexed(
             self.desc_dev.data_ptr(), self.n_leaves, self.block_leaf_dev.data_ptr(), plan.arena_elems,
-            self.params_dev.data_ptr(), self.params_stride, self.arena.data_ptr(),
-            plan.arena_elems, plan.batch, self.code, stream), "b2_build_leaves")
+            self.params_dev.data_ptr(), self.params_stride,
+            self.shared_dev.data_ptr() if self.shared_dev is not None else None,
+            self.arena.data_ptr(), plan.arena_elems, plan.batch, self.code, stream), "b2_build_leaves")
         self.launches += 1
 
     # ---- steps --------------------------------------------------------------

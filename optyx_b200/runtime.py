@@ -30,14 +30,14 @@ class LeafDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("ndim", C.c_int32),
         ("dims", C.c_int32 * MAX_LEAF_RANK),
-        ("ipar", C.c_int32), ("reserved", C.c_int32),
+        ("ipar", C.c_int32), ("shared", C.c_int32),
         ("offset", C.c_int64), ("nelem", C.c_int64), ("poff", C.c_int64),
     ]
 
 
 LEAF_DESC_DTYPE = np.dtype([
     ("kind", "<i4"), ("ndim", "<i4"), ("dims", "<i4", (MAX_LEAF_RANK,)),
-    ("ipar", "<i4"), ("reserved", "<i4"),
+    ("ipar", "<i4"), ("shared", "<i4"),
     ("offset", "<i8"), ("nelem", "<i8"), ("poff", "<i8"),
 ])
 assert LEAF_DESC_DTYPE.itemsize == C.sizeof(LeafDesc) == 72
@@ -130,7 +130,7 @@ def load():
     lib.b2_last_kernel.restype = C.c_char_p
     lib.b2_device_sms.restype = C.c_int
     lib.b2_build_leaves.argtypes = [vp, i32, i64, vp, i64, vp, i64, i32, i32, vp]
-    lib.b2_build_leaves_indexed.argtypes = [vp, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.b2_build_leaves_indexed.argtypes = [vp, i32, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
     lib.b2_contract_direct.argtypes = [C.POINTER(Modes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_contract_gemm.argtypes = [C.POINTER(GemmModes), vp, vp, vp, dbl, dbl, i32, i32, vp]
     lib.b2_run_small_program.argtypes = [C.POINTER(SmallProgramArgs), i32, vp]
