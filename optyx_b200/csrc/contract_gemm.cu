@@ -433,6 +433,18 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
             if (want > chunks / 8) want = chunks / 8;
             if (want > 64) want = 64;
             if (want > 1) ksplit = (int)want;
+        } else if (tiles < 6 * slots && chunks >= 128 && (dense_c || accumulate)) {
+            // a few waves of long-K tiles: the last, partly filled wave idles much of the
+            // GPU (256 tiles on 296 slots: 86 %).  Splitting K multiplies the CTA count;
+            // take the smallest split whose last wave is at least 97 % full.
+            auto fill = [&](long long ks) {
+                const long long ctas = tiles * ks, waves = (ctas + slots - 1) / slots;
+                return (double)ctas / (double)(waves * slots);
+            };
+            const long long max_split = chunks / 64 < 32 ? chunks / 64 : 32;
+            double best = fill(1);
+            for (long long ks = 2; ks <= max_split && best < 0.97; ++ks)
+                if (fill(ks) > best + 0.02) { best = fill(ks); ksplit = (int)ks; }
         }
         if (ksplit > 1 && !accumulate) {
             cudaError_t e = cudaMemsetAsync(c_dev, 0, (size_t)(Bt * M * N) * sizeof(double2),

@@ -682,8 +682,7 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
 # --------------------------------------------------------------------------
 # the small-step program (csrc/contract_small.cu)
 # --------------------------------------------------------------------------
-SMALL_ELEMS = 8192                  # largest operand / result of a step the interpreter takes
-                                    # (128 KB of complex128; offsets stay below 2^16)
+SMALL_ELEMS = 4096                  # largest operand / result of a step the interpreter takes
 SMALL_WORK = 1 << 18                # ... and its multiply-adds
 SMALL_SCRATCH_ELEMS = 11264         # scratch budget of one task (complex elements: 176 KB c128;
                                     # the task blob -- records + staged tables -- rides beside it)
@@ -1090,13 +1089,6 @@ def plan_network(net: Network, dtype=np.complex128, batch: int = 1, trials: int 
     if len(inputs) >= 2:
         info = find_path(inputs, net.dims, output, trials=trials, seed=seed,
                          target_size=target_size, min_slices=min_slices)
-        if batch > 1 and target_size is None and min_slices <= 1 and info.peak > SMALL_ELEMS:
-            # a batch of small evals: a tree whose every intermediate fits the small-step
-            # interpreter runs each eval entirely out of shared memory (one CTA per eval,
-            # no HBM round trip per step) -- worth some extra multiply-adds
-            narrow = find_path(inputs, net.dims, output, trials=trials, seed=seed, minimize="size")
-            if narrow.peak <= SMALL_ELEMS and narrow.macs <= 4.0 * info.macs:
-                info = narrow
     else:
         info = PathInfo([], (), 0.0, 0.0, 1, [])
     return compile_plan(net, info, dtype=dtype, batch=batch, gemm_threshold=gemm_threshold)
