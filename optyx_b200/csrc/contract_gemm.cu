@@ -374,8 +374,10 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     for (int i = 0; i < g.n_batch; ++i) b_total *= g.dim[i];
     const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
                                  2ll * num_sms() && k_total >= 256;
-    // (B2_CTILE_KMAX: experiment knob, reductions up to this length take the ctile kernel)
-    static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 32;
+    // reductions up to ctile_kmax take the ctile kernel (B2_CTILE_KMAX: experiment knob).
+    // Measured (profiles/r02_shortk.md): from K = 16 on the 64x64 tiling is faster on
+    // plain AND permuted layouts -- (2,16384,1024,32) of cfg4: 1336 -> 489 us
+    static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 8;
     if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
