@@ -22,7 +22,10 @@
 
 namespace b2 {
 
-constexpr int BM = 64, BN = 64, BK = 8, STAGES = 4, PITCH = 66, GEMM_THREADS = 128;
+constexpr int BM = 64, BN = 64, PITCH = 66, GEMM_THREADS = 128;
+// K chunk and ring depth are template parameters of the kernel: (8, 4) for short
+// reductions, (16, 3) for long ones (half the block barriers per multiply-add: the ncu
+// capture of the (8, 4) kernel shows 20 % of the stall samples on the barrier)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -54,6 +57,7 @@ __device__ __forceinline__ void decode3(long long flat, const b2_gemm_modes& g, 
     }
 }
 
+template <int BK, int STAGES>
 struct gemm_smem {
     double2 a[STAGES][BK][PITCH];
     double2 b[STAGES][BK][PITCH];
@@ -61,7 +65,7 @@ struct gemm_smem {
     long long k_a[STAGES][BK], k_b[STAGES][BK];
 };
 
-template <bool SPLITK>
+template <bool SPLITK, int BK, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
                           const double2* __restrict__ B, double2* __restrict__ Cout,
@@ -69,7 +73,8 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
                           int a_kfast, int b_kfast, double alpha_re, double alpha_im,
                           int accumulate, int ksplit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    gemm_smem& sm = *reinterpret_cast<gemm_smem*>(smem_raw);
+    using smem_t = gemm_smem<BK, STAGES>;
+    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
@@ -409,14 +414,22 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         set_error("b2_contract_gemm: grid too large (tiles=%lld batch=%lld)", tiles_m * tiles_n, Bt);
         return 1;
     }
+    // long reductions: K chunk 16, 3 stages (half the block barriers per multiply-add);
+    // short ones keep chunk 8, 4 stages.  (B2_GEMM_BK: experiment knob.)
+    static const int force_bk = getenv("B2_GEMM_BK") ? atoi(getenv("B2_GEMM_BK")) : 0;
+    const int BK = force_bk ? force_bk : (K >= 128 ? 16 : 8);
+    const int smem = BK == 16 ? (int)sizeof(gemm_smem<16, 3>) : (int)sizeof(gemm_smem<8, 4>);
     static b2::once_flags attr_set;
-    const int smem = (int)sizeof(gemm_smem);
     if (!b2::is_done(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(contract_gemm_c128_kernel<false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(contract_gemm_c128_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* fn, int bytes) {
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        };
+        set((const void*)contract_gemm_c128_kernel<false, 8, 4>, (int)sizeof(gemm_smem<8, 4>));
+        set((const void*)contract_gemm_c128_kernel<true, 8, 4>, (int)sizeof(gemm_smem<8, 4>));
+        set((const void*)contract_gemm_c128_kernel<false, 16, 3>, (int)sizeof(gemm_smem<16, 3>));
+        set((const void*)contract_gemm_c128_kernel<true, 16, 3>, (int)sizeof(gemm_smem<16, 3>));
         if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
         b2::mark_done(attr_set);
     }
@@ -456,13 +469,15 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     }
     set_last_kernel(ksplit > 1 ? "gemm_splitk" : "gemm");
     dim3 grid((unsigned)(tiles_m * tiles_n * Bt), 1u, (unsigned)ksplit);
-    if (ksplit > 1)
-        contract_gemm_c128_kernel<true><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-            g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
-            tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, ksplit);
-    else
-        contract_gemm_c128_kernel<false><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(
-            g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,
-            tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, 1);
+#define B2_GEMM_LAUNCH(SPLIT, BKV, STV, KS)                                                      \
+    contract_gemm_c128_kernel<SPLIT, BKV, STV><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>( \
+        g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,  \
+        tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, KS)
+    if (BK == 16) {
+        if (ksplit > 1) B2_GEMM_LAUNCH(true, 16, 3, ksplit); else B2_GEMM_LAUNCH(false, 16, 3, 1);
+    } else {
+        if (ksplit > 1) B2_GEMM_LAUNCH(true, 8, 4, ksplit); else B2_GEMM_LAUNCH(false, 8, 4, 1);
+    }
+#undef B2_GEMM_LAUNCH
     return check_launch("b2_contract_gemm");
 }
