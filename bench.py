@@ -59,7 +59,7 @@ def workload(name: str):
     diagrams per step)."""
     from optyx_b200 import workloads as cases
     if name == "cfg4":
-        n, depth = 30, 44
+        n, depth = 30, 48
         return dict(kind="sliced", factory=lambda: cases.random_clifford_t(n, depth, seed=0),
                     target=CFG4_TARGET, trials=16, min_slices=CFG4_MIN_SLICES,
                     desc=f"cfg4: {n}-qubit brickwork Clifford+T depth {depth} amplitude <0|C|0>, "

@@ -325,6 +325,12 @@ int b2_plan_greedy(int32_t n, const int32_t* ind_ptr, const int32_t* inds, int32
 int b2_plan_cost(int32_t n, const int32_t* ind_ptr, const int32_t* inds, int32_t n_inds,
                  const int32_t* dims, const uint8_t* is_output, const int32_t* path,
                  const uint8_t* is_sliced, double* out, double* step_sizes_out);
+/* subtree reconfiguration: every subtree of at most max_leaves (3..10) frontier nodes gets
+ * the optimal internal pair order (dynamic programming over subsets; multiply-adds with
+ * the sliced indices fixed); the SSA path is rewritten in place                          */
+int b2_plan_reconfigure(int32_t n, const int32_t* ind_ptr, const int32_t* inds, int32_t n_inds,
+                        const int32_t* dims, const uint8_t* is_output, const uint8_t* is_sliced,
+                        int32_t max_leaves, int32_t* path, int32_t* improved_out);
 
 /* micro-benchmarks used by bench.py to measure the FP64 pipes of this GPU:
  * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = DMMA m16n8k16 (falls back to 1 if the

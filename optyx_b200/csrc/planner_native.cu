@@ -232,3 +232,242 @@ extern "C" int b2_plan_cost(int32_t n, const int32_t* ind_ptr, const int32_t* in
     out[0] = macs; out[1] = peak; out[2] = nslices; out[3] = t_inv + nslices * t_dep;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Subtree reconfiguration: walk the contraction tree, and for every subtree of at most
+// `max_leaves` frontier nodes replace its internal pair order by the OPTIMAL one (dynamic
+// programming over subsets, cost = multiply-adds with the sliced indices fixed).  The
+// classic local search of tensor-network path optimisers (cotengra's
+// `subtree_reconfigure`), here hyper-index aware: an index survives a partial result as
+// long as some tensor outside it -- inside or outside the subtree -- or the output still
+// carries it.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Node {
+    int left = -1, right = -1;          // children (-1: an input tensor)
+    std::vector<int> inds;              // sorted result indices
+};
+
+static void merge_inds(const std::vector<int>& A, const std::vector<int>& B,
+                       const std::vector<int>& outside, std::vector<int>& res,
+                       std::vector<int>* uni) {
+    // outside[q]: how many tensors OUTSIDE A and B (incl. the output) carry q
+    res.clear();
+    if (uni) uni->clear();
+    size_t i = 0, j = 0;
+    while (i < A.size() || j < B.size()) {
+        int q;
+        if (j >= B.size() || (i < A.size() && A[i] < B[j])) q = A[i++];
+        else if (i >= A.size() || B[j] < A[i]) q = B[j++];
+        else { q = A[i]; ++i; ++j; }
+        if (uni) uni->push_back(q);
+        if (outside[q] > 0) res.push_back(q);
+    }
+}
+
+}  // namespace
+
+// path: SSA pair order (2 * (n - 1) ids), rewritten in place.  Returns the number of
+// subtrees that were improved through *improved_out.
+extern "C" int b2_plan_reconfigure(int32_t n, const int32_t* ind_ptr, const int32_t* inds,
+                                   int32_t n_inds, const int32_t* dims, const uint8_t* is_output,
+                                   const uint8_t* is_sliced, int32_t max_leaves, int32_t* path,
+                                   int32_t* improved_out) {
+    if (n < 2 || !ind_ptr || !inds || !dims || !path) { b2::set_error("b2_plan_reconfigure: bad arguments"); return 1; }
+    if (max_leaves < 3) max_leaves = 3;
+    if (max_leaves > 10) max_leaves = 10;
+    const int total = 2 * n - 1;
+    std::vector<double> ldim(n_inds);
+    for (int q = 0; q < n_inds; ++q) ldim[q] = (is_sliced && is_sliced[q]) ? 0.0 : std::log2((double)dims[q]);
+    // ---- build the tree from the SSA path
+    std::vector<Node> node(total);
+    std::vector<int> carriers(n_inds, 0);            // live tensors + output carrying q
+    for (int k = 0; k < n; ++k) {
+        std::vector<int>& t = node[k].inds;
+        t.assign(inds + ind_ptr[k], inds + ind_ptr[k + 1]);
+        std::sort(t.begin(), t.end());
+        t.erase(std::unique(t.begin(), t.end()), t.end());
+        for (int q : t) ++carriers[q];
+    }
+    for (int q = 0; q < n_inds; ++q) if (is_output && is_output[q]) ++carriers[q];
+    {
+        std::vector<int> cnt = carriers, res;
+        for (int s = 0; s < n - 1; ++s) {
+            const int a = path[2 * s], b = path[2 * s + 1], c = n + s;
+            if (a < 0 || b < 0 || a >= c || b >= c || a == b) { b2::set_error("b2_plan_reconfigure: bad path"); return 1; }
+            for (int q : node[a].inds) --cnt[q];
+            for (int q : node[b].inds) --cnt[q];
+            merge_inds(node[a].inds, node[b].inds, cnt, res, nullptr);
+            for (int q : res) ++cnt[q];
+            node[c].left = a; node[c].right = b; node[c].inds = res;
+        }
+    }
+    const int root = total - 1;
+    int improved = 0;
+    // ---- local search: every internal node is the root of one candidate subtree
+    std::vector<int> order;                          // internal nodes, root first (BFS)
+    {
+        std::vector<int> q{root};
+        for (size_t h = 0; h < q.size(); ++h) {
+            const int v = q[h];
+            if (node[v].left < 0) continue;
+            order.push_back(v);
+            q.push_back(node[v].left); q.push_back(node[v].right);
+        }
+    }
+    std::vector<int> frontier, internal, local_of(n_inds, -1), touched;
+    for (int v : order) {
+        if (node[v].left < 0) continue;
+        // frontier: expand the largest expandable node until max_leaves
+        frontier.assign({node[v].left, node[v].right});
+        internal.assign({v});
+        while ((int)frontier.size() < max_leaves) {
+            int pick = -1; double best = -1.0;
+            for (size_t i = 0; i < frontier.size(); ++i) {
+                const int f = frontier[i];
+                if (node[f].left < 0) continue;
+                double s = 0.0;
+                for (int q : node[f].inds) s += ldim[q];
+                if (s > best) { best = s; pick = (int)i; }
+            }
+            if (pick < 0) break;
+            const int f = frontier[pick];
+            internal.push_back(f);
+            frontier[pick] = node[f].left;
+            frontier.push_back(node[f].right);
+        }
+        const int L = (int)frontier.size();
+        if (L < 3) continue;
+        // local index table and per-leaf bitsets (up to 64 * W local indices)
+        touched.clear();
+        for (int f : frontier) for (int q : node[f].inds) if (local_of[q] < 0) { local_of[q] = (int)touched.size(); touched.push_back(q); }
+        const int nl = (int)touched.size(), W = (nl + 63) / 64;
+        std::vector<uint64_t> leafbits((size_t)L * W, 0), extbits(W, 0);
+        std::vector<int> inside(nl, 0);
+        for (int i = 0; i < L; ++i) for (int q : node[frontier[i]].inds) {
+            const int l = local_of[q];
+            leafbits[(size_t)i * W + l / 64] |= 1ull << (l % 64);
+            ++inside[l];
+        }
+        // external: carried by a tensor outside the subtree or by the output
+        //   = appears in the subtree root's result
+        for (int q : node[v].inds) { const int l = local_of[q]; if (l >= 0) extbits[l / 64] |= 1ull << (l % 64); }
+        std::vector<double> lw(nl);
+        for (int l = 0; l < nl; ++l) lw[l] = ldim[touched[l]];
+        const int NS = 1 << L;
+        std::vector<uint64_t> ib((size_t)NS * W, 0);          // inds of a subset (union of leaves)
+        for (int S = 1; S < NS; ++S) {
+            const int low = __builtin_ctz(S), rest = S & (S - 1);
+            for (int w = 0; w < W; ++w) ib[(size_t)S * W + w] = ib[(size_t)rest * W + w] | leafbits[(size_t)low * W + w];
+        }
+        // kept(S) = inds(S) & (ext | inds(~S))
+        auto kept_size = [&](int S1, int S2, std::vector<uint64_t>& tmp) {   // log2 MACs of S1 x S2
+            const int comp1 = (NS - 1) & ~S1, comp2 = (NS - 1) & ~S2;
+            double s = 0.0;
+            for (int w = 0; w < W; ++w) {
+                const uint64_t k1 = ib[(size_t)S1 * W + w] & (extbits[w] | ib[(size_t)comp1 * W + w]);
+                const uint64_t k2 = ib[(size_t)S2 * W + w] & (extbits[w] | ib[(size_t)comp2 * W + w]);
+                uint64_t u = k1 | k2;
+                while (u) { const int b = __builtin_ctzll(u); u &= u - 1; s += lw[w * 64 + b]; }
+            }
+            (void)tmp;
+            return s;
+        };
+        std::vector<double> bestc(NS, 1e300);
+        std::vector<int> split(NS, 0);
+        std::vector<uint64_t> tmp(W);
+        for (int i = 0; i < L; ++i) bestc[1 << i] = 0.0;
+        for (int S = 1; S < NS; ++S) {
+            if ((S & (S - 1)) == 0) continue;
+            // enumerate splits S1 < S2, S1 | S2 = S
+            for (int S1 = (S - 1) & S; S1 > 0; S1 = (S1 - 1) & S) {
+                const int S2 = S ^ S1;
+                if (S1 < S2) continue;
+                if (bestc[S1] >= 1e299 || bestc[S2] >= 1e299) continue;
+                const double c = std::exp2(kept_size(S1, S2, tmp));
+                const double tot = bestc[S1] + bestc[S2] + c;
+                if (tot < bestc[S]) { bestc[S] = tot; split[S] = S1; }
+            }
+        }
+        // current cost of the subtree's internal order
+        double cur = 0.0;
+        {
+            std::vector<int> uni, res;
+            for (int u : internal) {
+                const std::vector<int>&A = node[node[u].left].inds, &B = node[node[u].right].inds;
+                double s = 0.0;
+                size_t i = 0, j = 0;
+                while (i < A.size() || j < B.size()) {
+                    int q;
+                    if (j >= B.size() || (i < A.size() && A[i] < B[j])) q = A[i++];
+                    else if (i >= A.size() || B[j] < A[i]) q = B[j++];
+                    else { q = A[i]; ++i; ++j; }
+                    s += ldim[q];
+                }
+                cur += std::exp2(s);
+            }
+        }
+        if (bestc[NS - 1] < cur * (1.0 - 1e-9)) {
+            // rebuild: reuse the internal node slots (v stays the subtree root)
+            ++improved;
+            std::vector<int> slots(internal.begin() + 1, internal.end());
+            std::vector<int> made(NS, -1);
+            for (int i = 0; i < L; ++i) made[1 << i] = frontier[i];
+            // post-order construction
+            std::vector<int> stack{NS - 1};
+            std::vector<int> post;
+            while (!stack.empty()) {
+                const int S = stack.back(); stack.pop_back();
+                if ((S & (S - 1)) == 0) continue;
+                post.push_back(S);
+                stack.push_back(split[S]); stack.push_back(S ^ split[S]);
+            }
+            for (auto it = post.rbegin(); it != post.rend(); ++it) {
+                const int S = *it, S1 = split[S], S2 = S ^ S1;
+                int slot;
+                if (S == NS - 1) slot = v;
+                else { slot = slots.back(); slots.pop_back(); }
+                node[slot].left = made[S1]; node[slot].right = made[S2];
+                // result indices: kept(S)
+                std::vector<int>& r = node[slot].inds;
+                if (S != NS - 1) {
+                    r.clear();
+                    const int comp = (NS - 1) & ~S;
+                    for (int w = 0; w < W; ++w) {
+                        uint64_t k = ib[(size_t)S * W + w] & (extbits[w] | ib[(size_t)comp * W + w]);
+                        while (k) { const int b = __builtin_ctzll(k); k &= k - 1; r.push_back(touched[w * 64 + b]); }
+                    }
+                    std::sort(r.begin(), r.end());
+                }
+                made[S] = slot;
+            }
+        }
+        for (int q : touched) local_of[q] = -1;
+    }
+    // ---- back to an SSA path (post-order; children before parents)
+    {
+        std::vector<int> ssa_id(total, -1);
+        for (int k = 0; k < n; ++k) ssa_id[k] = k;
+        int nxt = n, written = 0;
+        std::vector<std::pair<int, int>> st;          // (node, state)
+        st.push_back({root, 0});
+        while (!st.empty()) {
+            auto [u, state] = st.back();
+            st.pop_back();
+            if (node[u].left < 0) continue;
+            if (state == 0) {
+                st.push_back({u, 1});
+                st.push_back({node[u].right, 0});
+                st.push_back({node[u].left, 0});
+            } else {
+                path[written++] = ssa_id[node[u].left];
+                path[written++] = ssa_id[node[u].right];
+                ssa_id[u] = nxt++;
+            }
+        }
+        if (written != 2 * (n - 1)) { b2::set_error("b2_plan_reconfigure: tree corrupted"); return 1; }
+    }
+    if (improved_out) *improved_out = improved;
+    return 0;
+}

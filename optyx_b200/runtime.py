@@ -22,7 +22,7 @@ EXPORTS = [
     "b2_contract_direct", "b2_contract_gemm", "b2_run_small_program", "b2_axpy", "b2_fill_zero",
     "b2_probs_amp", "b2_probs_dm", "b2_compact_nonzero", "b2_permanent_amplitudes", "b2_permanent_histogram",
     "b2_fp64_peak_kernel", "b2_run_plan", "b2_workspace_bytes", "b2_build_leaves_indexed",
-    "b2_plan_greedy", "b2_plan_cost", "b2_conj", "b2_bond_compress", "b2_bond_compress_scratch_bytes",
+    "b2_plan_greedy", "b2_plan_cost", "b2_plan_reconfigure", "b2_conj", "b2_bond_compress", "b2_bond_compress_scratch_bytes",
 ]
 
 
@@ -143,6 +143,7 @@ def load():
     lib.b2_bond_compress_scratch_bytes.argtypes = [i32]
     lib.b2_plan_greedy.argtypes = [i32, vp, vp, i32, vp, vp, C.c_uint64, dbl, dbl, vp]
     lib.b2_plan_cost.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.b2_plan_reconfigure.argtypes = [i32, vp, vp, i32, vp, vp, vp, i32, vp, vp]
     lib.b2_axpy.argtypes = [i64, dbl, dbl, vp, vp, i32, vp]
     lib.b2_fill_zero.argtypes = [i64, vp, i32, vp]
     lib.b2_probs_amp.argtypes = [i64, vp, vp, vp, i32, vp]

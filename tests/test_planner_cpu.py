@@ -438,3 +438,32 @@ def test_array_valued_parameters_compile_a_whole_batch_in_one_pass():
             assert np.abs(pm[j] - params_vector(one)).max() <= 1e-15
             sc = net.scalar[j] if np.ndim(net.scalar) else net.scalar
             assert abs(sc - one.scalar) <= 1e-15
+
+
+def test_subtree_reconfiguration_never_hurts_and_keeps_the_tensor():
+    """b2_plan_reconfigure: optimal pair order inside every subtree of <= 8 frontier
+    nodes.  Cost never goes up, the rewritten SSA path is valid, and the plan compiled
+    from it contracts to the oracle's tensor (hyper-indices, open outputs, slicing)."""
+    import cases
+    from optyx_b200 import planner
+    for d, sliced_n in ((cases.random_clifford_t(12, 10, seed=4), 2), (cases.ghz(8, open_qubits=3, noise=0.9), 0),
+                        (cases.cfg1_interferometer(4, (1, 1, 0, 0)), 0)):
+        net = cases.compile_channel(d)
+        inputs = [frozenset(l.inds) for l in net.leaves]
+        output = frozenset(net.output_inds)
+        nn = planner.NativeNetwork(inputs, net.dims, output)
+        closed = sorted({q for s in inputs for q in s} - output)
+        sliced = tuple(closed[:sliced_n])
+        for seed in (1, 2, 3):
+            p = nn.greedy(seed=seed, temperature=1.0)
+            before = nn.cost(p, sliced)
+            p2 = nn.reconfigure(p, sliced, max_leaves=8)
+            after = nn.cost(p2, sliced)
+            assert after[0] <= before[0] * (1 + 1e-12)
+            n = len(inputs)
+            used = set()
+            for k, (a, b) in enumerate(p2.tolist()):
+                assert a != b and a < n + k and b < n + k and a not in used and b not in used
+                used.update((a, b))
+            plan = planner.plan_from_ssa_path(net, [tuple(x) for x in p2.tolist()], sliced)
+            assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)
