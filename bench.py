@@ -382,10 +382,16 @@ class Bench:
             step_fn()                            # the sampler start-up left the GPU idle
             self.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            profiled = os.environ.get("B2_PROFILE_TIMED") == name    # ncu --profile-from-start off
+            if profiled:
+                torch.cuda.profiler.start()
             e0.record()
             for _ in range(steps):
                 step_fn()
             e1.record()
+            if profiled:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
             self.barrier()
             secs = self.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
             # ---- dominant kernel alone, same stream, CUDA events over K launches

@@ -57,6 +57,61 @@ __device__ __forceinline__ void decode3(long long flat, const b2_gemm_modes& g, 
     }
 }
 
+// One K chunk of one operand, global -> shared ([k][pitch] layout), 16 B per cp.async.
+// `row_off` / `k_off` are BYTE offsets (tile rows / chunk reduction values through the
+// per-mode strides).  Rows beyond the matrix edge point at row 0 (valid memory, their
+// results are never stored); only the K tail needs zero fill (`kvalid` < BK in the last
+// chunk).  The thread -> element map keeps the per-copy work at one table load + one
+// 64-bit add, keeps global reads sector-exact and shared-memory writes conflict-free:
+//   K contiguous in the operand: a quarter warp = 4 consecutive k x 2 rows (2 full
+//     sectors per row; bank = 8*k + 4*row (mod 32) -- with the naive "k fastest" map the
+//     66-element pitch makes every write 2-way conflicted), a warp = BK k x 32/BK... rows
+//   rows contiguous: consecutive threads = consecutive rows of one k.
+template <int ROWS, int BK, int THREADS, int PITCH_>
+__device__ __forceinline__ void gather_chunk(double2* dst, const double2* __restrict__ base,
+                                             const long long* row_off, const long long* k_off,
+                                             int tid, bool kfast, int kvalid) {
+    constexpr int P = ROWS * BK / THREADS;
+    static_assert(P >= 1 && (ROWS * BK) % THREADS == 0, "tile / thread count mismatch");
+    const char* b = reinterpret_cast<const char*>(base);
+    if (kfast) {
+        constexpr int LOGBK = BK == 16 ? 4 : 3;
+        const int j = (tid & 3) | ((tid >> 1) & (BK - 4));
+        const int i0 = ((tid >> 2) & 1) | ((tid >> (LOGBK + 1)) << 1);
+        const char* src = b + k_off[j];
+        const int bytes = j < kvalid ? 16 : 0;
+        double2* d = dst + j * PITCH_ + i0;
+        #pragma unroll
+        for (int p = 0; p < P; ++p)
+            cp_async16(d + p * (THREADS / BK), src + row_off[i0 + p * (THREADS / BK)], bytes);
+    } else {
+        const int i = tid % ROWS, j0 = tid / ROWS;
+        const char* src = b + row_off[i];
+        double2* d = dst + j0 * PITCH_ + i;
+        #pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int j = j0 + p * (THREADS / ROWS);
+            cp_async16(d + p * (THREADS / ROWS) * PITCH_, src + k_off[j], j < kvalid ? 16 : 0);
+        }
+    }
+}
+
+// Tile order: groups of RASTER_GM row tiles x all column tiles, rows fastest inside a
+// group.  The ~2 x 148 CTAs resident at one time then form a near-square block of the
+// tile grid, so every operand tile is fetched from HBM about once and re-used out of L2
+// (ncu, cfg4's (2,16384,512,2048) pair with rows fastest over the WHOLE grid: 11.4 GB
+// read for 1.1 GB of operands -- A streamed once per column tile).
+constexpr int RASTER_GM = 16;
+__device__ __forceinline__ void raster_tile(long long tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const long long per_group = (long long)RASTER_GM * tiles_n;
+    const int group = (int)(tile / per_group);
+    const int first_m = group * RASTER_GM;
+    const int gm = tiles_m - first_m < RASTER_GM ? tiles_m - first_m : RASTER_GM;
+    const int r = (int)(tile - (long long)group * per_group);
+    tm = first_m + r % gm;
+    tn = r / gm;
+}
+
 template <int BK, int STAGES>
 struct gemm_smem {
     double2 a[STAGES][BK][PITCH];
@@ -81,7 +136,9 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
     // grid.x = batch x tiles (the batch extent -- eval batch times every hyper-index
     // batch mode -- can exceed the 65535 limit of grid.y)
     const long long tile = blockIdx.x % tiles_mn, batch_id = blockIdx.x / tiles_mn;
-    const long long m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    int tile_m, tile_n;
+    raster_tile(tile, tiles_m, (int)(tiles_mn / tiles_m), tile_m, tile_n);
+    const long long m0 = (long long)tile_m * BM, n0 = (long long)tile_n * BN;
     const int f_b = 0, f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
 
     long long ba, bb, bc;
@@ -93,13 +150,13 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
         long long oa, ob, oc;
         const long long m = m0 + tid;
         decode3(m < M ? m : 0, g, f_m, g.n_m, oa, ob, oc);
-        sm.row_a[tid] = oa; sm.row_c[tid] = oc;
+        sm.row_a[tid] = oa * 16; sm.row_c[tid] = oc;          // operand tables in BYTES
     } else {
         const int t = tid - BM;
         long long oa, ob, oc;
         const long long n = n0 + t;
         decode3(n < N ? n : 0, g, f_n, g.n_n, oa, ob, oc);
-        sm.col_b[t] = ob; sm.col_c[t] = oc;
+        sm.col_b[t] = ob * 16; sm.col_c[t] = oc;
     }
     // split-K (grid z): this CTA reduces chunks [c_begin, c_begin + nchunks) and adds
     // its partial tile into the zero-filled C with FP64 atomics
@@ -127,31 +184,18 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
                 oa += (long long)i * g.sa[f_k + m];
                 ob += (long long)i * g.sb[f_k + m];
             }
-            sm.k_a[chunk % STAGES][t] = oa;
-            sm.k_b[chunk % STAGES][t] = ob;
+            sm.k_a[chunk % STAGES][t] = oa * 16;
+            sm.k_b[chunk % STAGES][t] = ob * 16;
         }
     };
     auto issue = [&](int chunk) {
         const int st = chunk % STAGES;
-        const long long kbase = (long long)(c_begin + chunk) * BK;
-        #pragma unroll
-        for (int p = 0; p < (BM * BK) / GEMM_THREADS; ++p) {
-            const int e = tid + p * GEMM_THREADS;
-            int i, j;
-            if (a_kfast) { j = e % BK; i = e / BK; } else { i = e % BM; j = e / BM; }
-            const bool ok = (m0 + i < M) && (kbase + j < K);
-            const double2* src = ok ? A + sm.row_a[i] + sm.k_a[st][j] : A;
-            cp_async16(&sm.a[st][j][i], src, ok ? 16 : 0);
-        }
-        #pragma unroll
-        for (int p = 0; p < (BN * BK) / GEMM_THREADS; ++p) {
-            const int e = tid + p * GEMM_THREADS;
-            int i, j;
-            if (b_kfast) { j = e % BK; i = e / BK; } else { i = e % BN; j = e / BN; }
-            const bool ok = (n0 + i < N) && (kbase + j < K);
-            const double2* src = ok ? B + sm.col_b[i] + sm.k_b[st][j] : B;
-            cp_async16(&sm.b[st][j][i], src, ok ? 16 : 0);
-        }
+        const long long kleft = K - (long long)(c_begin + chunk) * BK;
+        const int kvalid = kleft < BK ? (int)kleft : BK;
+        gather_chunk<BM, BK, GEMM_THREADS, PITCH>(&sm.a[st][0][0], A, sm.row_a, sm.k_a[st], tid,
+                                                   a_kfast != 0, kvalid);
+        gather_chunk<BN, BK, GEMM_THREADS, PITCH>(&sm.b[st][0][0], B, sm.col_b, sm.k_b[st], tid,
+                                                   b_kfast != 0, kvalid);
     };
 
     for (int c = 0; c < STAGES - 1; ++c) if (c < nchunks) decode_k(c);
@@ -217,6 +261,176 @@ contract_gemm_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2
                 double2 v;
                 v.x = alpha_re * cre[r][q][h] - alpha_im * cim[r][q][h];
                 v.y = alpha_re * cim[r][q][h] + alpha_im * cre[r][q][h];
+                double2* dst = Cout + ro + sm.col_c[j];
+                if (SPLITK) {
+                    atomicAdd(&dst->x, v.x);
+                    atomicAdd(&dst->y, v.y);
+                } else {
+                    if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
+            }
+        }
+    }
+}
+
+// ---- 3M complex multiplication for long reductions.  A complex product needs only
+// three real products:   P1 = sum ar*br,  P2 = sum ai*bi,  P3 = sum (ar+ai)*(br+bi)
+//                        C_re = P1 - P2,  C_im = P3 - P1 - P2
+// i.e. 3 DMMAs per complex tile product instead of 4: the FP64 tensor pipe -- the unit
+// that bounds these pairs -- does 25 % less work per contraction (cuBLAS exposes the
+// same trade as zgemm3m).  The price is a third accumulator set, so the warp tile is
+// 32 x 16 (48 accumulator doubles per thread) and the two operand sums are formed in
+// registers from the fragments (6 DADD per 24 DMMA).  The imaginary part is a
+// difference of sums: its error is bounded relative to |A||B| (a few ulp of the larger
+// of the two parts of an output), far inside the 1e-10 bar of this path.
+// CTA tile 64 x BN3 (BN3 = 64: 8 warps, one CTA per SM; BN3 = 32: 4 warps, two CTAs
+// per SM), K chunk 16, 3-stage cp.async gather ring as above.
+template <int BN3>
+struct gemm3m_smem {
+    double2 a[3][16][PITCH];
+    double2 b[3][16][BN3 + 2];
+    long long row_a[BM], row_c[BM], col_b[BN3], col_c[BN3];
+    long long k_a[3][16], k_b[3][16];
+};
+
+template <bool SPLITK, int BN3>
+__global__ void __launch_bounds__(BN3 * 4, BN3 == 64 ? 1 : 2)
+contract_gemm3m_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
+                            const double2* __restrict__ B, double2* __restrict__ Cout,
+                            long long M, long long N, long long K, int tiles_m, long long tiles_mn,
+                            int a_kfast, int b_kfast, double alpha_re, double alpha_im,
+                            int accumulate, int ksplit) {
+    constexpr int BK = 16, STAGES = 3, THREADS = BN3 * 4, WN = BN3 / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using smem_t = gemm3m_smem<BN3>;
+    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const long long tile = blockIdx.x % tiles_mn, batch_id = blockIdx.x / tiles_mn;
+    int tile_m, tile_n;
+    raster_tile(tile, tiles_m, (int)(tiles_mn / tiles_m), tile_m, tile_n);
+    const long long m0 = (long long)tile_m * BM, n0 = (long long)tile_n * BN3;
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+
+    long long ba, bb, bc;
+    decode3(batch_id, g, 0, g.n_batch, ba, bb, bc);
+    A += ba; B += bb; Cout += bc;
+    if (tid < BM) {
+        long long oa, ob, oc;
+        const long long m = m0 + tid;
+        decode3(m < M ? m : 0, g, f_m, g.n_m, oa, ob, oc);
+        sm.row_a[tid] = oa * 16; sm.row_c[tid] = oc;
+    } else if (tid < BM + BN3) {
+        const int t = tid - BM;
+        long long oa, ob, oc;
+        const long long n = n0 + t;
+        decode3(n < N ? n : 0, g, f_n, g.n_n, oa, ob, oc);
+        sm.col_b[t] = ob * 16; sm.col_c[t] = oc;
+    }
+    const int all_chunks = (int)((K + BK - 1) / BK);
+    const int per_split = SPLITK ? (all_chunks + ksplit - 1) / ksplit : all_chunks;
+    const int c_begin = SPLITK ? (int)blockIdx.z * per_split : 0;
+    const int nchunks = !SPLITK ? all_chunks
+                        : (all_chunks - c_begin < per_split
+                               ? (all_chunks - c_begin > 0 ? all_chunks - c_begin : 0) : per_split);
+    auto decode_k = [&](int chunk) {
+        const int t = tid - (THREADS - 32);
+        if (t >= 0 && t < BK) {
+            unsigned k = (unsigned)(c_begin + chunk) * BK + (unsigned)t;
+            if ((long long)k >= K) k = 0;
+            long long oa = 0, ob = 0;
+            for (int m = 0; m < g.n_k; ++m) {
+                const unsigned d = (unsigned)g.dim[f_k + m];
+                const unsigned q = k / d, i = k - q * d;
+                k = q;
+                oa += (long long)i * g.sa[f_k + m];
+                ob += (long long)i * g.sb[f_k + m];
+            }
+            sm.k_a[chunk % STAGES][t] = oa * 16;
+            sm.k_b[chunk % STAGES][t] = ob * 16;
+        }
+    };
+    auto issue = [&](int chunk) {
+        const int st = chunk % STAGES;
+        const long long kleft = K - (long long)(c_begin + chunk) * BK;
+        const int kvalid = kleft < BK ? (int)kleft : BK;
+        gather_chunk<BM, BK, THREADS, PITCH>(&sm.a[st][0][0], A, sm.row_a, sm.k_a[st], tid,
+                                              a_kfast != 0, kvalid);
+        gather_chunk<BN3, BK, THREADS, BN3 + 2>(&sm.b[st][0][0], B, sm.col_b, sm.k_b[st], tid,
+                                                 b_kfast != 0, kvalid);
+    };
+
+    for (int c = 0; c < STAGES - 1; ++c) if (c < nchunks) decode_k(c);
+    __syncthreads();
+    for (int c = 0; c < STAGES - 1; ++c) {
+        if (c < nchunks) issue(c);
+        cp_async_commit();
+    }
+
+    double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+    #pragma unroll
+    for (int r = 0; r < 4; ++r)
+        #pragma unroll
+        for (int q = 0; q < 2; ++q)
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
+
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const int nxt = c + STAGES - 1;
+        if (nxt < nchunks) decode_k(nxt);
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (nxt < nchunks) issue(nxt);
+        cp_async_commit();
+        const int st = c % STAGES;
+        #pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double2 af[4], bf[2];
+            double as[4], bs[2];
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) af[r] = sm.a[st][k4 + fk][wm * 32 + r * 8 + frow];
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) bf[q] = sm.b[st][k4 + fk][wn * 16 + q * 8 + frow];
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) as[r] = af[r].x + af[r].y;
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) bs[q] = bf[q].x + bf[q].y;
+            // 24 independent accumulators: a dependent DMMA is 24 instructions behind
+            #pragma unroll
+            for (int r = 0; r < 4; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
+            #pragma unroll
+            for (int r = 0; r < 4; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
+            #pragma unroll
+            for (int r = 0; r < 4; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
+        }
+    }
+    cp_async_wait<0>();
+
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = wm * 32 + r * 8 + frow;
+        if (m0 + i >= M) continue;
+        const long long ro = sm.row_c[i];
+        #pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = wn * 16 + q * 8 + fk * 2 + h;
+                if (n0 + j >= N) continue;
+                const double re = p1[r][q][h] - p2[r][q][h];
+                const double im = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
+                double2 v;
+                v.x = alpha_re * re - alpha_im * im;
+                v.y = alpha_re * im + alpha_im * re;
                 double2* dst = Cout + ro + sm.col_c[j];
                 if (SPLITK) {
                     atomicAdd(&dst->x, v.x);
@@ -409,16 +623,21 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
     const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
-    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    // long reductions: 3M complex multiplication (3 DMMAs per complex tile product, K chunk
+    // 16); short ones: the 4-product kernel with chunk 8 / 4 stages.
+    // (B2_GEMM_3M = 0 | 32 | 64: off / N tile of the 3M kernel; B2_GEMM_BK: experiment knobs.)
+    static const int n3m = getenv("B2_GEMM_3M") ? atoi(getenv("B2_GEMM_3M")) : 64;
+    static const int force_bk = getenv("B2_GEMM_BK") ? atoi(getenv("B2_GEMM_BK")) : 0;
+    const bool three_m = (n3m == 32 || n3m == 64) && K >= 128;
+    const int bn = three_m ? n3m : BN;
+    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + bn - 1) / bn;
     if (tiles_m * tiles_n * Bt > 2147483647ll) {
         set_error("b2_contract_gemm: grid too large (tiles=%lld batch=%lld)", tiles_m * tiles_n, Bt);
         return 1;
     }
-    // long reductions: K chunk 16, 3 stages (half the block barriers per multiply-add);
-    // short ones keep chunk 8, 4 stages.  (B2_GEMM_BK: experiment knob.)
-    static const int force_bk = getenv("B2_GEMM_BK") ? atoi(getenv("B2_GEMM_BK")) : 0;
-    const int BK = force_bk ? force_bk : (K >= 128 ? 16 : 8);
-    const int smem = BK == 16 ? (int)sizeof(gemm_smem<16, 3>) : (int)sizeof(gemm_smem<8, 4>);
+    const int BK = three_m ? 16 : (force_bk ? force_bk : (K >= 128 ? 16 : 8));
+    const int smem = three_m ? (bn == 64 ? (int)sizeof(gemm3m_smem<64>) : (int)sizeof(gemm3m_smem<32>))
+                             : BK == 16 ? (int)sizeof(gemm_smem<16, 3>) : (int)sizeof(gemm_smem<8, 4>);
     static b2::once_flags attr_set;
     if (!b2::is_done(attr_set)) {
         cudaError_t e = cudaSuccess;
@@ -430,6 +649,10 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         set((const void*)contract_gemm_c128_kernel<true, 8, 4>, (int)sizeof(gemm_smem<8, 4>));
         set((const void*)contract_gemm_c128_kernel<false, 16, 3>, (int)sizeof(gemm_smem<16, 3>));
         set((const void*)contract_gemm_c128_kernel<true, 16, 3>, (int)sizeof(gemm_smem<16, 3>));
+        set((const void*)contract_gemm3m_c128_kernel<false, 64>, (int)sizeof(gemm3m_smem<64>));
+        set((const void*)contract_gemm3m_c128_kernel<true, 64>, (int)sizeof(gemm3m_smem<64>));
+        set((const void*)contract_gemm3m_c128_kernel<false, 32>, (int)sizeof(gemm3m_smem<32>));
+        set((const void*)contract_gemm3m_c128_kernel<true, 32>, (int)sizeof(gemm3m_smem<32>));
         if (e != cudaSuccess) { set_error("b2_contract_gemm: smem attr: %s", cudaGetErrorString(e)); return 1; }
         b2::mark_done(attr_set);
     }
@@ -438,7 +661,8 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     // that it can be zero-filled first (the partial tiles are added atomically).
     int ksplit = 1;
     {
-        const long long tiles = tiles_m * tiles_n * Bt, slots = 2ll * num_sms();
+        const long long tiles = tiles_m * tiles_n * Bt;
+        const long long slots = (three_m && bn == 64 ? 1ll : 2ll) * num_sms();    // resident CTAs
         const long long chunks = (K + BK - 1) / BK;
         long long span = 0;
         for (int i = 0; i < f_k; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
@@ -467,17 +691,25 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
             if (e != cudaSuccess) { set_error("b2_contract_gemm: memset: %s", cudaGetErrorString(e)); return 1; }
         }
     }
-    set_last_kernel(ksplit > 1 ? "gemm_splitk" : "gemm");
+    set_last_kernel(three_m ? (ksplit > 1 ? "gemm3m_splitk" : "gemm3m") : (ksplit > 1 ? "gemm_splitk" : "gemm"));
     dim3 grid((unsigned)(tiles_m * tiles_n * Bt), 1u, (unsigned)ksplit);
-#define B2_GEMM_LAUNCH(SPLIT, BKV, STV, KS)                                                      \
-    contract_gemm_c128_kernel<SPLIT, BKV, STV><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>( \
-        g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,  \
-        tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, KS)
-    if (BK == 16) {
-        if (ksplit > 1) B2_GEMM_LAUNCH(true, 16, 3, ksplit); else B2_GEMM_LAUNCH(false, 16, 3, 1);
+#define B2_GEMM_ARGS                                                                              \
+    g, (const double2*)a_dev, (const double2*)b_dev, (double2*)c_dev, M, N, K, (int)tiles_m,      \
+        tiles_m * tiles_n, a_kfast, b_kfast, alpha_re, alpha_im, accumulate, ksplit
+#define B2_GEMM_LAUNCH(SPLIT, BKV, STV)                                                           \
+    contract_gemm_c128_kernel<SPLIT, BKV, STV><<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(B2_GEMM_ARGS)
+#define B2_GEMM3M_LAUNCH(SPLIT, BNV)                                                              \
+    contract_gemm3m_c128_kernel<SPLIT, BNV><<<grid, BNV * 4, smem, (cudaStream_t)stream>>>(B2_GEMM_ARGS)
+    if (three_m) {
+        if (bn == 64) { if (ksplit > 1) B2_GEMM3M_LAUNCH(true, 64); else B2_GEMM3M_LAUNCH(false, 64); }
+        else          { if (ksplit > 1) B2_GEMM3M_LAUNCH(true, 32); else B2_GEMM3M_LAUNCH(false, 32); }
+    } else if (BK == 16) {
+        if (ksplit > 1) B2_GEMM_LAUNCH(true, 16, 3); else B2_GEMM_LAUNCH(false, 16, 3);
     } else {
-        if (ksplit > 1) B2_GEMM_LAUNCH(true, 8, 4, ksplit); else B2_GEMM_LAUNCH(false, 8, 4, 1);
+        if (ksplit > 1) B2_GEMM_LAUNCH(true, 8, 4); else B2_GEMM_LAUNCH(false, 8, 4);
     }
 #undef B2_GEMM_LAUNCH
+#undef B2_GEMM3M_LAUNCH
+#undef B2_GEMM_ARGS
     return check_launch("b2_contract_gemm");
 }
