@@ -23,7 +23,7 @@ LIB = os.path.join(LIBDIR, "liboptyx_b200.so")
 STAMP = os.path.join(LIBDIR, "liboptyx_b200.stamp")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["abi.cu", "leaf_build.cu", "contract_direct.cu", "contract_gemm.cu", "contract_gemm_c64.cu",
+SOURCES = ["abi.cu", "leaf_build.cu", "contract_direct.cu", "contract_gemm.cu", "contract_gemm_ws.cu", "contract_gemm_c64.cu",
            "contract_ctile.cu", "contract_fma.cu", "contract_small.cu", "permanent.cu", "probs.cu",
            "compact.cu", "plan_runner.cu", "planner_native.cu", "compress.cu"]
 NVCC_FLAGS = [

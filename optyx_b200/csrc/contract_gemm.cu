@@ -75,7 +75,8 @@ __device__ __forceinline__ void gather_chunk(double2* dst, const double2* __rest
     static_assert(P >= 1 && (ROWS * BK) % THREADS == 0, "tile / thread count mismatch");
     const char* b = reinterpret_cast<const char*>(base);
     if (kfast) {
-        constexpr int LOGBK = BK == 16 ? 4 : 3;
+        constexpr int LOGBK = BK == 64 ? 6 : BK == 32 ? 5 : BK == 16 ? 4 : 3;
+        static_assert(BK == 8 || BK == 16 || BK == 32 || BK == 64, "BK");
         const int j = (tid & 3) | ((tid >> 1) & (BK - 4));
         const int i0 = ((tid >> 2) & 1) | ((tid >> (LOGBK + 1)) << 1);
         const char* src = b + k_off[j];
@@ -444,6 +445,421 @@ contract_gemm3m_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doubl
     }
 }
 
+// ---- thin pairs: the whole M x N extent fits one small tile (<= 32 x 32) and the
+// reduction is long (the closing pairs of a sliced amplitude network: two big
+// intermediates that share almost all of their modes, e.g. (batch 2, 16 x 16,
+// K = 2^19)).  A 64 x 64 tile would be 1/16 full -- 16x wasted gathers and DMMAs
+// (cfg4, r01 kernel: 1959 us for 82 us of HBM traffic).  Here the tile is (8T) x (8T),
+// T = 1 | 2 | 4, K chunks of 1024 / (16 T) reduction values, the reduction range is split
+// over enough CTAs to fill the GPU, and inside a CTA the 4 warps split the k4 steps of
+// every chunk (each warp accumulates the full tile with the 3M scheme; one shared-
+// memory reduction at the end, then one atomic add per output and CTA).  HBM-bound.
+template <int T> struct thin_cfg {
+    static constexpr int ROWS = 8 * T, BK = T == 4 ? 32 : 64, PITCH_T = ROWS + 2;
+    static constexpr int STAGES = 3, THREADS = 128;
+};
+template <int T>
+struct thin_smem {
+    using cfg = thin_cfg<T>;
+    double2 a[cfg::STAGES][cfg::BK][cfg::PITCH_T];
+    double2 b[cfg::STAGES][cfg::BK][cfg::PITCH_T];
+    long long row_a[cfg::ROWS], row_c[cfg::ROWS], col_b[cfg::ROWS], col_c[cfg::ROWS];
+    long long k_a[cfg::STAGES][cfg::BK], k_b[cfg::STAGES][cfg::BK];
+};
+
+template <int T>
+__global__ void __launch_bounds__(128, 2)
+contract_gemm_thin_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
+                          const double2* __restrict__ B, double2* __restrict__ Cout,
+                          long long M, long long N, long long K, int a_kfast, int b_kfast,
+                          double alpha_re, double alpha_im, int ksplit) {
+    using cfg = thin_cfg<T>;
+    constexpr int BK = cfg::BK, STAGES = cfg::STAGES, THREADS = cfg::THREADS, ROWS = cfg::ROWS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    thin_smem<T>& sm = *reinterpret_cast<thin_smem<T>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+    const long long batch_id = blockIdx.x / ksplit;
+    const int split = (int)(blockIdx.x % ksplit);
+    long long ba, bb, bc;
+    decode3(batch_id, g, 0, g.n_batch, ba, bb, bc);
+    A += ba; B += bb; Cout += bc;
+    if (tid < ROWS) {
+        long long oa, ob, oc;
+        decode3(tid < M ? tid : 0, g, f_m, g.n_m, oa, ob, oc);
+        sm.row_a[tid] = oa * 16; sm.row_c[tid] = oc;
+    } else if (tid < 2 * ROWS) {
+        const int t = tid - ROWS;
+        long long oa, ob, oc;
+        decode3(t < N ? t : 0, g, f_n, g.n_n, oa, ob, oc);
+        sm.col_b[t] = ob * 16; sm.col_c[t] = oc;
+    }
+    const int all_chunks = (int)((K + BK - 1) / BK);
+    const int per_split = (all_chunks + ksplit - 1) / ksplit;
+    const int c_begin = split * per_split;
+    const int nchunks = all_chunks - c_begin < per_split
+                            ? (all_chunks - c_begin > 0 ? all_chunks - c_begin : 0) : per_split;
+    auto decode_k = [&](int chunk) {
+        if (tid < BK) {
+            unsigned k = (unsigned)(c_begin + chunk) * BK + (unsigned)tid;
+            if ((long long)k >= K) k = 0;
+            long long oa = 0, ob = 0;
+            for (int m = 0; m < g.n_k; ++m) {
+                const unsigned d = (unsigned)g.dim[f_k + m];
+                const unsigned q = k / d, i = k - q * d;
+                k = q;
+                oa += (long long)i * g.sa[f_k + m];
+                ob += (long long)i * g.sb[f_k + m];
+            }
+            sm.k_a[chunk % STAGES][tid] = oa * 16;
+            sm.k_b[chunk % STAGES][tid] = ob * 16;
+        }
+    };
+    auto issue = [&](int chunk) {
+        const int st = chunk % STAGES;
+        const long long kleft = K - (long long)(c_begin + chunk) * BK;
+        const int kvalid = kleft < BK ? (int)kleft : BK;
+        gather_chunk<ROWS, BK, THREADS, cfg::PITCH_T>(&sm.a[st][0][0], A, sm.row_a, sm.k_a[st], tid,
+                                                       a_kfast != 0, kvalid);
+        gather_chunk<ROWS, BK, THREADS, cfg::PITCH_T>(&sm.b[st][0][0], B, sm.col_b, sm.k_b[st], tid,
+                                                       b_kfast != 0, kvalid);
+    };
+    for (int c = 0; c < STAGES - 1; ++c) if (c < nchunks) decode_k(c);
+    __syncthreads();
+    for (int c = 0; c < STAGES - 1; ++c) {
+        if (c < nchunks) issue(c);
+        cp_async_commit();
+    }
+    double p1[T][T][2], p2[T][T][2], p3[T][T][2];
+    #pragma unroll
+    for (int r = 0; r < T; ++r)
+        #pragma unroll
+        for (int q = 0; q < T; ++q)
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const int nxt = c + STAGES - 1;
+        if (nxt < nchunks) decode_k(nxt);
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (nxt < nchunks) issue(nxt);
+        cp_async_commit();
+        const int st = c % STAGES;
+        #pragma unroll
+        for (int s4 = 0; s4 < BK / 16; ++s4) {              // this warp's k4 steps of the chunk
+            const int k4 = (s4 * 4 + warp) * 4;
+            double2 af[T], bf[T];
+            double as[T], bs[T];
+            #pragma unroll
+            for (int r = 0; r < T; ++r) { af[r] = sm.a[st][k4 + fk][r * 8 + frow]; as[r] = af[r].x + af[r].y; }
+            #pragma unroll
+            for (int q = 0; q < T; ++q) { bf[q] = sm.b[st][k4 + fk][q * 8 + frow]; bs[q] = bf[q].x + bf[q].y; }
+            #pragma unroll
+            for (int r = 0; r < T; ++r)
+                #pragma unroll
+                for (int q = 0; q < T; ++q) dmma884(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
+            #pragma unroll
+            for (int r = 0; r < T; ++r)
+                #pragma unroll
+                for (int q = 0; q < T; ++q) dmma884(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
+            #pragma unroll
+            for (int r = 0; r < T; ++r)
+                #pragma unroll
+                for (int q = 0; q < T; ++q) dmma884(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                        // the ring is free: reuse it
+    // cross-warp reduction: red[warp][tile element][re, im]
+    double2* red = reinterpret_cast<double2*>(&sm.a[0][0][0]);
+    #pragma unroll
+    for (int r = 0; r < T; ++r)
+        #pragma unroll
+        for (int q = 0; q < T; ++q)
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = r * 8 + frow, j = q * 8 + fk * 2 + h;
+                double2 v;
+                v.x = p1[r][q][h] - p2[r][q][h];
+                v.y = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
+                red[warp * ROWS * ROWS + i * ROWS + j] = v;
+            }
+    __syncthreads();
+    for (int e = tid; e < ROWS * ROWS; e += THREADS) {
+        const int i = e / ROWS, j = e % ROWS;
+        if (i >= M || j >= N) continue;
+        double re = 0.0, im = 0.0;
+        #pragma unroll
+        for (int w = 0; w < 4; ++w) { const double2 v = red[w * ROWS * ROWS + e]; re += v.x; im += v.y; }
+        double2* dst = Cout + sm.row_c[i] + sm.col_c[j];
+        atomicAdd(&dst->x, alpha_re * re - alpha_im * im);
+        atomicAdd(&dst->y, alpha_re * im + alpha_im * re);
+    }
+}
+
+template <int T>
+static int launch_thin_t(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+                         long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
+                         double ai, cudaStream_t s) {
+    using cfg = thin_cfg<T>;
+    const int smem = (int)sizeof(thin_smem<T>);
+    static b2::once_flags attr_set;
+    if (!b2::is_done(attr_set)) {
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_thin_kernel<T>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(thin): smem attr: %s", cudaGetErrorString(e)); return 1; }
+        b2::mark_done(attr_set);
+    }
+    const long long chunks = (K + cfg::BK - 1) / cfg::BK;
+    long long ksplit = (4ll * num_sms() + Bt - 1) / Bt;      // ~2 waves of 2 CTAs per SM
+    if (ksplit > chunks / 8) ksplit = chunks / 8;            // >= 8 chunks per CTA
+    if (ksplit < 1) ksplit = 1;
+    if (Bt * ksplit > 2147483647ll) { set_error("b2_contract_gemm(thin): grid too large"); return 1; }
+    contract_gemm_thin_kernel<T><<<(unsigned)(Bt * ksplit), cfg::THREADS, smem, s>>>(
+        g, (const double2*)a, (const double2*)b, (double2*)c, M, N, K, a_kfast, b_kfast, ar, ai,
+        (int)ksplit);
+    return check_launch("b2_contract_gemm(thin)");
+}
+
+// ---- short reductions (16 <= K <= 64): A-stationary persistent kernel.
+// With a reduction this short a 64 x 64 tile is 4 K-chunks of work behind a fixed cost
+// (row / column decode, a cold cp.async ring, the scatter of the tile): measured
+// ~10 us of overhead per CTA next to 8 - 17 us of DMMA work (cfg4: (4,32768,1024,64) at
+// 60 % of the FP64 pipe, (2,65536,256,32) at 44 %, the N <= 32 pairs on the C-tiled kernel
+// at 9 - 35 %).  Here ONE CTA per SM walks a list of jobs = (batch, 64-row panel, range of
+// 32-column panels).  The whole 64 x K panel of A is gathered ONCE per job and stays in
+// shared memory while the 32 x K panels of B stream through a double buffer; the next
+// job's A panel and the next step's B panel are in flight while the current 64 x 32
+// block is multiplied (8 warps, warp tile 16 x 16, 3M scheme) and scattered, so there is
+// no cold start after the first job.  All reduction offsets are decoded once per CTA.
+constexpr int PK_THREADS = 256, PK_BN = 32, PK_KMAX = 64, PK_PA = 66, PK_PB = 34;
+struct pk_smem {
+    double2 a[2][PK_KMAX][PK_PA];
+    double2 b[2][PK_KMAX][PK_PB];
+    // tables are written one step ahead while slower warps may still scatter the previous
+    // step's block: three generations
+    long long row_a[3][BM], row_c[3][BM];
+    long long col_b[3][PK_BN], col_c[3][PK_BN];
+    long long k_a[PK_KMAX], k_b[PK_KMAX];
+};
+
+// 32-bit mixed-radix decode (group extents < 2^31)
+__device__ __forceinline__ void decode3_u32(unsigned flat, const b2_gemm_modes& g, int first, int count,
+                                            long long& oa, long long& ob, long long& oc) {
+    oa = ob = oc = 0;
+    for (int m = 0; m < count; ++m) {
+        const unsigned d = (unsigned)g.dim[first + m];
+        const unsigned q = flat / d, i = flat - q * d;
+        flat = q;
+        oa += (long long)i * g.sa[first + m];
+        ob += (long long)i * g.sb[first + m];
+        oc += (long long)i * g.sc[first + m];
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+contract_gemm_pk_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
+                             const double2* __restrict__ B, double2* __restrict__ Cout,
+                             int M, int N, int K, int tiles_m, int tiles_n, int nsplit,
+                             long long jobs, int a_kfast, int b_kfast, double alpha_re,
+                             double alpha_im, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pk_smem& sm = *reinterpret_cast<pk_smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+    const int kchunks = (K + 15) >> 4, k4steps = (K + 3) >> 2;
+    const int per_split = (tiles_n + nsplit - 1) / nsplit;
+
+    if (tid < PK_KMAX) {                                   // reduction offsets: once per CTA
+        unsigned k = tid < K ? (unsigned)tid : 0u;
+        long long oa = 0, ob = 0;
+        for (int m = 0; m < g.n_k; ++m) {
+            const unsigned d = (unsigned)g.dim[f_k + m];
+            const unsigned q = k / d, i = k - q * d;
+            k = q;
+            oa += (long long)i * g.sa[f_k + m];
+            ob += (long long)i * g.sb[f_k + m];
+        }
+        sm.k_a[tid] = oa * 16; sm.k_b[tid] = ob * 16;
+    }
+    // job -> (batch, row panel, first / last column panel)
+    auto job_info = [&](long long job, long long& batch, int& tm, int& n_first, int& n_last) {
+        const int sp = (int)(job % nsplit);
+        const long long r = job / nsplit;
+        tm = (int)(r % tiles_m);
+        batch = r / tiles_m;
+        n_first = sp * per_split;
+        n_last = n_first + per_split < tiles_n ? n_first + per_split : tiles_n;
+    };
+    // tables of a job's row panel (threads 64..127) -- batch offsets folded in
+    auto rows_of = [&](long long batch, int tm, int buf) {
+        if (tid >= 64 && tid < 128) {
+            const int t = tid - 64;
+            long long ba, bb, bc, oa, ob, oc;
+            decode3_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
+            const int m = tm * BM + t;
+            decode3_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
+            sm.row_a[buf][t] = (ba + oa) * 16; sm.row_c[buf][t] = bc + oc;
+        }
+    };
+    // tables of one column panel (threads 0..31)
+    auto cols_of = [&](long long batch, int tn, int buf) {
+        if (tid < PK_BN) {
+            long long ba, bb, bc, oa, ob, oc;
+            decode3_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
+            const int n = tn * PK_BN + tid;
+            decode3_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
+            sm.col_b[buf][tid] = (bb + ob) * 16; sm.col_c[buf][tid] = oc;
+        }
+    };
+    auto load_a = [&](int buf, int rbuf) {
+        for (int c = 0; c < kchunks; ++c) {
+            const int kvalid = K - c * 16 < 16 ? K - c * 16 : 16;
+            gather_chunk<BM, 16, PK_THREADS, PK_PA>(&sm.a[buf][c * 16][0], A, sm.row_a[rbuf],
+                                                    sm.k_a + c * 16, tid, a_kfast != 0, kvalid);
+        }
+    };
+    auto load_b = [&](int buf, int cbuf) {
+        for (int c = 0; c < kchunks; ++c) {
+            const int kvalid = K - c * 16 < 16 ? K - c * 16 : 16;
+            gather_chunk<PK_BN, 16, PK_THREADS, PK_PB>(&sm.b[buf][c * 16][0], B, sm.col_b[cbuf],
+                                                       sm.k_b + c * 16, tid, b_kfast != 0, kvalid);
+        }
+    };
+
+    long long job = blockIdx.x;
+    if (job >= jobs) return;
+    long long batch; int tm, n_first, n_last;
+    job_info(job, batch, tm, n_first, n_last);
+    rows_of(batch, tm, 0);
+    cols_of(batch, n_first, 0);
+    __syncthreads();
+    load_a(0, 0);
+    load_b(0, 0);
+    cp_async_commit();
+
+    const int frow = lane >> 2, fk = lane & 3;
+    int jbuf = 0, rgen = 0, cgen = 0, tn = n_first;      // A buffer; table generations (mod 3)
+    for (long long step = 0;; ++step) {
+        const int sbuf = (int)(step & 1);
+        const int rnext = rgen == 2 ? 0 : rgen + 1, cnext = cgen == 2 ? 0 : cgen + 1;
+        // ---- what comes next: the next column panel of this job, or the next job
+        long long nxt_job = job, nxt_batch = batch;
+        int nxt_tm = tm, nxt_tn = tn + 1, nxt_first = n_first, nxt_last = n_last;
+        bool new_job = false, have_next = true;
+        if (nxt_tn >= n_last) {
+            nxt_job = job + gridDim.x;
+            if (nxt_job < jobs) {
+                job_info(nxt_job, nxt_batch, nxt_tm, nxt_first, nxt_last);
+                nxt_tn = nxt_first;
+                new_job = true;
+            } else {
+                have_next = false;
+            }
+        }
+        if (have_next) {
+            if (new_job) rows_of(nxt_batch, nxt_tm, rnext);
+            cols_of(nxt_batch, nxt_tn, cnext);
+        }
+        __syncthreads();               // next tables visible; buffers of step - 1 are free
+        if (have_next) {
+            if (new_job) load_a(jbuf ^ 1, rnext);
+            load_b(sbuf ^ 1, cnext);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();            // this step's panels (own copies) have landed
+        __syncthreads();               // ... and everyone else's
+
+        double p1[2][2][2], p2[2][2][2], p3[2][2][2];
+        #pragma unroll
+        for (int r = 0; r < 2; ++r)
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
+        const double2* ap = &sm.a[jbuf][fk][wm * 16 + frow];
+        const double2* bp = &sm.b[sbuf][fk][wn * 16 + frow];
+        #pragma unroll 4
+        for (int s4 = 0; s4 < k4steps; ++s4) {
+            double2 af[2], bf[2];
+            double as[2], bs[2];
+            #pragma unroll
+            for (int r = 0; r < 2; ++r) { af[r] = ap[s4 * 4 * PK_PA + r * 8]; as[r] = af[r].x + af[r].y; }
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) { bf[q] = bp[s4 * 4 * PK_PB + q * 8]; bs[q] = bf[q].x + bf[q].y; }
+            #pragma unroll
+            for (int r = 0; r < 2; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
+            #pragma unroll
+            for (int r = 0; r < 2; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
+            #pragma unroll
+            for (int r = 0; r < 2; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) dmma884(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
+        }
+        // ---- scatter the 64 x 32 block through the C permutation
+        const int m0 = tm * BM, n0 = tn * PK_BN;
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = wm * 16 + r * 8 + frow;
+            if (m0 + i >= M) continue;
+            const long long ro = sm.row_c[rgen][i];
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = wn * 16 + q * 8 + fk * 2 + h;
+                    if (n0 + j >= N) continue;
+                    const double re = p1[r][q][h] - p2[r][q][h];
+                    const double im = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
+                    double2 v;
+                    v.x = alpha_re * re - alpha_im * im;
+                    v.y = alpha_re * im + alpha_im * re;
+                    double2* dst = Cout + ro + sm.col_c[cgen][j];
+                    if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
+            }
+        }
+        if (!have_next) break;
+        if (new_job) { job = nxt_job; batch = nxt_batch; tm = nxt_tm; n_first = nxt_first; n_last = nxt_last; jbuf ^= 1; rgen = rnext; }
+        tn = nxt_tn;
+        cgen = cnext;
+    }
+    cp_async_wait<0>();
+}
+
+static int launch_pk(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+                     long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
+                     double ai, int accumulate, cudaStream_t s) {
+    const int smem = (int)sizeof(pk_smem);
+    static b2::once_flags attr_set;
+    if (!b2::is_done(attr_set)) {
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_pk_c128_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(pk): smem attr: %s", cudaGetErrorString(e)); return 1; }
+        b2::mark_done(attr_set);
+    }
+    const int sms = num_sms();
+    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + PK_BN - 1) / PK_BN;
+    long long nsplit = 1;
+    if (Bt * tiles_m < 4ll * sms) {                       // few row panels: share their columns
+        nsplit = (4ll * sms + Bt * tiles_m - 1) / (Bt * tiles_m);
+        if (nsplit > tiles_n) nsplit = tiles_n;
+    }
+    const long long jobs = Bt * tiles_m * nsplit;
+    const long long grid = jobs < sms ? jobs : sms;
+    contract_gemm_pk_c128_kernel<<<(unsigned)grid, PK_THREADS, smem, s>>>(
+        g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
+        (int)tiles_n, (int)nsplit, jobs, a_kfast, b_kfast, ar, ai, accumulate);
+    return check_launch("b2_contract_gemm(pk)");
+}
+
 // ---- few outputs, very long reduction with many modes (the last pair of a sliced
 // amplitude network: <psi_left | psi_right> over 2^20 index values spread over 20
 // binary modes).  A tile of the DMMA kernel would be 1/4096 full; here every CTA takes a
@@ -553,6 +969,9 @@ int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, 
                  double ai, int accumulate, cudaStream_t s, bool& handled);
 int launch_gemm_c64(const b2_gemm_modes& g, const void* a_dev, const void* b_dev, void* c_dev,
                     double ar, double ai, int accumulate, cudaStream_t s);
+int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+                   long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
+                   double ai, int accumulate, cudaStream_t s, bool& handled);
 
 }  // namespace b2
 
@@ -597,7 +1016,11 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     // Measured (profiles/r02_shortk.md): from K = 16 on the 64x64 tiling is faster on
     // plain AND permuted layouts -- (2,16384,1024,32) of cfg4: 1336 -> 489 us
     static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 8;
-    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
+    static const bool use_pk = !getenv("B2_NO_PK");
+    // 16 <= K <= 64 with at least one full row panel: the A-stationary persistent kernel
+    const bool pk = use_pk && dtype == B2_C128 && k_total >= 16 && k_total <= PK_KMAX && m_total >= BM &&
+                    n_total >= 8 && m_total < (1ll << 31) && n_total < (1ll << 31) && b_total < (1ll << 31);
+    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled && !pk) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
         // classic 64x64 tiling below (4x4 register blocking per warp).
@@ -623,10 +1046,45 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
     const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
+    // many full tiles: the persistent warp-specialised kernel (B2_GEMM_WS = 0 | min tiles per SM)
+    {
+        static const int ws_min = getenv("B2_GEMM_WS") ? atoi(getenv("B2_GEMM_WS")) : 4;
+        const long long tiles64 = ((M + 63) / 64) * ((N + 63) / 64) * Bt;
+        if (ws_min > 0 && N >= 48 && K >= 16 && tiles64 >= (long long)ws_min * num_sms()) {
+            bool handled = false;
+            int st = launch_gemm_ws(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re,
+                                    alpha_im, accumulate, (cudaStream_t)stream, handled);
+            if (st != 0 || handled) return st;
+        }
+    }
+    if (pk) {
+        set_last_kernel("gemm_pk");
+        return launch_pk(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im,
+                         accumulate, (cudaStream_t)stream);
+    }
+    // thin pairs (M, N <= 32, long K): split-K over the whole GPU with a tile of their size
+    if (M <= 32 && N <= 32 && K >= 1024 && !getenv("B2_NO_THIN")) {
+        long long span = 0;
+        for (int i = 0; i < f_k; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
+        if (span + 1 == Bt * M * N || accumulate) {          // C is one dense block (zero fill)
+            if (!accumulate) {
+                cudaError_t e = cudaMemsetAsync(c_dev, 0, (size_t)(Bt * M * N) * sizeof(double2),
+                                                (cudaStream_t)stream);
+                if (e != cudaSuccess) { set_error("b2_contract_gemm: memset: %s", cudaGetErrorString(e)); return 1; }
+            }
+            set_last_kernel("gemm_thin");
+            const long long mx = M > N ? M : N;
+            if (mx <= 8)
+                return launch_thin_t<1>(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im, (cudaStream_t)stream);
+            if (mx <= 16)
+                return launch_thin_t<2>(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im, (cudaStream_t)stream);
+            return launch_thin_t<4>(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im, (cudaStream_t)stream);
+        }
+    }
     // long reductions: 3M complex multiplication (3 DMMAs per complex tile product, K chunk
     // 16); short ones: the 4-product kernel with chunk 8 / 4 stages.
     // (B2_GEMM_3M = 0 | 32 | 64: off / N tile of the 3M kernel; B2_GEMM_BK: experiment knobs.)
-    static const int n3m = getenv("B2_GEMM_3M") ? atoi(getenv("B2_GEMM_3M")) : 64;
+    static const int n3m = getenv("B2_GEMM_3M") ? atoi(getenv("B2_GEMM_3M")) : 32;
     static const int force_bk = getenv("B2_GEMM_BK") ? atoi(getenv("B2_GEMM_BK")) : 0;
     const bool three_m = (n3m == 32 || n3m == 64) && K >= 128;
     const int bn = three_m ? n3m : BN;

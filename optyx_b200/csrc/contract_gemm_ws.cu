@@ -1,0 +1,349 @@
+// Piece (2b), complex128, the many-tile case: persistent, warp-specialised fused
+// index-permute + complex GEMM on the FP64 tensor pipe.
+//
+//   C[b, m, n] (+)= alpha * sum_k A[b, m, k] * B[b, k, n]
+//
+// (reference: the transpose + tensordot/zgemm quimb/cotengra run per tree node, call
+// sites optyx/core/backends.py:514, 539-545.)
+//
+// Why another kernel: in the barrier-per-chunk kernels of contract_gemm.cu every warp both
+// gathers and multiplies, in lock step.  ncu on cfg4's pairs (profiles/r02_*): the DMMA
+// pipe idles while all warps compute gather addresses, wait on the block barrier, decode
+// reduction offsets or scatter a tile; a short reduction (K <= 128) pays the cold start of
+// the cp.async ring and the row / column decode once per 64 x 64 tile (~10 us next to
+// 8 - 17 us of math).  Here:
+//   * ONE CTA per SM, persistent: it walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+//     (grouped raster order, so that the tiles in flight share operand panels in L2);
+//   * a PRODUCER warp owns everything that is not math: per-tile row / column offset
+//     tables, reduction offsets (a two-level table: K = low x high, the low table lives
+//     in shared memory, the high offset is recomputed only when the low index wraps),
+//     and all cp.async gathers into a 5-stage ring; stages are handed over with
+//     mbarriers (cp.async.mbarrier.arrive), it runs ahead ACROSS tile boundaries, so
+//     the ring never drains between tiles;
+//   * 8 MMA warps (2 x 4, warp tile 32 x 16) only wait for a stage, issue LDS + DMMA
+//     (3M complex multiplication: P1 = ar*br, P2 = ai*bi, P3 = (ar+ai)(br+bi)), release
+//     the stage, and scatter their part of the tile at its end -- each warp on its own
+//     clock, so one warp's epilogue overlaps the others' math.
+#include <stdlib.h>
+#include "b2_common.cuh"
+
+namespace b2 {
+
+namespace ws {
+
+constexpr int BM = 64, BN = 64, BK = 16, PITCH = 66, STAGES = 5;
+constexpr int MMA_WARPS = 8, THREADS = (MMA_WARPS + 1) * 32;
+constexpr int TAB_GEN = 4;                     // generations of the per-tile C tables
+constexpr int KLOW_MAX = 1024;                 // entries of the low reduction-offset table
+
+struct smem_t {
+    double2 a[STAGES][BK][PITCH];
+    double2 b[STAGES][BK][PITCH];
+    long long row_c[TAB_GEN][BM], col_c[TAB_GEN][BN];      // read by the MMA warps
+    long long row_a[2][BM], col_b[2][BN];                  // producer only (byte offsets)
+    long long klow_a[KLOW_MAX], klow_b[KLOW_MAX];          // byte offsets of k % klow
+    uint64_t full[STAGES], empty[STAGES], tab_free[TAB_GEN];
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(s32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s32(bar)) : "memory");
+}
+// the barrier receives one arrival once every cp.async this thread issued so far has landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp16(uint32_t smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void decode_u32(unsigned flat, const b2_gemm_modes& g, int first, int count,
+                                           long long& oa, long long& ob, long long& oc) {
+    oa = ob = oc = 0;
+    for (int m = 0; m < count; ++m) {
+        const unsigned d = (unsigned)g.dim[first + m];
+        const unsigned q = flat / d, i = flat - q * d;
+        flat = q;
+        oa += (long long)i * g.sa[first + m];
+        ob += (long long)i * g.sb[first + m];
+        oc += (long long)i * g.sc[first + m];
+    }
+}
+
+constexpr int RASTER_GM = 16;
+__device__ __forceinline__ void raster(long long tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const long long per_group = (long long)RASTER_GM * tiles_n;
+    const int group = (int)(tile / per_group);
+    const int first_m = group * RASTER_GM;
+    const int gm = tiles_m - first_m < RASTER_GM ? tiles_m - first_m : RASTER_GM;
+    const int r = (int)(tile - (long long)group * per_group);
+    tm = first_m + r % gm;
+    tn = r / gm;
+}
+
+// One operand tile chunk (64 rows x 16 k) by the 32 producer lanes: 32 copies per lane.
+//   rows contiguous in the operand: a lane owns 2 rows (lane, lane + 32), walks the 16 k
+//   K contiguous: a quarter warp = 4 consecutive k x 2 rows (see contract_gemm.cu)
+__device__ __forceinline__ void gather64(uint32_t dst, const char* base, const long long* row_off,
+                                         const long long* klow, int klo, long long khi, int lane,
+                                         bool kfast, int kvalid) {
+    if (kfast) {
+        const int j = (lane & 3) | ((lane >> 1) & 12);
+        const int i0 = (lane >> 2) & 1;
+        const char* src = base + klow[klo + j] + khi;
+        const int bytes = j < kvalid ? 16 : 0;
+        const uint32_t d = dst + (uint32_t)(j * PITCH + i0) * 16u;
+        #pragma unroll 8
+        for (int p = 0; p < 32; ++p) cp16(d + (uint32_t)p * 32u, src + row_off[i0 + 2 * p], bytes);
+    } else {
+        const char* s0 = base + row_off[lane] + khi;
+        const char* s1 = base + row_off[lane + 32] + khi;
+        const uint32_t d = dst + (uint32_t)lane * 16u;
+        #pragma unroll 8
+        for (int j = 0; j < BK; ++j) {
+            const long long ko = klow[klo + j];
+            const int bytes = j < kvalid ? 16 : 0;
+            cp16(d + (uint32_t)(j * PITCH) * 16u, s0 + ko, bytes);
+            cp16(d + (uint32_t)(j * PITCH + 32) * 16u, s1 + ko, bytes);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
+                             const double2* __restrict__ B, double2* __restrict__ Cout, int M, int N,
+                             int K, int tiles_m, int tiles_n, long long total_tiles, int klow,
+                             int n_klow_modes, int a_kfast, int b_kfast, double alpha_re,
+                             double alpha_im, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const int nchunks = (K + BK - 1) / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 32); mbar_init(&sm.empty[s], MMA_WARPS); }
+        for (int t = 0; t < TAB_GEN; ++t) mbar_init(&sm.tab_free[t], MMA_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // low reduction-offset table: k_lo in [0, klow) over the first n_klow_modes K modes
+    // (entries up to the next multiple of the chunk are addressed by the zero-filled K tail)
+    const int klow_pad = (klow + BK - 1) / BK * BK < KLOW_MAX ? (klow + BK - 1) / BK * BK : KLOW_MAX;
+    for (int k = tid; k < klow_pad; k += THREADS) {
+        unsigned r = k < klow ? (unsigned)k : 0u;
+        long long oa = 0, ob = 0;
+        for (int m = 0; m < n_klow_modes; ++m) {
+            const unsigned d = (unsigned)g.dim[f_k + m];
+            const unsigned q = r / d, i = r - q * d;
+            r = q;
+            oa += (long long)i * g.sa[f_k + m];
+            ob += (long long)i * g.sb[f_k + m];
+        }
+        sm.klow_a[k] = oa * 16; sm.klow_b[k] = ob * 16;
+    }
+    __syncthreads();
+
+    if (warp == MMA_WARPS) {
+        // ============================ producer warp ============================
+        const char* Ab = reinterpret_cast<const char*>(A);
+        const char* Bb = reinterpret_cast<const char*>(B);
+        long long chunk_seq = 0;                     // chunks issued so far (ring position)
+        int tcount = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const long long batch = tile / tiles_mn;
+            int tm, tn;
+            raster(tile - batch * tiles_mn, tiles_m, tiles_n, tm, tn);
+            const int gen = tcount % TAB_GEN, pg = tcount & 1;
+            // the C tables of generation `gen` are free once the MMA warps finished the
+            // tile that used them (TAB_GEN tiles ago)
+            if (tcount >= TAB_GEN) mbar_wait(&sm.tab_free[gen], (uint32_t)((tcount / TAB_GEN - 1) & 1));
+            long long ba, bb, bc;
+            decode_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = lane + 32 * h;
+                long long oa, ob, oc;
+                const int m = tm * BM + t;
+                decode_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
+                sm.row_a[pg][t] = (ba + oa) * 16; sm.row_c[gen][t] = bc + oc;
+                const int n = tn * BN + t;
+                decode_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
+                sm.col_b[pg][t] = (bb + ob) * 16; sm.col_c[gen][t] = oc;
+            }
+            __threadfence_block();
+            __syncwarp();
+            int klo = 0;                              // (chunk * 16) % klow
+            unsigned khi_idx = 0;                     // (chunk * 16) / klow
+            long long khi_a = 0, khi_b = 0;
+            for (int c = 0; c < nchunks; ++c, ++chunk_seq) {
+                const int st = (int)(chunk_seq % STAGES);
+                const uint32_t ph = (uint32_t)((chunk_seq / STAGES) & 1);
+                mbar_wait(&sm.empty[st], ph ^ 1u);   // passes at once on the first lap
+                const int kleft = K - c * BK;
+                const int kvalid = kleft < BK ? kleft : BK;
+                gather64(s32(&sm.a[st][0][0]), Ab, sm.row_a[pg], sm.klow_a, klo, khi_a, lane,
+                         a_kfast != 0, kvalid);
+                gather64(s32(&sm.b[st][0][0]), Bb, sm.col_b[pg], sm.klow_b, klo, khi_b, lane,
+                         b_kfast != 0, kvalid);
+                cp_async_arrive(&sm.full[st]);
+                klo += BK;
+                if (klo >= klow) {                    // klow is a multiple of 16 (or >= K)
+                    klo = 0;
+                    ++khi_idx;
+                    unsigned r = khi_idx;
+                    khi_a = khi_b = 0;
+                    for (int m = n_klow_modes; m < g.n_k; ++m) {
+                        const unsigned d = (unsigned)g.dim[f_k + m];
+                        const unsigned q = r / d, i = r - q * d;
+                        r = q;
+                        khi_a += (long long)i * g.sa[f_k + m];
+                        khi_b += (long long)i * g.sb[f_k + m];
+                    }
+                    khi_a *= 16; khi_b *= 16;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else {
+        // ============================== MMA warps ==============================
+        const int wm = warp >> 2, wn = warp & 3;
+        const int frow = lane >> 2, fk = lane & 3;
+        long long chunk_seq = 0;
+        int tcount = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const long long batch = tile / tiles_mn;
+            int tm, tn;
+            raster(tile - batch * tiles_mn, tiles_m, tiles_n, tm, tn);
+            double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+            #pragma unroll
+            for (int r = 0; r < 4; ++r)
+                #pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
+            for (int c = 0; c < nchunks; ++c, ++chunk_seq) {
+                const int st = (int)(chunk_seq % STAGES);
+                mbar_wait(&sm.full[st], (uint32_t)((chunk_seq / STAGES) & 1));
+                const double2* ap = &sm.a[st][fk][wm * 32 + frow];
+                const double2* bp = &sm.b[st][fk][wn * 16 + frow];
+                #pragma unroll
+                for (int k4 = 0; k4 < BK; k4 += 4) {
+                    double2 af[4], bf[2];
+                    double as[4], bs[2];
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r) af[r] = ap[k4 * PITCH + r * 8];
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q) bf[q] = bp[k4 * PITCH + q * 8];
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r) as[r] = af[r].x + af[r].y;
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q) bs[q] = bf[q].x + bf[q].y;
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        #pragma unroll
+                        for (int q = 0; q < 2; ++q) dmma(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        #pragma unroll
+                        for (int q = 0; q < 2; ++q) dmma(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
+                    #pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        #pragma unroll
+                        for (int q = 0; q < 2; ++q) dmma(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[st]);
+            }
+            // ---- scatter this warp's 32 x 16 part of the tile through the C permutation
+            const int gen = tcount % TAB_GEN;
+            const int m0 = tm * BM, n0 = tn * BN;
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = wm * 32 + r * 8 + frow;
+                if (m0 + i >= M) continue;
+                const long long ro = sm.row_c[gen][i];
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = wn * 16 + q * 8 + fk * 2 + h;
+                        if (n0 + j >= N) continue;
+                        const double re = p1[r][q][h] - p2[r][q][h];
+                        const double im = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
+                        double2 v;
+                        v.x = alpha_re * re - alpha_im * im;
+                        v.y = alpha_re * im + alpha_im * re;
+                        double2* dst = Cout + ro + sm.col_c[gen][j];
+                        if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                        *dst = v;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tab_free[gen]);
+        }
+    }
+}
+
+}  // namespace ws
+
+// returns handled = false when the pair does not fit this kernel (the caller falls
+// back to the barrier-per-chunk kernels of contract_gemm.cu)
+int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+                   long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
+                   double ai, int accumulate, cudaStream_t s, bool& handled) {
+    using namespace ws;
+    handled = false;
+    if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31) || Bt >= (1ll << 31)) return 0;
+    // two-level reduction offsets: the low table covers the leading K modes, up to
+    // KLOW_MAX entries; with more than one level its extent must be a multiple of the
+    // K chunk so that a chunk never straddles two high indices
+    const int f_k = g.n_batch + g.n_m + g.n_n;
+    long long klow = 1;
+    int n_low = 0;
+    while (n_low < g.n_k && klow * g.dim[f_k + n_low] <= KLOW_MAX) klow *= g.dim[f_k + n_low++];
+    if (n_low < g.n_k && klow % BK != 0) {
+        // try a shorter prefix whose extent is a multiple of 16
+        while (n_low > 0 && klow % BK != 0) klow /= g.dim[f_k + --n_low];
+        if (n_low == 0 || klow % BK != 0) return 0;
+    }
+    const int sms = num_sms();
+    if (sms <= 0) return 1;
+    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const long long total = tiles_m * tiles_n * Bt;
+    const int smem = (int)sizeof(smem_t);
+    static b2::once_flags attr_set;
+    if (!b2::is_done(attr_set)) {
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_ws_c128_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(ws): smem attr: %s", cudaGetErrorString(e)); return 1; }
+        b2::mark_done(attr_set);
+    }
+    const long long grid = total < sms ? total : sms;
+    contract_gemm_ws_c128_kernel<<<(unsigned)grid, THREADS, smem, s>>>(
+        g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
+        (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate);
+    handled = true;
+    set_last_kernel("gemm_ws");
+    return check_launch("b2_contract_gemm(ws)");
+}
+
+}  // namespace b2
