@@ -38,6 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC, UNIT = "eval_diagrams_per_sec", "diagrams/s"
 FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profiles/r01_probe.json)
+THREE_M_VARIANTS = ("gemm_ws", "gemm3m", "gemm3m_splitk", "gemm_pk", "gemm_thin")
 CFG4_TARGET = float(2 ** 27)       # <= 2^27 elements (2 GiB complex128) per slice
 CFG4_MIN_SLICES = 32               # ... and >= 32 slices, so that 8 GPUs get >= 4 each
 
@@ -402,6 +403,7 @@ class Bench:
             for _ in range(3):
                 sess._launch(dom, zeros, 1.0 + 0j, 0, stream)
             dom_secs = self.timed(lambda: sess._launch(dom, zeros, 1.0 + 0j, 0, stream), max(steps, 5))
+            dom_variant = self.lib.b2_last_kernel().decode().split()[0]
             leaf_secs = self.timed(sess.build_leaves, max(steps, 20))
             clocks.hold_load(step_fn, torch.cuda.synchronize)
         per_step = secs / steps
@@ -421,7 +423,8 @@ class Bench:
             achieved, peak_val, unit = 8.0 * dom.macs / dom_secs / 1e12, FP64_PIPE_TFLOPS, "TFLOP/s"
         else:
             achieved, peak_val, unit = dom.bytes / dom_secs / 1e9, self.hbm, "GB/s"
-        kernel_sig = f"{dom.kernel}:{'x'.join(str(x) for x in dom.mnk)}"
+        kernel_sig = f"{dom_variant}:{'x'.join(str(x) for x in dom.mnk)}"
+        three_m = dom_variant in THREE_M_VARIANTS
         roofline = {
             "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak_val,
             "unit": unit, "frac": achieved / peak_val,
@@ -429,13 +432,22 @@ class Bench:
             "peak_source": ("FP64 DMMA peak measured on this pool (profiles/r01_probe.json)"
                             if tensor_bound else
                             "MEASURED_PEAKS.json hbm_gbs" if peaks() else "fallback 6650 GB/s"),
-            "kernel": f"b2_contract_{dom.kernel} ({'final step, ' if dom.final else ''}"
+            "kernel": f"b2_contract_{dom.kernel} [{dom_variant}] ({'final step, ' if dom.final else ''}"
                       f"(batch,M,N,K)={dom.mnk})",
             "kernel_signature": kernel_sig,
             "algorithmic_bytes_per_launch": dom.bytes, "launch_ms": dom_secs * 1e3,
             "macs_per_launch": dom.macs,
             "share_of_step": dom_secs * (plan.nslices / world if dom.per_slice else 1) / per_step,
         }
+        if tensor_bound and three_m:
+            # 3M complex multiplication: the kernel EXECUTES 6 flops per complex multiply-add
+            # on the FP64 pipe for the 8 algorithmic ones, so `frac` (algorithmic / pipe peak)
+            # can exceed 1; pipe_frac is what the tensor pipe itself is doing
+            roofline["executed_flops_per_launch"] = 6.0 * dom.macs
+            roofline["pipe_frac"] = 6.0 * dom.macs / dom_secs / 1e12 / FP64_PIPE_TFLOPS
+            roofline["note"] = ("3M complex multiplication (3 real DMMA products per complex product): "
+                                "achieved/frac count the 8 algorithmic flops per complex multiply-add "
+                                "(SURVEY.md 8(d)), pipe_frac the 6 executed ones")
         bound_s = plan_bound_seconds(plan, self.hbm, FP64_PIPE_TFLOPS) / (world if plan.sliced else 1)
         arena_bytes = plan.arena_elems * plan.dtype.itemsize * batch
         line = {

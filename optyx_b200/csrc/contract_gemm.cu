@@ -971,7 +971,7 @@ int launch_gemm_c64(const b2_gemm_modes& g, const void* a_dev, const void* b_dev
                     double ar, double ai, int accumulate, cudaStream_t s);
 int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                    long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
-                   double ai, int accumulate, cudaStream_t s, bool& handled);
+                   double ai, int accumulate, int min_tiles_per_sm, cudaStream_t s, bool& handled);
 
 }  // namespace b2
 
@@ -1007,9 +1007,37 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     if (dtype == B2_C64)      // tcgen05 kind::tf32, 3-product split precision (contract_gemm_c64.cu)
         return launch_gemm_c64(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
                                (cudaStream_t)stream);
-    long long m_total = 1, b_total = 1;
-    for (int i = 0; i < g.n_m; ++i) m_total *= g.dim[g.n_batch + i];
-    for (int i = 0; i < g.n_batch; ++i) b_total *= g.dim[i];
+    long long Bt = 1, M = 1, N = 1, K = 1;
+    {
+        int p = 0;
+        for (int i = 0; i < g.n_batch; ++i) Bt *= g.dim[p++];
+        for (int i = 0; i < g.n_m; ++i) M *= g.dim[p++];
+        for (int i = 0; i < g.n_n; ++i) N *= g.dim[p++];
+        for (int i = 0; i < g.n_k; ++i) K *= g.dim[p++];
+    }
+    if (Bt == 0 || M == 0 || N == 0) return 0;
+    const long long m_total = M, b_total = Bt;
+    // load direction: walk the group that is contiguous in the operand
+    auto min_stride = [&](const int64_t* s, int first, int count) {
+        long long best = (1ll << 62);
+        for (int i = 0; i < count; ++i)
+            if (g.dim[first + i] > 1 && s[first + i] > 0 && s[first + i] < best) best = s[first + i];
+        return best;
+    };
+    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
+    const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
+    const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
+    // enough tiles per SM: the persistent warp-specialised kernel (contract_gemm_ws.cu)
+    // (B2_GEMM_WS = 0: off, else the minimum number of tiles per SM)
+    {
+        static const int ws_min = getenv("B2_GEMM_WS") ? atoi(getenv("B2_GEMM_WS")) : 2;
+        if (ws_min > 0 && M >= 64 && N >= 8 && K >= 16) {
+            bool handled = false;
+            int st = launch_gemm_ws(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re,
+                                    alpha_im, accumulate, ws_min, (cudaStream_t)stream, handled);
+            if (st != 0 || handled) return st;
+        }
+    }
     const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
                                  2ll * num_sms() && k_total >= 256;
     // reductions up to ctile_kmax take the ctile kernel (B2_CTILE_KMAX: experiment knob).
@@ -1028,34 +1056,6 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
         int st = launch_ctile(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
                               (cudaStream_t)stream, handled);
         if (st != 0 || handled) return st;
-    }
-    long long Bt = 1, M = 1, N = 1, K = 1;
-    int p = 0;
-    for (int i = 0; i < g.n_batch; ++i) Bt *= g.dim[p++];
-    for (int i = 0; i < g.n_m; ++i) M *= g.dim[p++];
-    for (int i = 0; i < g.n_n; ++i) N *= g.dim[p++];
-    for (int i = 0; i < g.n_k; ++i) K *= g.dim[p++];
-    if (Bt == 0 || M == 0 || N == 0) return 0;
-    // load direction: walk the group that is contiguous in the operand
-    auto min_stride = [&](const int64_t* s, int first, int count) {
-        long long best = (1ll << 62);
-        for (int i = 0; i < count; ++i)
-            if (g.dim[first + i] > 1 && s[first + i] > 0 && s[first + i] < best) best = s[first + i];
-        return best;
-    };
-    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
-    const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
-    const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
-    // many full tiles: the persistent warp-specialised kernel (B2_GEMM_WS = 0 | min tiles per SM)
-    {
-        static const int ws_min = getenv("B2_GEMM_WS") ? atoi(getenv("B2_GEMM_WS")) : 4;
-        const long long tiles64 = ((M + 63) / 64) * ((N + 63) / 64) * Bt;
-        if (ws_min > 0 && N >= 48 && K >= 16 && tiles64 >= (long long)ws_min * num_sms()) {
-            bool handled = false;
-            int st = launch_gemm_ws(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re,
-                                    alpha_im, accumulate, (cudaStream_t)stream, handled);
-            if (st != 0 || handled) return st;
-        }
     }
     if (pk) {
         set_last_kernel("gemm_pk");

@@ -316,35 +316,61 @@ contract_gemm_c64_kernel(const __grid_constant__ b2_gemm_modes g, const float2* 
         constexpr uint32_t RAW_A_STAGE = G4_BM * (G4_KC + 1) * 8;
         const int b_r0 = b_kfast ? tid / G4_KG : tid % NT, b_rstep = b_kfast ? G4_CONV / G4_KG : 0;
         const int b_p0 = b_kfast ? tid % G4_KG : (tid / NT) * B_ITEMS, b_pstep = b_kfast ? 0 : 1;
-        const int mrem = (int)(M - m0 < G4_BM ? M - m0 : G4_BM), nrem = (int)(N - n0 < NT ? N - n0 : NT);
         const uint32_t raw0 = g4_smem_u32(&sm.raw[0][0][tid]);
         constexpr uint32_t RAW_SLOT = G4_CONV * 8, RAW_STAGE = g4_smem<NT>::LOADS * RAW_SLOT;
 
-        // asynchronous gather of chunk c through the per-mode strides
+        // asynchronous gather of chunk c through the per-mode strides.  Per copy: one
+        // table load + one 64-bit add (r01: ~28 instructions of index arithmetic and
+        // predicates per copy made the converter warps issue-bound -- tensor pipe 28 %
+        // active).  Rows / columns beyond the edge read row 0 (valid memory, never
+        // stored); only the K tail is zero-filled.
         auto issue = [&](int c) {
             if (c < nchunks) {
                 const int kt = c & 3;
                 const uint32_t dst = raw0 + (uint32_t)(c % G4_RAW) * RAW_STAGE;
+                const uint32_t dst_a = raw_a0 + (uint32_t)(c % G4_RAW) * RAW_A_STAGE;
                 const long long kleft = K - (long long)c * G4_KC;
                 const int krem = (int)(kleft < G4_KC ? kleft : G4_KC);
-                #pragma unroll
-                for (int p = 0; p < A_LOADS; ++p) {
-                    const int r = c_r0 + p * c_rstep, k = c_k0 + p * c_kstep;
-                    const int bytes = (r < mrem && k < krem) ? 8 : 0;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                     raw_a0 + (uint32_t)(c % G4_RAW) * RAW_A_STAGE + (uint32_t)p * a_dstep),
-                                 "l"(A + (sm.row_a[r] + sm.k_a[kt][k])), "r"(bytes));
-                }
-                #pragma unroll
-                for (int p = 0; p < B_ITEMS; ++p) {
-                    const int n = b_r0 + p * b_rstep, kp = b_p0 + p * b_pstep;
-                    const long long co = sm.col_b[n];
+                if (a_kfast) {
+                    const float2* src = A + sm.k_a[kt][c_k0];
+                    const int bytes = c_k0 < krem ? 8 : 0;
                     #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int bytes = (n < nrem && 2 * kp + h < krem) ? 8 : 0;
+                    for (int p = 0; p < A_LOADS; ++p)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
-                                         dst + (uint32_t)(2 * p + h) * RAW_SLOT),
-                                     "l"(B + (co + sm.k_b[kt][2 * kp + h])), "r"(bytes));
+                                         dst_a + (uint32_t)p * a_dstep),
+                                     "l"(src + sm.row_a[c_r0 + p * (G4_CONV / G4_KC)]), "r"(bytes));
+                } else {
+                    const float2* src = A + sm.row_a[c_r0];
+                    #pragma unroll
+                    for (int p = 0; p < A_LOADS; ++p) {
+                        const int k = c_k0 + p * (G4_CONV / G4_BM);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                         dst_a + (uint32_t)p * a_dstep),
+                                     "l"(src + sm.k_a[kt][k]), "r"(k < krem ? 8 : 0));
+                    }
+                }
+                if (b_kfast) {
+                    const float2* s0 = B + sm.k_b[kt][2 * b_p0];
+                    const float2* s1 = B + sm.k_b[kt][2 * b_p0 + 1];
+                    const int y0 = 2 * b_p0 < krem ? 8 : 0, y1 = 2 * b_p0 + 1 < krem ? 8 : 0;
+                    #pragma unroll
+                    for (int p = 0; p < B_ITEMS; ++p) {
+                        const long long co = sm.col_b[b_r0 + p * (G4_CONV / G4_KG)];
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                         dst + (uint32_t)(2 * p) * RAW_SLOT), "l"(s0 + co), "r"(y0));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                         dst + (uint32_t)(2 * p + 1) * RAW_SLOT), "l"(s1 + co), "r"(y1));
+                    }
+                } else {
+                    const float2* src = B + sm.col_b[b_r0];
+                    #pragma unroll
+                    for (int p = 0; p < B_ITEMS; ++p) {
+                        const int kp = b_p0 + p;
+                        #pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                             dst + (uint32_t)(2 * p + h) * RAW_SLOT),
+                                         "l"(src + sm.k_b[kt][2 * kp + h]), "r"(2 * kp + h < krem ? 8 : 0));
                     }
                 }
             }

@@ -31,14 +31,15 @@ namespace b2 {
 
 namespace ws {
 
-constexpr int BM = 64, BN = 64, BK = 16, PITCH = 66, STAGES = 5;
+constexpr int BM = 64, BK = 16, PITCH = 66, STAGES = 5;    // column tile: 16 * RT (template)
 constexpr int MMA_WARPS = 8, THREADS = (MMA_WARPS + 1) * 32;
 constexpr int TAB_GEN = 4;                     // generations of the per-tile C tables
 constexpr int KLOW_MAX = 1024;                 // entries of the low reduction-offset table
 
+template <int BN>
 struct smem_t {
     double2 a[STAGES][BK][PITCH];
-    double2 b[STAGES][BK][PITCH];
+    double2 b[STAGES][BK][BN + 2];
     long long row_c[TAB_GEN][BM], col_c[TAB_GEN][BN];      // read by the MMA warps
     long long row_a[2][BM], col_b[2][BN];                  // producer only (byte offsets)
     long long klow_a[KLOW_MAX], klow_b[KLOW_MAX];          // byte offsets of k % klow
@@ -98,42 +99,55 @@ __device__ __forceinline__ void raster(long long tile, int tiles_m, int tiles_n,
     tn = r / gm;
 }
 
-// One operand tile chunk (64 rows x 16 k) by the 32 producer lanes: 32 copies per lane.
-//   rows contiguous in the operand: a lane owns 2 rows (lane, lane + 32), walks the 16 k
+// One operand tile chunk (ROWS rows x 16 k, shared layout [k][ROWS + 2]) by the 32 producer
+// lanes: ROWS / 2 copies per lane.
+//   rows contiguous in the operand: consecutive lanes = consecutive rows of one k
 //   K contiguous: a quarter warp = 4 consecutive k x 2 rows (see contract_gemm.cu)
-__device__ __forceinline__ void gather64(uint32_t dst, const char* base, const long long* row_off,
-                                         const long long* klow, int klo, long long khi, int lane,
-                                         bool kfast, int kvalid) {
+template <int ROWS>
+__device__ __forceinline__ void gather_rows(uint32_t dst, const char* base, const long long* row_off,
+                                            const long long* klow, int klo, long long khi, int lane,
+                                            bool kfast, int kvalid) {
+    constexpr int P_ = ROWS + 2;
     if (kfast) {
         const int j = (lane & 3) | ((lane >> 1) & 12);
         const int i0 = (lane >> 2) & 1;
         const char* src = base + klow[klo + j] + khi;
         const int bytes = j < kvalid ? 16 : 0;
-        const uint32_t d = dst + (uint32_t)(j * PITCH + i0) * 16u;
+        const uint32_t d = dst + (uint32_t)(j * P_ + i0) * 16u;
         #pragma unroll 8
-        for (int p = 0; p < 32; ++p) cp16(d + (uint32_t)p * 32u, src + row_off[i0 + 2 * p], bytes);
-    } else {
+        for (int p = 0; p < ROWS / 2; ++p) cp16(d + (uint32_t)p * 32u, src + row_off[i0 + 2 * p], bytes);
+    } else if (ROWS >= 32) {
         const char* s0 = base + row_off[lane] + khi;
-        const char* s1 = base + row_off[lane + 32] + khi;
+        const char* s1 = base + row_off[ROWS == 64 ? lane + 32 : lane] + khi;
         const uint32_t d = dst + (uint32_t)lane * 16u;
         #pragma unroll 8
         for (int j = 0; j < BK; ++j) {
             const long long ko = klow[klo + j];
             const int bytes = j < kvalid ? 16 : 0;
-            cp16(d + (uint32_t)(j * PITCH) * 16u, s0 + ko, bytes);
-            cp16(d + (uint32_t)(j * PITCH + 32) * 16u, s1 + ko, bytes);
+            cp16(d + (uint32_t)(j * P_) * 16u, s0 + ko, bytes);
+            if (ROWS == 64) cp16(d + (uint32_t)(j * P_ + 32) * 16u, s1 + ko, bytes);
+        }
+    } else {                                            // 16 rows: the half warps split the k values
+        const char* s0 = base + row_off[lane & 15] + khi;
+        const uint32_t d = dst + (uint32_t)(lane & 15) * 16u;
+        #pragma unroll
+        for (int jj = 0; jj < BK / 2; ++jj) {
+            const int j = 2 * jj + (lane >> 4);
+            cp16(d + (uint32_t)(j * P_) * 16u, s0 + klow[klo + j], j < kvalid ? 16 : 0);
         }
     }
 }
 
+template <int RT>
 __global__ void __launch_bounds__(THREADS, 1)
 contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
                              const double2* __restrict__ B, double2* __restrict__ Cout, int M, int N,
                              int K, int tiles_m, int tiles_n, long long total_tiles, int klow,
                              int n_klow_modes, int a_kfast, int b_kfast, double alpha_re,
                              double alpha_im, int accumulate) {
+    constexpr int BN = 16 * RT, WN = RT, PITCH_B = BN + 2;   // 8 MMA warps: (8 / WN) x WN, warp tile 8 RT x 16
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    smem_t& sm = *reinterpret_cast<smem_t*>(smem_raw);
+    smem_t<BN>& sm = *reinterpret_cast<smem_t<BN>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const long long tiles_mn = (long long)tiles_m * tiles_n;
@@ -184,9 +198,11 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
                 const int m = tm * BM + t;
                 decode_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
                 sm.row_a[pg][t] = (ba + oa) * 16; sm.row_c[gen][t] = bc + oc;
-                const int n = tn * BN + t;
-                decode_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
-                sm.col_b[pg][t] = (bb + ob) * 16; sm.col_c[gen][t] = oc;
+                if (t < BN) {
+                    const int n = tn * BN + t;
+                    decode_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
+                    sm.col_b[pg][t] = (bb + ob) * 16; sm.col_c[gen][t] = oc;
+                }
             }
             __threadfence_block();
             __syncwarp();
@@ -199,10 +215,10 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
                 mbar_wait(&sm.empty[st], ph ^ 1u);   // passes at once on the first lap
                 const int kleft = K - c * BK;
                 const int kvalid = kleft < BK ? kleft : BK;
-                gather64(s32(&sm.a[st][0][0]), Ab, sm.row_a[pg], sm.klow_a, klo, khi_a, lane,
-                         a_kfast != 0, kvalid);
-                gather64(s32(&sm.b[st][0][0]), Bb, sm.col_b[pg], sm.klow_b, klo, khi_b, lane,
-                         b_kfast != 0, kvalid);
+                gather_rows<BM>(s32(&sm.a[st][0][0]), Ab, sm.row_a[pg], sm.klow_a, klo, khi_a, lane,
+                                a_kfast != 0, kvalid);
+                gather_rows<BN>(s32(&sm.b[st][0][0]), Bb, sm.col_b[pg], sm.klow_b, klo, khi_b, lane,
+                                b_kfast != 0, kvalid);
                 cp_async_arrive(&sm.full[st]);
                 klo += BK;
                 if (klo >= klow) {                    // klow is a multiple of 16 (or >= K)
@@ -224,7 +240,7 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
         asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         // ============================== MMA warps ==============================
-        const int wm = warp >> 2, wn = warp & 3;
+        const int wm = warp / WN, wn = warp % WN;
         const int frow = lane >> 2, fk = lane & 3;
         long long chunk_seq = 0;
         int tcount = 0;
@@ -232,9 +248,9 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
             const long long batch = tile / tiles_mn;
             int tm, tn;
             raster(tile - batch * tiles_mn, tiles_m, tiles_n, tm, tn);
-            double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+            double p1[RT][2][2], p2[RT][2][2], p3[RT][2][2];
             #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < RT; ++r)
                 #pragma unroll
                 for (int q = 0; q < 2; ++q)
                     #pragma unroll
@@ -242,42 +258,42 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
             for (int c = 0; c < nchunks; ++c, ++chunk_seq) {
                 const int st = (int)(chunk_seq % STAGES);
                 mbar_wait(&sm.full[st], (uint32_t)((chunk_seq / STAGES) & 1));
-                const double2* ap = &sm.a[st][fk][wm * 32 + frow];
+                const double2* ap = &sm.a[st][fk][wm * (8 * RT) + frow];
                 const double2* bp = &sm.b[st][fk][wn * 16 + frow];
                 #pragma unroll
                 for (int k4 = 0; k4 < BK; k4 += 4) {
-                    double2 af[4], bf[2];
-                    double as[4], bs[2];
+                    double2 af[RT], bf[2];
+                    double as[RT], bs[2];
                     #pragma unroll
-                    for (int r = 0; r < 4; ++r) af[r] = ap[k4 * PITCH + r * 8];
+                    for (int r = 0; r < RT; ++r) af[r] = ap[k4 * PITCH + r * 8];
                     #pragma unroll
-                    for (int q = 0; q < 2; ++q) bf[q] = bp[k4 * PITCH + q * 8];
+                    for (int q = 0; q < 2; ++q) bf[q] = bp[k4 * PITCH_B + q * 8];
                     #pragma unroll
-                    for (int r = 0; r < 4; ++r) as[r] = af[r].x + af[r].y;
+                    for (int r = 0; r < RT; ++r) as[r] = af[r].x + af[r].y;
                     #pragma unroll
                     for (int q = 0; q < 2; ++q) bs[q] = bf[q].x + bf[q].y;
                     #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < RT; ++r)
                         #pragma unroll
                         for (int q = 0; q < 2; ++q) dmma(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
                     #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < RT; ++r)
                         #pragma unroll
                         for (int q = 0; q < 2; ++q) dmma(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
                     #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < RT; ++r)
                         #pragma unroll
                         for (int q = 0; q < 2; ++q) dmma(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[st]);
             }
-            // ---- scatter this warp's 32 x 16 part of the tile through the C permutation
+            // ---- scatter this warp's (8 RT) x 16 part of the tile through the C permutation
             const int gen = tcount % TAB_GEN;
             const int m0 = tm * BM, n0 = tn * BN;
             #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int i = wm * 32 + r * 8 + frow;
+            for (int r = 0; r < RT; ++r) {
+                const int i = wm * (8 * RT) + r * 8 + frow;
                 if (m0 + i >= M) continue;
                 const long long ro = sm.row_c[gen][i];
                 #pragma unroll
@@ -305,14 +321,43 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
 
 }  // namespace ws
 
+template <int RT>
+static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+                        long long M, long long N, long long K, long long klow, int n_low, int a_kfast,
+                        int b_kfast, double ar, double ai, int accumulate, cudaStream_t s) {
+    using namespace ws;
+    constexpr int BN = 16 * RT;
+    const int sms = num_sms();
+    if (sms <= 0) return 1;
+    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const long long total = tiles_m * tiles_n * Bt;
+    const int smem = (int)sizeof(smem_t<BN>);
+    static b2::once_flags attr_set;
+    if (!b2::is_done(attr_set)) {
+        cudaError_t e = cudaFuncSetAttribute(contract_gemm_ws_c128_kernel<RT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(ws): smem attr: %s", cudaGetErrorString(e)); return 1; }
+        b2::mark_done(attr_set);
+    }
+    const long long grid = total < sms ? total : sms;
+    contract_gemm_ws_c128_kernel<RT><<<(unsigned)grid, THREADS, smem, s>>>(
+        g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
+        (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate);
+    return check_launch("b2_contract_gemm(ws)");
+}
+
 // returns handled = false when the pair does not fit this kernel (the caller falls
-// back to the barrier-per-chunk kernels of contract_gemm.cu)
+// back to the barrier-per-chunk kernels of contract_gemm.cu).  min_tiles_per_sm: the
+// persistent grid needs enough tiles per SM to balance.
 int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                    long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
-                   double ai, int accumulate, cudaStream_t s, bool& handled) {
+                   double ai, int accumulate, int min_tiles_per_sm, cudaStream_t s, bool& handled) {
     using namespace ws;
     handled = false;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31) || Bt >= (1ll << 31)) return 0;
+    const int bn = N >= 48 ? 64 : N > 16 ? 32 : 16;
+    const long long tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn) * Bt;
+    if (tiles < (long long)min_tiles_per_sm * num_sms()) return 0;
     // two-level reduction offsets: the low table covers the leading K modes, up to
     // KLOW_MAX entries; with more than one level its extent must be a multiple of the
     // K chunk so that a chunk never straddles two high indices
@@ -325,25 +370,11 @@ int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c
         while (n_low > 0 && klow % BK != 0) klow /= g.dim[f_k + --n_low];
         if (n_low == 0 || klow % BK != 0) return 0;
     }
-    const int sms = num_sms();
-    if (sms <= 0) return 1;
-    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    const long long total = tiles_m * tiles_n * Bt;
-    const int smem = (int)sizeof(smem_t);
-    static b2::once_flags attr_set;
-    if (!b2::is_done(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(contract_gemm_ws_c128_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { set_error("b2_contract_gemm(ws): smem attr: %s", cudaGetErrorString(e)); return 1; }
-        b2::mark_done(attr_set);
-    }
-    const long long grid = total < sms ? total : sms;
-    contract_gemm_ws_c128_kernel<<<(unsigned)grid, THREADS, smem, s>>>(
-        g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
-        (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate);
     handled = true;
-    set_last_kernel("gemm_ws");
-    return check_launch("b2_contract_gemm(ws)");
+    set_last_kernel(bn == 64 ? "gemm_ws" : bn == 32 ? "gemm_ws32" : "gemm_ws16");
+    if (bn == 64) return launch_ws_rt<4>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    if (bn == 32) return launch_ws_rt<2>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    return launch_ws_rt<1>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
 }
 
 }  // namespace b2

@@ -52,7 +52,8 @@ elif what == "small":
     fn, sig = (lambda: sess._launch_small_groups(stream)), "small_program"
 else:
     fn = lambda: sess._launch(dom, zeros, 1.0 + 0j, 0, stream)  # noqa: E731
-    sig = f"{dom.kernel}:{'x'.join(str(x) for x in dom.mnk)}"
+    fn()
+    sig = f"{sess.lib.b2_last_kernel().decode().split()[0]}:{'x'.join(str(x) for x in dom.mnk)}"
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
