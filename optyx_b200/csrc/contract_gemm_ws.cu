@@ -31,14 +31,13 @@ namespace b2 {
 
 namespace ws {
 
-constexpr int BM = 64, BK = 16, PITCH = 66, STAGES = 5;    // column tile: 16 * RT (template)
-constexpr int MMA_WARPS = 8, THREADS = (MMA_WARPS + 1) * 32;
+constexpr int BK = 16, STAGES = 5;       // tile: BM x BN = (MW / RT) * 8 RT  x  16 RT  (templates)
 constexpr int TAB_GEN = 4;                     // generations of the per-tile C tables
-constexpr int KLOW_MAX = 1024;                 // entries of the low reduction-offset table
+constexpr int KLOW_MAX = 512;                  // entries of the low reduction-offset table
 
-template <int BN>
+template <int BM, int BN>
 struct smem_t {
-    double2 a[STAGES][BK][PITCH];
+    double2 a[STAGES][BK][BM + 2];
     double2 b[STAGES][BK][BN + 2];
     long long row_c[TAB_GEN][BM], col_c[TAB_GEN][BN];      // read by the MMA warps
     long long row_a[2][BM], col_b[2][BN];                  // producer only (byte offsets)
@@ -117,15 +116,17 @@ __device__ __forceinline__ void gather_rows(uint32_t dst, const char* base, cons
         #pragma unroll 8
         for (int p = 0; p < ROWS / 2; ++p) cp16(d + (uint32_t)p * 32u, src + row_off[i0 + 2 * p], bytes);
     } else if (ROWS >= 32) {
-        const char* s0 = base + row_off[lane] + khi;
-        const char* s1 = base + row_off[ROWS == 64 ? lane + 32 : lane] + khi;
+        constexpr int R = ROWS >= 32 ? ROWS / 32 : 1;   // rows per lane
+        const char* sr[R];
+        #pragma unroll
+        for (int r = 0; r < R; ++r) sr[r] = base + row_off[lane + 32 * r] + khi;
         const uint32_t d = dst + (uint32_t)lane * 16u;
         #pragma unroll 8
         for (int j = 0; j < BK; ++j) {
             const long long ko = klow[klo + j];
             const int bytes = j < kvalid ? 16 : 0;
-            cp16(d + (uint32_t)(j * P_) * 16u, s0 + ko, bytes);
-            if (ROWS == 64) cp16(d + (uint32_t)(j * P_ + 32) * 16u, s1 + ko, bytes);
+            #pragma unroll
+            for (int r = 0; r < R; ++r) cp16(d + (uint32_t)(j * P_ + 32 * r) * 16u, sr[r] + ko, bytes);
         }
     } else {                                            // 16 rows: the half warps split the k values
         const char* s0 = base + row_off[lane & 15] + khi;
@@ -138,19 +139,20 @@ __device__ __forceinline__ void gather_rows(uint32_t dst, const char* base, cons
     }
 }
 
-template <int RT>
-__global__ void __launch_bounds__(THREADS, 1)
-contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
-                             const double2* __restrict__ B, double2* __restrict__ Cout, int M, int N,
-                             int K, int tiles_m, int tiles_n, long long total_tiles, int klow,
-                             int n_klow_modes, int a_kfast, int b_kfast, double alpha_re,
-                             double alpha_im, int accumulate) {
-    constexpr int BN = 16 * RT, WN = RT, PITCH_B = BN + 2;   // 8 MMA warps: (8 / WN) x WN, warp tile 8 RT x 16
+template <int RT, int MW>
+__device__ __forceinline__ void
+ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __restrict__ B,
+        double2* __restrict__ Cout, int M, int N, int K, int tiles_m, int tiles_n,
+        long long total_tiles, int klow, int n_klow_modes, int a_kfast, int b_kfast, double alpha_re,
+        double alpha_im, int accumulate) {
+    // MW MMA warps as (MW / WN) x WN, warp tile 8 RT x 16; warp MW is the producer
+    constexpr int BN = 16 * RT, WN = RT, BM = (MW / WN) * 8 * RT, PITCH = BM + 2, PITCH_B = BN + 2;
+    constexpr int MMA_WARPS = MW, THREADS = (MW + 1) * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    smem_t<BN>& sm = *reinterpret_cast<smem_t<BN>*>(smem_raw);
+    smem_t<BM, BN>& sm = *reinterpret_cast<smem_t<BM, BN>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
-    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const long long nbatch = total_tiles / ((long long)tiles_m * tiles_n);
     const int nchunks = (K + BK - 1) / BK;
 
     if (tid == 0) {
@@ -182,9 +184,11 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
         long long chunk_seq = 0;                     // chunks issued so far (ring position)
         int tcount = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const long long batch = tile / tiles_mn;
+            // batch index fastest: batch modes often sit between the row modes in the operand's
+            // memory order, so the tiles of all batch values share cache lines -- run them together
+            const long long batch = tile % nbatch;
             int tm, tn;
-            raster(tile - batch * tiles_mn, tiles_m, tiles_n, tm, tn);
+            raster(tile / nbatch, tiles_m, tiles_n, tm, tn);
             const int gen = tcount % TAB_GEN, pg = tcount & 1;
             // the C tables of generation `gen` are free once the MMA warps finished the
             // tile that used them (TAB_GEN tiles ago)
@@ -192,7 +196,7 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
             long long ba, bb, bc;
             decode_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
             #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < BM / 32; ++h) {
                 const int t = lane + 32 * h;
                 long long oa, ob, oc;
                 const int m = tm * BM + t;
@@ -245,9 +249,10 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
         long long chunk_seq = 0;
         int tcount = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const long long batch = tile / tiles_mn;
+            // batch index fastest: batch modes often sit between the row modes in the operand's
+            // memory order, so the tiles of all batch values share cache lines -- run them together
             int tm, tn;
-            raster(tile - batch * tiles_mn, tiles_m, tiles_n, tm, tn);
+            raster(tile / nbatch, tiles_m, tiles_n, tm, tn);
             double p1[RT][2][2], p2[RT][2][2], p3[RT][2][2];
             #pragma unroll
             for (int r = 0; r < RT; ++r)
@@ -255,6 +260,10 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
                 for (int q = 0; q < 2; ++q)
                     #pragma unroll
                     for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
+            // (Loading the fragments one k4 step ahead across the stage hand-over by hand was
+            // tried: 24 more live registers push the kernel over the 168 it may use with 9 warps
+            // and the spills cost more than the hidden latency -- 6561 -> 6831 us on cfg4's
+            // dominant pair.)
             for (int c = 0; c < nchunks; ++c, ++chunk_seq) {
                 const int st = (int)(chunk_seq % STAGES);
                 mbar_wait(&sm.full[st], (uint32_t)((chunk_seq / STAGES) & 1));
@@ -319,19 +328,36 @@ contract_gemm_ws_c128_kernel(const __grid_constant__ b2_gemm_modes g, const doub
     }
 }
 
+#define B2_WS_PARAMS                                                                              \
+    const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,                       \
+        const double2* __restrict__ B, double2* __restrict__ Cout, int M, int N, int K, int tiles_m, \
+        int tiles_n, long long total_tiles, int klow, int n_klow_modes, int a_kfast, int b_kfast,  \
+        double alpha_re, double alpha_im, int accumulate
+#define B2_WS_ARGS                                                                                \
+    g, A, B, Cout, M, N, K, tiles_m, tiles_n, total_tiles, klow, n_klow_modes, a_kfast, b_kfast,   \
+        alpha_re, alpha_im, accumulate
+
+// 8 MMA warps + the producer = 288 threads.  (A 12 + 1 warp, 96-row variant was tried: with
+// 13 warps one scheduler hosts 4 of them, which caps the kernel at 128 registers per thread
+// -- the 3M accumulators then spill.)
+template <int RT>
+__global__ void __launch_bounds__(288, 1) contract_gemm_ws_c128_kernel(B2_WS_PARAMS) {
+    ws_body<RT, 8>(B2_WS_ARGS);
+}
+
 }  // namespace ws
 
-template <int RT>
+template <int RT, int MW>
 static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                         long long M, long long N, long long K, long long klow, int n_low, int a_kfast,
                         int b_kfast, double ar, double ai, int accumulate, cudaStream_t s) {
     using namespace ws;
-    constexpr int BN = 16 * RT;
+    constexpr int BN = 16 * RT, BM = (MW / RT) * 8 * RT;
     const int sms = num_sms();
     if (sms <= 0) return 1;
     const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     const long long total = tiles_m * tiles_n * Bt;
-    const int smem = (int)sizeof(smem_t<BN>);
+    const int smem = (int)sizeof(smem_t<BM, BN>);
     static b2::once_flags attr_set;
     if (!b2::is_done(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(contract_gemm_ws_c128_kernel<RT>,
@@ -340,7 +366,7 @@ static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, vo
         b2::mark_done(attr_set);
     }
     const long long grid = total < sms ? total : sms;
-    contract_gemm_ws_c128_kernel<RT><<<(unsigned)grid, THREADS, smem, s>>>(
+    contract_gemm_ws_c128_kernel<RT><<<(unsigned)grid, (MW + 1) * 32, smem, s>>>(
         g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
         (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate);
     return check_launch("b2_contract_gemm(ws)");
@@ -356,7 +382,8 @@ int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c
     handled = false;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31) || Bt >= (1ll << 31)) return 0;
     const int bn = N >= 48 ? 64 : N > 16 ? 32 : 16;
-    const long long tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn) * Bt;
+    const int bm = 64;
+    const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Bt;
     if (tiles < (long long)min_tiles_per_sm * num_sms()) return 0;
     // two-level reduction offsets: the low table covers the leading K modes, up to
     // KLOW_MAX entries; with more than one level its extent must be a multiple of the
@@ -372,9 +399,9 @@ int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c
     }
     handled = true;
     set_last_kernel(bn == 64 ? "gemm_ws" : bn == 32 ? "gemm_ws32" : "gemm_ws16");
-    if (bn == 64) return launch_ws_rt<4>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
-    if (bn == 32) return launch_ws_rt<2>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
-    return launch_ws_rt<1>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    if (bn == 64) return launch_ws_rt<4, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    if (bn == 32) return launch_ws_rt<2, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    return launch_ws_rt<1, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
 }
 
 }  // namespace b2

@@ -275,9 +275,10 @@ def test_gemm_kernel_permuted_operands(case):
     (((4,) * 7, (4, 4, 2), (4, 4, 4), (2,)), "gemm_ws32"),           # 16384 x 32 x 64, batch 2
     (((13, 11, 9), (5, 4), (5, 7), (2, 2, 2, 2)), "gemm_ws32"),      # ragged 1287 x 20 x 35, batch 16
     (((13, 11, 9), (3, 3), (5, 7), (2, 2, 2, 2)), "gemm_ws16"),      # ragged 1287 x 9 x 35
-    (((4,) * 6, (4,) * 5, (4, 4, 2), ()), "gemm_ws"),                # 1024 tiles, 2 chunks each
-    (((4,) * 6, (4, 4, 4, 4, 2), (4, 4, 4, 4, 4, 2), (2,)), "gemm_ws"),   # K = 2048: two-level K offsets
-    (((13, 11, 9), (7, 11, 3), (5, 7), (2, 2, 2)), "gemm_ws"),       # ragged tiles, K tail, batch
+    (((4,) * 6, (4,) * 5, (4, 4, 2), ()), "gemm_ws"),              # 1024 tiles, 2 chunks each
+    (((4,) * 6, (4, 4, 4, 4, 2), (4, 4, 4, 4, 4, 2), (2,)), "gemm_ws"),  # K = 2048: two-level K offsets
+    (((13, 11, 9), (7, 11, 3), (5, 7), (2, 2, 2)), "gemm_ws"),     # ragged tiles, K tail, batch
+    (((4, 4, 4, 4, 2), (4, 4, 4, 4, 2), (4, 4, 2), (2, 2, 2)), "gemm_ws"),   # batch 8, 64 tiles each
     (((4,) * 6, (4,) * 5, (3,) * 7, ()), None),                      # K prefix never a multiple of 16
 ])
 def test_gemm_thin_and_3m_kernels(case, kernel):
