@@ -622,244 +622,6 @@ static int launch_thin_t(const b2_gemm_modes& g, const void* a, const void* b, v
     return check_launch("b2_contract_gemm(thin)");
 }
 
-// ---- short reductions (16 <= K <= 64): A-stationary persistent kernel.
-// With a reduction this short a 64 x 64 tile is 4 K-chunks of work behind a fixed cost
-// (row / column decode, a cold cp.async ring, the scatter of the tile): measured
-// ~10 us of overhead per CTA next to 8 - 17 us of DMMA work (cfg4: (4,32768,1024,64) at
-// 60 % of the FP64 pipe, (2,65536,256,32) at 44 %, the N <= 32 pairs on the C-tiled kernel
-// at 9 - 35 %).  Here ONE CTA per SM walks a list of jobs = (batch, 64-row panel, range of
-// 32-column panels).  The whole 64 x K panel of A is gathered ONCE per job and stays in
-// shared memory while the 32 x K panels of B stream through a double buffer; the next
-// job's A panel and the next step's B panel are in flight while the current 64 x 32
-// block is multiplied (8 warps, warp tile 16 x 16, 3M scheme) and scattered, so there is
-// no cold start after the first job.  All reduction offsets are decoded once per CTA.
-constexpr int PK_THREADS = 256, PK_BN = 32, PK_KMAX = 64, PK_PA = 66, PK_PB = 34;
-struct pk_smem {
-    double2 a[2][PK_KMAX][PK_PA];
-    double2 b[2][PK_KMAX][PK_PB];
-    // tables are written one step ahead while slower warps may still scatter the previous
-    // step's block: three generations
-    long long row_a[3][BM], row_c[3][BM];
-    long long col_b[3][PK_BN], col_c[3][PK_BN];
-    long long k_a[PK_KMAX], k_b[PK_KMAX];
-};
-
-// 32-bit mixed-radix decode (group extents < 2^31)
-__device__ __forceinline__ void decode3_u32(unsigned flat, const b2_gemm_modes& g, int first, int count,
-                                            long long& oa, long long& ob, long long& oc) {
-    oa = ob = oc = 0;
-    for (int m = 0; m < count; ++m) {
-        const unsigned d = (unsigned)g.dim[first + m];
-        const unsigned q = flat / d, i = flat - q * d;
-        flat = q;
-        oa += (long long)i * g.sa[first + m];
-        ob += (long long)i * g.sb[first + m];
-        oc += (long long)i * g.sc[first + m];
-    }
-}
-
-__global__ void __launch_bounds__(PK_THREADS, 1)
-contract_gemm_pk_c128_kernel(const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,
-                             const double2* __restrict__ B, double2* __restrict__ Cout,
-                             int M, int N, int K, int tiles_m, int tiles_n, int nsplit,
-                             long long jobs, int a_kfast, int b_kfast, double alpha_re,
-                             double alpha_im, int accumulate) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    pk_smem& sm = *reinterpret_cast<pk_smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;
-    const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
-    const int kchunks = (K + 15) >> 4, k4steps = (K + 3) >> 2;
-    const int per_split = (tiles_n + nsplit - 1) / nsplit;
-
-    if (tid < PK_KMAX) {                                   // reduction offsets: once per CTA
-        unsigned k = tid < K ? (unsigned)tid : 0u;
-        long long oa = 0, ob = 0;
-        for (int m = 0; m < g.n_k; ++m) {
-            const unsigned d = (unsigned)g.dim[f_k + m];
-            const unsigned q = k / d, i = k - q * d;
-            k = q;
-            oa += (long long)i * g.sa[f_k + m];
-            ob += (long long)i * g.sb[f_k + m];
-        }
-        sm.k_a[tid] = oa * 16; sm.k_b[tid] = ob * 16;
-    }
-    // job -> (batch, row panel, first / last column panel)
-    auto job_info = [&](long long job, long long& batch, int& tm, int& n_first, int& n_last) {
-        const int sp = (int)(job % nsplit);
-        const long long r = job / nsplit;
-        tm = (int)(r % tiles_m);
-        batch = r / tiles_m;
-        n_first = sp * per_split;
-        n_last = n_first + per_split < tiles_n ? n_first + per_split : tiles_n;
-    };
-    // tables of a job's row panel (threads 64..127) -- batch offsets folded in
-    auto rows_of = [&](long long batch, int tm, int buf) {
-        if (tid >= 64 && tid < 128) {
-            const int t = tid - 64;
-            long long ba, bb, bc, oa, ob, oc;
-            decode3_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
-            const int m = tm * BM + t;
-            decode3_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
-            sm.row_a[buf][t] = (ba + oa) * 16; sm.row_c[buf][t] = bc + oc;
-        }
-    };
-    // tables of one column panel (threads 0..31)
-    auto cols_of = [&](long long batch, int tn, int buf) {
-        if (tid < PK_BN) {
-            long long ba, bb, bc, oa, ob, oc;
-            decode3_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
-            const int n = tn * PK_BN + tid;
-            decode3_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
-            sm.col_b[buf][tid] = (bb + ob) * 16; sm.col_c[buf][tid] = oc;
-        }
-    };
-    auto load_a = [&](int buf, int rbuf) {
-        for (int c = 0; c < kchunks; ++c) {
-            const int kvalid = K - c * 16 < 16 ? K - c * 16 : 16;
-            gather_chunk<BM, 16, PK_THREADS, PK_PA>(&sm.a[buf][c * 16][0], A, sm.row_a[rbuf],
-                                                    sm.k_a + c * 16, tid, a_kfast != 0, kvalid);
-        }
-    };
-    auto load_b = [&](int buf, int cbuf) {
-        for (int c = 0; c < kchunks; ++c) {
-            const int kvalid = K - c * 16 < 16 ? K - c * 16 : 16;
-            gather_chunk<PK_BN, 16, PK_THREADS, PK_PB>(&sm.b[buf][c * 16][0], B, sm.col_b[cbuf],
-                                                       sm.k_b + c * 16, tid, b_kfast != 0, kvalid);
-        }
-    };
-
-    long long job = blockIdx.x;
-    if (job >= jobs) return;
-    long long batch; int tm, n_first, n_last;
-    job_info(job, batch, tm, n_first, n_last);
-    rows_of(batch, tm, 0);
-    cols_of(batch, n_first, 0);
-    __syncthreads();
-    load_a(0, 0);
-    load_b(0, 0);
-    cp_async_commit();
-
-    const int frow = lane >> 2, fk = lane & 3;
-    int jbuf = 0, rgen = 0, cgen = 0, tn = n_first;      // A buffer; table generations (mod 3)
-    for (long long step = 0;; ++step) {
-        const int sbuf = (int)(step & 1);
-        const int rnext = rgen == 2 ? 0 : rgen + 1, cnext = cgen == 2 ? 0 : cgen + 1;
-        // ---- what comes next: the next column panel of this job, or the next job
-        long long nxt_job = job, nxt_batch = batch;
-        int nxt_tm = tm, nxt_tn = tn + 1, nxt_first = n_first, nxt_last = n_last;
-        bool new_job = false, have_next = true;
-        if (nxt_tn >= n_last) {
-            nxt_job = job + gridDim.x;
-            if (nxt_job < jobs) {
-                job_info(nxt_job, nxt_batch, nxt_tm, nxt_first, nxt_last);
-                nxt_tn = nxt_first;
-                new_job = true;
-            } else {
-                have_next = false;
-            }
-        }
-        if (have_next) {
-            if (new_job) rows_of(nxt_batch, nxt_tm, rnext);
-            cols_of(nxt_batch, nxt_tn, cnext);
-        }
-        __syncthreads();               // next tables visible; buffers of step - 1 are free
-        if (have_next) {
-            if (new_job) load_a(jbuf ^ 1, rnext);
-            load_b(sbuf ^ 1, cnext);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();            // this step's panels (own copies) have landed
-        __syncthreads();               // ... and everyone else's
-
-        double p1[2][2][2], p2[2][2][2], p3[2][2][2];
-        #pragma unroll
-        for (int r = 0; r < 2; ++r)
-            #pragma unroll
-            for (int q = 0; q < 2; ++q)
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) p1[r][q][h] = p2[r][q][h] = p3[r][q][h] = 0.0;
-        const double2* ap = &sm.a[jbuf][fk][wm * 16 + frow];
-        const double2* bp = &sm.b[sbuf][fk][wn * 16 + frow];
-        #pragma unroll 4
-        for (int s4 = 0; s4 < k4steps; ++s4) {
-            double2 af[2], bf[2];
-            double as[2], bs[2];
-            #pragma unroll
-            for (int r = 0; r < 2; ++r) { af[r] = ap[s4 * 4 * PK_PA + r * 8]; as[r] = af[r].x + af[r].y; }
-            #pragma unroll
-            for (int q = 0; q < 2; ++q) { bf[q] = bp[s4 * 4 * PK_PB + q * 8]; bs[q] = bf[q].x + bf[q].y; }
-            #pragma unroll
-            for (int r = 0; r < 2; ++r)
-                #pragma unroll
-                for (int q = 0; q < 2; ++q) dmma884(p1[r][q][0], p1[r][q][1], af[r].x, bf[q].x);
-            #pragma unroll
-            for (int r = 0; r < 2; ++r)
-                #pragma unroll
-                for (int q = 0; q < 2; ++q) dmma884(p2[r][q][0], p2[r][q][1], af[r].y, bf[q].y);
-            #pragma unroll
-            for (int r = 0; r < 2; ++r)
-                #pragma unroll
-                for (int q = 0; q < 2; ++q) dmma884(p3[r][q][0], p3[r][q][1], as[r], bs[q]);
-        }
-        // ---- scatter the 64 x 32 block through the C permutation
-        const int m0 = tm * BM, n0 = tn * PK_BN;
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int i = wm * 16 + r * 8 + frow;
-            if (m0 + i >= M) continue;
-            const long long ro = sm.row_c[rgen][i];
-            #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = wn * 16 + q * 8 + fk * 2 + h;
-                    if (n0 + j >= N) continue;
-                    const double re = p1[r][q][h] - p2[r][q][h];
-                    const double im = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
-                    double2 v;
-                    v.x = alpha_re * re - alpha_im * im;
-                    v.y = alpha_re * im + alpha_im * re;
-                    double2* dst = Cout + ro + sm.col_c[cgen][j];
-                    if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-                    *dst = v;
-                }
-            }
-        }
-        if (!have_next) break;
-        if (new_job) { job = nxt_job; batch = nxt_batch; tm = nxt_tm; n_first = nxt_first; n_last = nxt_last; jbuf ^= 1; rgen = rnext; }
-        tn = nxt_tn;
-        cgen = cnext;
-    }
-    cp_async_wait<0>();
-}
-
-static int launch_pk(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
-                     long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
-                     double ai, int accumulate, cudaStream_t s) {
-    const int smem = (int)sizeof(pk_smem);
-    static b2::once_flags attr_set;
-    if (!b2::is_done(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(contract_gemm_pk_c128_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { set_error("b2_contract_gemm(pk): smem attr: %s", cudaGetErrorString(e)); return 1; }
-        b2::mark_done(attr_set);
-    }
-    const int sms = num_sms();
-    const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + PK_BN - 1) / PK_BN;
-    long long nsplit = 1;
-    if (Bt * tiles_m < 4ll * sms) {                       // few row panels: share their columns
-        nsplit = (4ll * sms + Bt * tiles_m - 1) / (Bt * tiles_m);
-        if (nsplit > tiles_n) nsplit = tiles_n;
-    }
-    const long long jobs = Bt * tiles_m * nsplit;
-    const long long grid = jobs < sms ? jobs : sms;
-    contract_gemm_pk_c128_kernel<<<(unsigned)grid, PK_THREADS, smem, s>>>(
-        g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
-        (int)tiles_n, (int)nsplit, jobs, a_kfast, b_kfast, ar, ai, accumulate);
-    return check_launch("b2_contract_gemm(pk)");
-}
-
 // ---- few outputs, very long reduction with many modes (the last pair of a sliced
 // amplitude network: <psi_left | psi_right> over 2^20 index values spread over 20
 // binary modes).  A tile of the DMMA kernel would be 1/4096 full; here every CTA takes a
@@ -971,7 +733,7 @@ int launch_gemm_c64(const b2_gemm_modes& g, const void* a_dev, const void* b_dev
                     double ar, double ai, int accumulate, cudaStream_t s);
 int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                    long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
-                   double ai, int accumulate, int min_tiles_per_sm, cudaStream_t s, bool& handled);
+                   double ai, int accumulate, cudaStream_t s, bool& handled);
 
 }  // namespace b2
 
@@ -1027,14 +789,15 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const int a_kfast = min_stride(g.sa, f_k, g.n_k) < min_stride(g.sa, f_m, g.n_m);
     const int b_kfast = min_stride(g.sb, f_k, g.n_k) < min_stride(g.sb, f_n, g.n_n);
-    // enough tiles per SM: the persistent warp-specialised kernel (contract_gemm_ws.cu)
-    // (B2_GEMM_WS = 0: off, else the minimum number of tiles per SM)
+    // the persistent warp-specialised kernel (contract_gemm_ws.cu) takes every pair with at
+    // least one full row panel, unless its tiles would leave most SMs idle while the reduction
+    // is long (split-K below).  (B2_GEMM_WS = 0: off -- experiment knob)
     {
-        static const int ws_min = getenv("B2_GEMM_WS") ? atoi(getenv("B2_GEMM_WS")) : 2;
-        if (ws_min > 0 && M >= 64 && N >= 8 && K >= 16) {
+        static const bool use_ws = !(getenv("B2_GEMM_WS") && atoi(getenv("B2_GEMM_WS")) == 0);
+        if (use_ws && M >= 64 && N >= 8 && K >= 16) {
             bool handled = false;
             int st = launch_gemm_ws(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re,
-                                    alpha_im, accumulate, ws_min, (cudaStream_t)stream, handled);
+                                    alpha_im, accumulate, (cudaStream_t)stream, handled);
             if (st != 0 || handled) return st;
         }
     }
@@ -1044,11 +807,7 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
     // Measured (profiles/r02_shortk.md): from K = 16 on the 64x64 tiling is faster on
     // plain AND permuted layouts -- (2,16384,1024,32) of cfg4: 1336 -> 489 us
     static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 8;
-    static const bool use_pk = !getenv("B2_NO_PK");
-    // 16 <= K <= 64 with at least one full row panel: the A-stationary persistent kernel
-    const bool pk = use_pk && dtype == B2_C128 && k_total >= 16 && k_total <= PK_KMAX && m_total >= BM &&
-                    n_total >= 8 && m_total < (1ll << 31) && n_total < (1ll << 31) && b_total < (1ll << 31);
-    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled && !pk) {
+    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
         // short reductions / skinny pairs: tile from the output side (coalesced
         // staged stores, one gather per tile).  Long-K square-ish pairs keep the
         // classic 64x64 tiling below (4x4 register blocking per warp).
@@ -1057,13 +816,8 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
                               (cudaStream_t)stream, handled);
         if (st != 0 || handled) return st;
     }
-    if (pk) {
-        set_last_kernel("gemm_pk");
-        return launch_pk(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im,
-                         accumulate, (cudaStream_t)stream);
-    }
     // thin pairs (M, N <= 32, long K): split-K over the whole GPU with a tile of their size
-    if (M <= 32 && N <= 32 && K >= 1024 && !getenv("B2_NO_THIN")) {
+    if (M <= 32 && N <= 32 && K >= 256 && !getenv("B2_NO_THIN")) {
         long long span = 0;
         for (int i = 0; i < f_k; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
         if (span + 1 == Bt * M * N || accumulate) {          // C is one dense block (zero fill)

@@ -373,18 +373,17 @@ static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, vo
 }
 
 // returns handled = false when the pair does not fit this kernel (the caller falls
-// back to the barrier-per-chunk kernels of contract_gemm.cu).  min_tiles_per_sm: the
-// persistent grid needs enough tiles per SM to balance.
+// back to the barrier-per-chunk kernels of contract_gemm.cu).
 int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                    long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
-                   double ai, int accumulate, int min_tiles_per_sm, cudaStream_t s, bool& handled) {
+                   double ai, int accumulate, cudaStream_t s, bool& handled) {
     using namespace ws;
     handled = false;
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31) || Bt >= (1ll << 31)) return 0;
     const int bn = N >= 48 ? 64 : N > 16 ? 32 : 16;
     const int bm = 64;
     const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Bt;
-    if (tiles < (long long)min_tiles_per_sm * num_sms()) return 0;
+    if (tiles * 2 <= num_sms() && K >= 256) return 0;      // few tiles, long reduction: split-K
     // two-level reduction offsets: the low table covers the leading K modes, up to
     // KLOW_MAX entries; with more than one level its extent must be a multiple of the
     // K chunk so that a chunk never straddles two high indices

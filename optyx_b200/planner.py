@@ -611,6 +611,13 @@ def compile_plan(net: Network, info: PathInfo, dtype=np.complex128, batch: int =
         use_gemm = (Mx >= gemm_threshold[0]
                     and Nx >= gemm_threshold[1] and Kx >= gemm_threshold[2]
                     and intensity >= min_ai)
+        # small output over a long reduction (two big intermediates sharing almost all of
+        # their modes): the thin split-K kernel behind b2_contract_gemm reads both operands at
+        # HBM speed; the direct kernels serialise the reduction (cfg3: (16, 16, K = 16384) took
+        # 237 us on the reduce kernel)
+        if (not use_gemm and not final and 4 <= Mx <= 32 and 4 <= Nx <= 32 and Kx >= 256
+                and np.dtype(dtype) == np.complex128):
+            use_gemm = True
         desc = None
         if not use_gemm:
             # out modes in C *memory* order so that stores are coalesced

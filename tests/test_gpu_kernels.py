@@ -264,13 +264,13 @@ def test_gemm_kernel_permuted_operands(case):
     (((4, 4), (2, 2, 2, 2), (2,) * 13, (2,)), "gemm_thin"),        # 16 x 16, K = 8192, batch 2
     (((8,), (5,), (4, 4, 4, 4, 4, 3), ()), "gemm_thin"),             # T = 1, ragged K tail
     (((5, 5), (3, 7), (2, 3, 5, 7, 11), (3,)), "gemm_thin"),         # T = 4, ragged M / N / K
-    (((4,) * 5, (2,) * 9, (4,) * 4, ()), "gemm3m"),                  # 1024 x 512 x 256: 3M, unsplit
-    (((9, 9), (70,), (150,), (2,)), "gemm3m"),                       # ragged tiles and K tail
+    (((4,) * 5, (2,) * 9, (4,) * 4, ()), "gemm_ws"),                 # 1024 x 512 x 256: 128 tiles
+    (((9, 9), (70,), (150,), (2,)), "gemm_ws"),                      # ragged tiles and K tail
     (((64,), (48,), (4096,), ()), "gemm3m_splitk"),
-    (((2,) * 8, (2,) * 5, (2,) * 6, (2,)), "gemm_pk"),               # 256 x 32 x 64, batch 2
-    (((7, 7, 3), (5, 7), (3, 7), (3,)), "gemm_pk"),                  # ragged rows / columns / K
-    (((130,), (9,), (40,), ()), "gemm_pk"),
-    (((4, 4, 4, 4, 2), (4, 4, 4, 4), (4, 4, 2), ()), "gemm_pk"),     # several jobs per CTA, column splits
+    (((2,) * 8, (2,) * 5, (2,) * 6, (2,)), "gemm_ws32"),             # 256 x 32 x 64, batch 2
+    (((7, 7, 3), (5, 7), (3, 7), (3,)), "gemm_ws32"),                # ragged rows / columns / K
+    (((130,), (9,), (40,), ()), "gemm_ws16"),
+    (((4, 4, 4, 4, 2), (4, 4, 4, 4), (4, 4, 2), ()), "gemm_ws"),     # 32 tiles of 2 chunks
     (((2,) * 14, (2,) * 4, (2,) * 4, (2, 2)), "gemm_ws16"),          # 16384 x 16 x 16, batch 4
     (((4,) * 7, (4, 4, 2), (4, 4, 4), (2,)), "gemm_ws32"),           # 16384 x 32 x 64, batch 2
     (((13, 11, 9), (5, 4), (5, 7), (2, 2, 2, 2)), "gemm_ws32"),      # ragged 1287 x 20 x 35, batch 16
@@ -279,7 +279,7 @@ def test_gemm_kernel_permuted_operands(case):
     (((4,) * 6, (4, 4, 4, 4, 2), (4, 4, 4, 4, 4, 2), (2,)), "gemm_ws"),  # K = 2048: two-level K offsets
     (((13, 11, 9), (7, 11, 3), (5, 7), (2, 2, 2)), "gemm_ws"),     # ragged tiles, K tail, batch
     (((4, 4, 4, 4, 2), (4, 4, 4, 4, 2), (4, 4, 2), (2, 2, 2)), "gemm_ws"),   # batch 8, 64 tiles each
-    (((4,) * 6, (4,) * 5, (3,) * 7, ()), None),                      # K prefix never a multiple of 16
+    (((4,) * 6, (4,) * 5, (3,) * 7, ()), "gemm3m"),                  # K prefix never a multiple of 16: not ws
 ])
 def test_gemm_thin_and_3m_kernels(case, kernel):
     """The r02 FP64 kernels: thin split-K pairs (whole M x N in one small tile) and the 3M
