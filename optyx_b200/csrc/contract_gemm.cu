@@ -801,21 +801,6 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
             if (st != 0 || handled) return st;
         }
     }
-    const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
-                                 2ll * num_sms() && k_total >= 256;
-    // reductions up to ctile_kmax take the ctile kernel (B2_CTILE_KMAX: experiment knob).
-    // Measured (profiles/r02_shortk.md): from K = 16 on the 64x64 tiling is faster on
-    // plain AND permuted layouts -- (2,16384,1024,32) of cfg4: 1336 -> 489 us
-    static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 8;
-    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
-        // short reductions / skinny pairs: tile from the output side (coalesced
-        // staged stores, one gather per tile).  Long-K square-ish pairs keep the
-        // classic 64x64 tiling below (4x4 register blocking per warp).
-        bool handled = false;
-        int st = launch_ctile(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
-                              (cudaStream_t)stream, handled);
-        if (st != 0 || handled) return st;
-    }
     // thin pairs (M, N <= 32, long K): split-K over the whole GPU with a tile of their size
     if (M <= 32 && N <= 32 && K >= 256 && !getenv("B2_NO_THIN")) {
         long long span = 0;
@@ -834,6 +819,21 @@ extern "C" int b2_contract_gemm(const b2_gemm_modes* modes, const void* a_dev, c
                 return launch_thin_t<2>(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im, (cudaStream_t)stream);
             return launch_thin_t<4>(g, a_dev, b_dev, c_dev, Bt, M, N, K, a_kfast, b_kfast, alpha_re, alpha_im, (cudaStream_t)stream);
         }
+    }
+    const bool underfilled = ((m_total + BM - 1) / BM) * ((n_total + BN - 1) / BN) * b_total * 2 <=
+                                 2ll * num_sms() && k_total >= 256;
+    // reductions up to ctile_kmax take the ctile kernel (B2_CTILE_KMAX: experiment knob).
+    // Measured (profiles/r02_shortk.md): from K = 16 on the 64x64 tiling is faster on
+    // plain AND permuted layouts -- (2,16384,1024,32) of cfg4: 1336 -> 489 us
+    static const long long ctile_kmax = getenv("B2_CTILE_KMAX") ? atoll(getenv("B2_CTILE_KMAX")) : 8;
+    if ((k_total <= ctile_kmax || n_total < 64) && !underfilled) {
+        // short reductions / skinny pairs: tile from the output side (coalesced
+        // staged stores, one gather per tile).  Long-K square-ish pairs keep the
+        // classic 64x64 tiling below (4x4 register blocking per warp).
+        bool handled = false;
+        int st = launch_ctile(g, a_dev, b_dev, c_dev, alpha_re, alpha_im, accumulate,
+                              (cudaStream_t)stream, handled);
+        if (st != 0 || handled) return st;
     }
     // long reductions: 3M complex multiplication (3 DMMAs per complex tile product, K chunk
     // 16); short ones: the 4-product kernel with chunk 8 / 4 stages.
