@@ -46,7 +46,9 @@ constexpr int G4_CONV = 256;                      // converter threads (8 warps)
 constexpr int G4_THREADS = G4_CONV + 32;         // + the MMA warp
 constexpr int G4_BM = 128, G4_KC = 16;
 constexpr int G4_RAW = 3;                        // cp.async stages of raw complex64 operands
-constexpr int G4_STAGES = 2;                     // UMMA operand stages (hi/lo split tiles)
+constexpr int G4_STAGES = 2;                     // UMMA operand stages (hi/lo split tiles); 4 stages measured
+                                                 // slower (r02: 124 -> 119 TFLOP/s): the converter warps, not the
+                                                 // hand-over latency, bound the kernel (shared-memory pipe 65 % busy)
 constexpr int G4_KG = G4_KC / 2;                 // 16-byte k-groups (2 complex) per chunk
 constexpr int G4_SEG = 4;                        // chunks per TMEM accumulation segment
 
