@@ -40,6 +40,7 @@ METRIC, UNIT = "eval_diagrams_per_sec", "diagrams/s"
 FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profiles/r01_probe.json)
 THREE_M_VARIANTS = ("gemm_ws", "gemm3m", "gemm3m_splitk", "gemm_pk", "gemm_thin")
 CFG4_TARGET = float(2 ** 27)       # <= 2^27 elements (2 GiB complex128) per slice
+CFG4_TRIALS = 128                  # path-search budget (cotengra's default hyper-optimiser: 128 repeats)
 CFG4_MIN_SLICES = 32               # ... and >= 32 slices, so that 8 GPUs get >= 4 each
 
 
@@ -62,7 +63,7 @@ def workload(name: str):
     if name == "cfg4":
         n, depth = 30, 48
         return dict(kind="sliced", factory=lambda: cases.random_clifford_t(n, depth, seed=0),
-                    target=CFG4_TARGET, trials=16, min_slices=CFG4_MIN_SLICES,
+                    target=CFG4_TARGET, trials=CFG4_TRIALS, min_slices=CFG4_MIN_SLICES,
                     desc=f"cfg4: {n}-qubit brickwork Clifford+T depth {depth} amplitude <0|C|0>, "
                          f"sliced to <= 2^{int(math.log2(CFG4_TARGET))} elements per slice, "
                          f">= {CFG4_MIN_SLICES} slices")

@@ -7,6 +7,7 @@
 // predicate of the box.  Write-only, HBM-write-bound: 16 B (complex128) per
 // element, no reads except the tiny descriptor table (L1/L2 resident) and the
 // host-computed params of VEC/DENSE leaves.
+#include <stdlib.h>
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -153,7 +154,8 @@ extern "C" int b2_build_leaves_indexed(const b2_leaf_desc* desc_dev, int32_t n_l
     if (blocks > 2147483647ll) { b2::set_error("b2_build_leaves: arena too large"); return 1; }
     // evals per thread: enough CTAs to fill the GPU a few times over, long enough store
     // runs to amortise the decode
-    long long ev_per = (long long)batch * blocks / ((long long)sms * 16);
+    static const int ctas_per_sm = getenv("B2_LEAF_CTAS_PER_SM") ? atoi(getenv("B2_LEAF_CTAS_PER_SM")) : 16;
+    long long ev_per = (long long)batch * blocks / ((long long)sms * ctas_per_sm);
     if (ev_per < 1) ev_per = 1;
     if (ev_per > 64) ev_per = 64;
     long long gy = (batch + ev_per - 1) / ev_per;

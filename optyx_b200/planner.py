@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import heapq
 import math
+import os
 import random
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -188,6 +189,8 @@ def analyse_path(inputs: Sequence[frozenset], dims: Dict[int, int], output: froz
 
 NATIVE_MIN_TENSORS = 64        # from here on the search runs in C++ (csrc/planner_native.cu)
 NATIVE_TRIALS_PER_TRIAL = 16   # ... and affords this many more randomised trials
+NATIVE_SLICE_CANDIDATES = int(os.environ.get("B2_SLICE_CANDS", "48"))   # trees taken through slicing
+SLICE_RECONF_ROUNDS = int(os.environ.get("B2_SLICE_ROUNDS", "4"))
 RECONF_LEAVES = 8              # frontier size of the subtree reconfiguration
 
 
@@ -205,7 +208,7 @@ def find_path(inputs, dims, output, trials: int = 8, seed: int = 0,
     need_slicing = target_size is not None or min_slices > 1
     if len(inputs) >= NATIVE_MIN_TENSORS:
         return _find_path_native(inputs, dims, output, max(1, trials) * NATIVE_TRIALS_PER_TRIAL,
-                                 seed, minimize, target_size, max(slice_candidates, 12), min_slices)
+                                 seed, minimize, target_size, max(slice_candidates, NATIVE_SLICE_CANDIDATES), min_slices)
     cands = []
     rng = random.Random(seed)
     for t in range(max(1, trials)):
@@ -233,15 +236,23 @@ def _find_path_native(inputs, dims, output, trials, seed, minimize, target_size,
                       slice_candidates, min_slices) -> PathInfo:
     nn = NativeNetwork(inputs, dims, output)
     rng = random.Random(seed)
-    cands = []
-    for t in range(trials):
+    # the trial parameters are drawn in order (the result does not depend on the thread
+    # count); the C++ searches run on a thread pool (ctypes releases the GIL)
+    knobs = [(0.0, 1.0)] + [(0.3 + 0.7 * rng.random(), rng.choice([0.5, 1.0, 1.0, 2.0]))
+                            for _ in range(1, trials)]
+
+    def one_trial(t):
         if t == 0:
             p = nn.greedy(seed=seed)
         else:
-            p = nn.greedy(seed=seed * 7919 + t, temperature=0.3 + 0.7 * rng.random(),
-                          costmod=rng.choice([0.5, 1.0, 1.0, 2.0]))
+            p = nn.greedy(seed=seed * 7919 + t, temperature=knobs[t][0], costmod=knobs[t][1])
         macs, peak, _, _ = nn.cost(p)
-        cands.append((macs, peak, t, p))
+        return (macs, peak, t, p)
+
+    workers = max(1, min(16, os.cpu_count() or 1, trials))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        cands = list(pool.map(one_trial, range(trials)))
     need_slicing = target_size is not None or min_slices > 1
 
     def info_of(p, sliced=()):
@@ -250,11 +261,13 @@ def _find_path_native(inputs, dims, output, trials, seed, minimize, target_size,
     # nodes) on the most promising trees: 3x fewer multiply-adds on cfg4
     tgt = target_size if target_size is not None else float("inf")
     cands.sort(key=lambda c: (c[0] * max(1.0, c[1] / tgt), c[2]))
-    refined = []
-    for macs, peak, t, p in cands[:max(16, 2 * slice_candidates)]:
-        p = nn.reconfigure(p, (), RECONF_LEAVES)
+    def refine(c):
+        p = nn.reconfigure(c[3], (), RECONF_LEAVES)
         macs, peak, _, _ = nn.cost(p)
-        refined.append((macs, peak, t, p))
+        return (macs, peak, c[2], p)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        refined = list(pool.map(refine, cands[:max(16, 2 * slice_candidates)]))
     if not need_slicing:
         refined.sort(key=lambda c: (c[0], c[1], c[2]) if minimize == "flops" else (c[1], c[0], c[2]))
         return info_of(refined[0][3])
@@ -262,18 +275,31 @@ def _find_path_native(inputs, dims, output, trials, seed, minimize, target_size,
     # target costs at least one sliced index), slice the best few, re-optimise the tree
     # for the sliced network, compare by the roofline time estimate
     refined.sort(key=lambda c: (c[0] * max(1.0, c[1] / tgt), c[2]))
-    best = None
-    for macs, peak, _, p in refined[:max(1, slice_candidates)]:
+    def slice_one(c):
+        p = c[3]
         info = info_of(p)
         if info.peak > tgt or min_slices > 1:
             info = slice_path(inputs, dims, output, info, target_size, min_slices=min_slices)
-            p2 = nn.reconfigure(p, info.sliced, RECONF_LEAVES)
-            again = info_of(p2, info.sliced)
-            if again.peak > tgt:          # the re-ordered tree is wider: cut it down again
-                again = slice_path(inputs, dims, output, info_of(p2), target_size,
-                                   min_slices=min_slices)
-            if again.time_est < info.time_est and again.peak <= tgt:
-                info = again
+            # alternate: re-order the tree for the sliced network, re-choose the slices for
+            # the re-ordered tree, ... while the roofline estimate keeps improving
+            for _ in range(SLICE_RECONF_ROUNDS):
+                p2 = nn.reconfigure(p, info.sliced, RECONF_LEAVES)
+                options = [info_of(p2, info.sliced),
+                           slice_path(inputs, dims, output, info_of(p2), target_size,
+                                      min_slices=min_slices)]
+                options = [o for o in options if o.peak <= tgt and o.nslices >= min_slices]
+                if not options:
+                    break
+                again = min(options, key=lambda o: o.time_est)
+                if again.time_est >= 0.99 * info.time_est:
+                    break
+                info, p = again, p2
+        return info
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        infos = list(pool.map(slice_one, refined[:max(1, slice_candidates)]))
+    best = None
+    for info in infos:                    # first of equals wins: independent of the thread count
         if best is None or info.time_est < best.time_est:
             best = info
     return best
