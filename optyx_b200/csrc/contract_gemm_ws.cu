@@ -88,14 +88,14 @@ __device__ __forceinline__ void decode_u32(unsigned flat, const b2_gemm_modes& g
 }
 
 constexpr int RASTER_GM = 16;
-__device__ __forceinline__ void raster(long long tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-    const long long per_group = (long long)RASTER_GM * tiles_n;
-    const int group = (int)(tile / per_group);
-    const int first_m = group * RASTER_GM;
+__device__ __forceinline__ void raster(unsigned tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const unsigned per_group = (unsigned)RASTER_GM * (unsigned)tiles_n;
+    const unsigned group = tile / per_group;
+    const int first_m = (int)group * RASTER_GM;
     const int gm = tiles_m - first_m < RASTER_GM ? tiles_m - first_m : RASTER_GM;
-    const int r = (int)(tile - (long long)group * per_group);
-    tm = first_m + r % gm;
-    tn = r / gm;
+    const unsigned r = tile - group * per_group;
+    tn = (int)(r / (unsigned)gm);
+    tm = first_m + (int)(r - (unsigned)tn * (unsigned)gm);
 }
 
 // One operand tile chunk (ROWS rows x 16 k, shared layout [k][ROWS + 2]) by the 32 producer
@@ -144,19 +144,23 @@ __device__ __forceinline__ void
 ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __restrict__ B,
         double2* __restrict__ Cout, int M, int N, int K, int tiles_m, int tiles_n,
         long long total_tiles, int klow, int n_klow_modes, int a_kfast, int b_kfast, double alpha_re,
-        double alpha_im, int accumulate) {
+        double alpha_im, int accumulate, int ksplit) {
     // MW MMA warps as (MW / WN) x WN, warp tile 8 RT x 16; warp MW is the producer
     constexpr int BN = 16 * RT, WN = RT, BM = (MW / WN) * 8 * RT, PITCH = BM + 2, PITCH_B = BN + 2;
-    constexpr int MMA_WARPS = MW, THREADS = (MW + 1) * 32;
+    constexpr int MMA_WARPS = MW, THREADS = (MW + 2) * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     smem_t<BM, BN>& sm = *reinterpret_cast<smem_t<BM, BN>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f_m = g.n_batch, f_n = f_m + g.n_m, f_k = f_n + g.n_n;
     const long long nbatch = total_tiles / ((long long)tiles_m * tiles_n);
-    const int nchunks = (K + BK - 1) / BK;
+    const int all_chunks = (K + BK - 1) / BK;
+    // work item = (tile, part of the reduction range): ksplit > 1 only when the tiles alone would
+    // leave most SMs idle; the partial tiles are then added into the zero-filled C atomically
+    const int per_split = (all_chunks + ksplit - 1) / ksplit;
+    const long long total_items = total_tiles * ksplit;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 32); mbar_init(&sm.empty[s], MMA_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 64); mbar_init(&sm.empty[s], MMA_WARPS); }
         for (int t = 0; t < TAB_GEN; ++t) mbar_init(&sm.tab_free[t], MMA_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -177,67 +181,97 @@ ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __
     }
     __syncthreads();
 
-    if (warp == MMA_WARPS) {
-        // ============================ producer warp ============================
-        const char* Ab = reinterpret_cast<const char*>(A);
-        const char* Bb = reinterpret_cast<const char*>(B);
+    if (warp >= MMA_WARPS) {
+        // ======================= producer warps: A (warp MW), B (warp MW + 1) =======================
+        // Each owns one operand: its offset table per tile, its reduction offsets, its gathers.
+        // (One producer warp was the limit of short reductions and narrow column tiles: ~1100
+        // instructions of decode + gather issue per 64 x 64 x 16 chunk against 3072 clk of math.)
+        const bool is_a = warp == MMA_WARPS;
+        const char* base = reinterpret_cast<const char*>(is_a ? (const void*)A : (const void*)B);
+        const long long* klow_tab = is_a ? sm.klow_a : sm.klow_b;
+        const bool kfast = is_a ? a_kfast != 0 : b_kfast != 0;
         long long chunk_seq = 0;                     // chunks issued so far (ring position)
         int tcount = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        for (unsigned item = blockIdx.x; item < (unsigned)total_items; item += gridDim.x, ++tcount) {
+            // (32-bit index arithmetic: the host only launches item counts below 2^31)
+            const unsigned tile = ksplit > 1 ? item / (unsigned)ksplit : item;
+            const int c0 = ksplit > 1 ? (int)(item - tile * (unsigned)ksplit) * per_split : 0;
+            const int nchunks = all_chunks - c0 < per_split ? (all_chunks - c0 > 0 ? all_chunks - c0 : 0)
+                                                            : per_split;
             // batch index fastest: batch modes often sit between the row modes in the operand's
             // memory order, so the tiles of all batch values share cache lines -- run them together
-            const long long batch = tile % nbatch;
+            const unsigned rest = tile / (unsigned)nbatch;
+            const long long batch = tile - rest * (unsigned)nbatch;
             int tm, tn;
-            raster(tile / nbatch, tiles_m, tiles_n, tm, tn);
+            raster(rest, tiles_m, tiles_n, tm, tn);
             const int gen = tcount % TAB_GEN, pg = tcount & 1;
             // the C tables of generation `gen` are free once the MMA warps finished the
             // tile that used them (TAB_GEN tiles ago)
             if (tcount >= TAB_GEN) mbar_wait(&sm.tab_free[gen], (uint32_t)((tcount / TAB_GEN - 1) & 1));
             long long ba, bb, bc;
             decode_u32((unsigned)batch, g, 0, g.n_batch, ba, bb, bc);
-            #pragma unroll
-            for (int h = 0; h < BM / 32; ++h) {
-                const int t = lane + 32 * h;
-                long long oa, ob, oc;
-                const int m = tm * BM + t;
-                decode_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
-                sm.row_a[pg][t] = (ba + oa) * 16; sm.row_c[gen][t] = bc + oc;
-                if (t < BN) {
-                    const int n = tn * BN + t;
-                    decode_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
-                    sm.col_b[pg][t] = (bb + ob) * 16; sm.col_c[gen][t] = oc;
+            if (is_a) {
+                #pragma unroll
+                for (int h = 0; h < BM / 32; ++h) {
+                    const int t = lane + 32 * h;
+                    long long oa, ob, oc;
+                    const int m = tm * BM + t;
+                    decode_u32(m < M ? (unsigned)m : 0u, g, f_m, g.n_m, oa, ob, oc);
+                    sm.row_a[pg][t] = (ba + oa) * 16; sm.row_c[gen][t] = bc + oc;
+                }
+            } else {
+                #pragma unroll
+                for (int h = 0; h < (BN + 31) / 32; ++h) {
+                    const int t = lane + 32 * h;
+                    if (t < BN) {
+                        long long oa, ob, oc;
+                        const int n = tn * BN + t;
+                        decode_u32(n < N ? (unsigned)n : 0u, g, f_n, g.n_n, oa, ob, oc);
+                        sm.col_b[pg][t] = (bb + ob) * 16; sm.col_c[gen][t] = oc;
+                    }
                 }
             }
             __threadfence_block();
             __syncwarp();
-            int klo = 0;                              // (chunk * 16) % klow
-            unsigned khi_idx = 0;                     // (chunk * 16) / klow
-            long long khi_a = 0, khi_b = 0;
-            for (int c = 0; c < nchunks; ++c, ++chunk_seq) {
+            int klo = (int)(((long long)c0 * BK) % klow);                  // (chunk * 16) % klow
+            unsigned khi_idx = (unsigned)(((long long)c0 * BK) / klow);    // (chunk * 16) / klow
+            long long khi = 0;
+            {
+                unsigned r = khi_idx;
+                for (int m = n_klow_modes; m < g.n_k; ++m) {
+                    const unsigned d = (unsigned)g.dim[f_k + m];
+                    const unsigned q = r / d, i = r - q * d;
+                    r = q;
+                    khi += (long long)i * (is_a ? g.sa[f_k + m] : g.sb[f_k + m]);
+                }
+                khi *= 16;
+            }
+            for (int c = c0; c < c0 + nchunks; ++c, ++chunk_seq) {
                 const int st = (int)(chunk_seq % STAGES);
                 const uint32_t ph = (uint32_t)((chunk_seq / STAGES) & 1);
                 mbar_wait(&sm.empty[st], ph ^ 1u);   // passes at once on the first lap
                 const int kleft = K - c * BK;
                 const int kvalid = kleft < BK ? kleft : BK;
-                gather_rows<BM>(s32(&sm.a[st][0][0]), Ab, sm.row_a[pg], sm.klow_a, klo, khi_a, lane,
-                                a_kfast != 0, kvalid);
-                gather_rows<BN>(s32(&sm.b[st][0][0]), Bb, sm.col_b[pg], sm.klow_b, klo, khi_b, lane,
-                                b_kfast != 0, kvalid);
+                if (is_a)
+                    gather_rows<BM>(s32(&sm.a[st][0][0]), base, sm.row_a[pg], klow_tab, klo, khi, lane,
+                                    kfast, kvalid);
+                else
+                    gather_rows<BN>(s32(&sm.b[st][0][0]), base, sm.col_b[pg], klow_tab, klo, khi, lane,
+                                    kfast, kvalid);
                 cp_async_arrive(&sm.full[st]);
                 klo += BK;
                 if (klo >= klow) {                    // klow is a multiple of 16 (or >= K)
                     klo = 0;
                     ++khi_idx;
                     unsigned r = khi_idx;
-                    khi_a = khi_b = 0;
+                    khi = 0;
                     for (int m = n_klow_modes; m < g.n_k; ++m) {
                         const unsigned d = (unsigned)g.dim[f_k + m];
                         const unsigned q = r / d, i = r - q * d;
                         r = q;
-                        khi_a += (long long)i * g.sa[f_k + m];
-                        khi_b += (long long)i * g.sb[f_k + m];
+                        khi += (long long)i * (is_a ? g.sa[f_k + m] : g.sb[f_k + m]);
                     }
-                    khi_a *= 16; khi_b *= 16;
+                    khi *= 16;
                 }
             }
         }
@@ -248,11 +282,14 @@ ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __
         const int frow = lane >> 2, fk = lane & 3;
         long long chunk_seq = 0;
         int tcount = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            // batch index fastest: batch modes often sit between the row modes in the operand's
-            // memory order, so the tiles of all batch values share cache lines -- run them together
+        for (unsigned item = blockIdx.x; item < (unsigned)total_items; item += gridDim.x, ++tcount) {
+            // (32-bit index arithmetic: the host only launches item counts below 2^31)
+            const unsigned tile = ksplit > 1 ? item / (unsigned)ksplit : item;
+            const int c0 = ksplit > 1 ? (int)(item - tile * (unsigned)ksplit) * per_split : 0;
+            const int nchunks = all_chunks - c0 < per_split ? (all_chunks - c0 > 0 ? all_chunks - c0 : 0)
+                                                            : per_split;
             int tm, tn;
-            raster(tile / nbatch, tiles_m, tiles_n, tm, tn);
+            raster(tile / (unsigned)nbatch, tiles_m, tiles_n, tm, tn);
             double p1[RT][2][2], p2[RT][2][2], p3[RT][2][2];
             #pragma unroll
             for (int r = 0; r < RT; ++r)
@@ -317,8 +354,13 @@ ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __
                         v.x = alpha_re * re - alpha_im * im;
                         v.y = alpha_re * im + alpha_im * re;
                         double2* dst = Cout + ro + sm.col_c[gen][j];
-                        if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-                        *dst = v;
+                        if (ksplit > 1) {
+                            atomicAdd(&dst->x, v.x);
+                            atomicAdd(&dst->y, v.y);
+                        } else {
+                            if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
+                            *dst = v;
+                        }
                     }
                 }
             }
@@ -332,16 +374,16 @@ ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __
     const __grid_constant__ b2_gemm_modes g, const double2* __restrict__ A,                       \
         const double2* __restrict__ B, double2* __restrict__ Cout, int M, int N, int K, int tiles_m, \
         int tiles_n, long long total_tiles, int klow, int n_klow_modes, int a_kfast, int b_kfast,  \
-        double alpha_re, double alpha_im, int accumulate
+        double alpha_re, double alpha_im, int accumulate, int ksplit
 #define B2_WS_ARGS                                                                                \
     g, A, B, Cout, M, N, K, tiles_m, tiles_n, total_tiles, klow, n_klow_modes, a_kfast, b_kfast,   \
-        alpha_re, alpha_im, accumulate
+        alpha_re, alpha_im, accumulate, ksplit
 
-// 8 MMA warps + the producer = 288 threads.  (A 12 + 1 warp, 96-row variant was tried: with
+// 8 MMA warps + the two producers = 320 threads.  (A 12 + 1 warp, 96-row variant was tried: with
 // 13 warps one scheduler hosts 4 of them, which caps the kernel at 128 registers per thread
 // -- the 3M accumulators then spill.)
 template <int RT>
-__global__ void __launch_bounds__(288, 1) contract_gemm_ws_c128_kernel(B2_WS_PARAMS) {
+__global__ void __launch_bounds__(320, 1) contract_gemm_ws_c128_kernel(B2_WS_PARAMS) {
     ws_body<RT, 8>(B2_WS_ARGS);
 }
 
@@ -350,7 +392,7 @@ __global__ void __launch_bounds__(288, 1) contract_gemm_ws_c128_kernel(B2_WS_PAR
 template <int RT, int MW>
 static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
                         long long M, long long N, long long K, long long klow, int n_low, int a_kfast,
-                        int b_kfast, double ar, double ai, int accumulate, cudaStream_t s) {
+                        int b_kfast, double ar, double ai, int accumulate, int ksplit, cudaStream_t s) {
     using namespace ws;
     constexpr int BN = 16 * RT, BM = (MW / RT) * 8 * RT;
     const int sms = num_sms();
@@ -365,25 +407,79 @@ static int launch_ws_rt(const b2_gemm_modes& g, const void* a, const void* b, vo
         if (e != cudaSuccess) { set_error("b2_contract_gemm(ws): smem attr: %s", cudaGetErrorString(e)); return 1; }
         b2::mark_done(attr_set);
     }
-    const long long grid = total < sms ? total : sms;
-    contract_gemm_ws_c128_kernel<RT><<<(unsigned)grid, (MW + 1) * 32, smem, s>>>(
+    const long long items = total * ksplit;
+    if (items >= (1ll << 31) || tiles_n * RASTER_GM >= (1ll << 31)) {
+        set_error("b2_contract_gemm(ws): too many tiles (%lld)", items);
+        return 1;
+    }
+    const long long grid = items < sms ? items : sms;
+    if (ksplit > 1 && !accumulate) {
+        cudaError_t e = cudaMemsetAsync(c, 0, (size_t)(Bt * M * N) * sizeof(double2), s);
+        if (e != cudaSuccess) { set_error("b2_contract_gemm(ws): memset: %s", cudaGetErrorString(e)); return 1; }
+    }
+    contract_gemm_ws_c128_kernel<RT><<<(unsigned)grid, (MW + 2) * 32, smem, s>>>(
         g, (const double2*)a, (const double2*)b, (double2*)c, (int)M, (int)N, (int)K, (int)tiles_m,
-        (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate);
+        (int)tiles_n, total, (int)klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, ksplit);
     return check_launch("b2_contract_gemm(ws)");
 }
 
 // returns handled = false when the pair does not fit this kernel (the caller falls
 // back to the barrier-per-chunk kernels of contract_gemm.cu).
-int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c, long long Bt,
+int launch_gemm_ws(const b2_gemm_modes& g_in, const void* a, const void* b, void* c, long long Bt,
                    long long M, long long N, long long K, int a_kfast, int b_kfast, double ar,
                    double ai, int accumulate, cudaStream_t s, bool& handled) {
     using namespace ws;
     handled = false;
+    // The planner merges stride-compatible reduction modes; the two-level offset table needs
+    // a leading group of at most KLOW_MAX values, so a long merged mode is split back into
+    // (low, high) factors here: index = lo + f * hi, strides (s, f * s) -- the same addresses.
+    b2_gemm_modes g = g_in;
+    {
+        const int f_k0 = g.n_batch + g.n_m + g.n_n;
+        long long low = 1;
+        for (int i = 0; i < g.n_k; ++i) {
+            const long long d = g.dim[f_k0 + i];
+            if (low * d <= KLOW_MAX) { low *= d; continue; }
+            // largest factor of d that keeps the low group within the table and, if it
+            // can, makes its extent a multiple of the K chunk
+            long long best = 0;
+            for (long long f = KLOW_MAX / low; f >= 2; --f)
+                if (d % f == 0 && ((low * f) % BK == 0 || best == 0)) {
+                    if ((low * f) % BK == 0) { best = f; break; }
+                    best = f;
+                }
+            const int total = f_k0 + g.n_k;
+            if (best >= 2 && total < B2_MAX_MODES) {
+                for (int j = total; j > f_k0 + i + 1; --j) {         // make room for the high factor
+                    g.dim[j] = g.dim[j - 1]; g.sa[j] = g.sa[j - 1]; g.sb[j] = g.sb[j - 1]; g.sc[j] = g.sc[j - 1];
+                }
+                g.dim[f_k0 + i] = (int)best;
+                g.dim[f_k0 + i + 1] = (int)(d / best);
+                g.sa[f_k0 + i + 1] = g.sa[f_k0 + i] * best;
+                g.sb[f_k0 + i + 1] = g.sb[f_k0 + i] * best;
+                g.sc[f_k0 + i + 1] = 0;
+                ++g.n_k;
+            }
+            break;
+        }
+    }
     if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31) || Bt >= (1ll << 31)) return 0;
     const int bn = N >= 48 ? 64 : N > 16 ? 32 : 16;
     const int bm = 64;
     const long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Bt;
-    if (tiles * 2 <= num_sms() && K >= 256) return 0;      // few tiles, long reduction: split-K
+    // few tiles over a long reduction: split the reduction range so that every SM gets ~2 items
+    // (C must be one dense block: it is zero-filled and the partial tiles are added atomically)
+    int ksplit = 1;
+    if (tiles * 2 <= num_sms() && K >= 256) {
+        const int f_free = g.n_batch + g.n_m + g.n_n;
+        long long span = 0;
+        for (int i = 0; i < f_free; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
+        if (span + 1 != Bt * M * N && !accumulate) return 0;
+        const long long chunks = (K + BK - 1) / BK;
+        long long want = (2ll * num_sms() + tiles - 1) / tiles;
+        if (want > chunks / 4) want = chunks / 4;            // >= 4 chunks per item
+        if (want > 1) ksplit = (int)want;
+    }
     // two-level reduction offsets: the low table covers the leading K modes, up to
     // KLOW_MAX entries; with more than one level its extent must be a multiple of the
     // K chunk so that a chunk never straddles two high indices
@@ -397,10 +493,10 @@ int launch_gemm_ws(const b2_gemm_modes& g, const void* a, const void* b, void* c
         if (n_low == 0 || klow % BK != 0) return 0;
     }
     handled = true;
-    set_last_kernel(bn == 64 ? "gemm_ws" : bn == 32 ? "gemm_ws32" : "gemm_ws16");
-    if (bn == 64) return launch_ws_rt<4, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
-    if (bn == 32) return launch_ws_rt<2, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
-    return launch_ws_rt<1, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, s);
+    set_last_kernel(ksplit > 1 ? "gemm_ws_splitk" : bn == 64 ? "gemm_ws" : bn == 32 ? "gemm_ws32" : "gemm_ws16");
+    if (bn == 64) return launch_ws_rt<4, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, ksplit, s);
+    if (bn == 32) return launch_ws_rt<2, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, ksplit, s);
+    return launch_ws_rt<1, 8>(g, a, b, c, Bt, M, N, K, klow, n_low, a_kfast, b_kfast, ar, ai, accumulate, ksplit, s);
 }
 
 }  // namespace b2

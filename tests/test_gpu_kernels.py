@@ -266,7 +266,8 @@ def test_gemm_kernel_permuted_operands(case):
     (((5, 5), (3, 7), (2, 3, 5, 7, 11), (3,)), "gemm_thin"),         # T = 4, ragged M / N / K
     (((4,) * 5, (2,) * 9, (4,) * 4, ()), "gemm_ws"),                 # 1024 x 512 x 256: 128 tiles
     (((9, 9), (70,), (150,), (2,)), "gemm_ws"),                      # ragged tiles and K tail
-    (((64,), (48,), (4096,), ()), "gemm3m_splitk"),
+    (((64,), (48,), (4096,), ()), "gemm_ws_splitk"),                 # one tile, 256 chunks: split-K items
+    (((5, 13), (3, 11), (4, 4, 4, 4, 4, 2), (2,)), "gemm_ws_splitk"),   # ragged 65 x 33, K = 2048, batch 2
     (((2,) * 8, (2,) * 5, (2,) * 6, (2,)), "gemm_ws32"),             # 256 x 32 x 64, batch 2
     (((7, 7, 3), (5, 7), (3, 7), (3,)), "gemm_ws32"),                # ragged rows / columns / K
     (((130,), (9,), (40,), ()), "gemm_ws16"),
