@@ -344,22 +344,46 @@ ws_body(const b2_gemm_modes& g, const double2* __restrict__ A, const double2* __
                 const long long ro = sm.row_c[gen][i];
                 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
+                    // a lane holds two ADJACENT columns (2 fk, 2 fk + 1) of its row: when they are
+                    // adjacent in C too (the usual case: the column modes are C's fastest), one
+                    // 32-byte store (STG.256) writes a whole sector instead of two half sectors
+                    const int j = wn * 16 + q * 8 + fk * 2;
+                    if (n0 + j >= N) continue;
+                    double2 v[2];
                     #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int j = wn * 16 + q * 8 + fk * 2 + h;
-                        if (n0 + j >= N) continue;
                         const double re = p1[r][q][h] - p2[r][q][h];
                         const double im = p3[r][q][h] - p1[r][q][h] - p2[r][q][h];
-                        double2 v;
-                        v.x = alpha_re * re - alpha_im * im;
-                        v.y = alpha_re * im + alpha_im * re;
-                        double2* dst = Cout + ro + sm.col_c[gen][j];
-                        if (ksplit > 1) {
-                            atomicAdd(&dst->x, v.x);
-                            atomicAdd(&dst->y, v.y);
-                        } else {
-                            if (accumulate) { const double2 o = *dst; v.x += o.x; v.y += o.y; }
-                            *dst = v;
+                        v[h].x = alpha_re * re - alpha_im * im;
+                        v[h].y = alpha_re * im + alpha_im * re;
+                    }
+                    const long long c0off = sm.col_c[gen][j], c1off = sm.col_c[gen][j + 1];
+                    double2* dst = Cout + ro + c0off;
+                    const bool second = n0 + j + 1 < N;
+                    if (ksplit > 1) {
+                        atomicAdd(&dst->x, v[0].x);
+                        atomicAdd(&dst->y, v[0].y);
+                        if (second) {
+                            double2* d1 = Cout + ro + c1off;
+                            atomicAdd(&d1->x, v[1].x);
+                            atomicAdd(&d1->y, v[1].y);
+                        }
+                    } else if (second && c1off == c0off + 1 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+                        if (accumulate) {
+                            double o0, o1, o2, o3;
+                            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                         : "=d"(o0), "=d"(o1), "=d"(o2), "=d"(o3) : "l"(dst));
+                            v[0].x += o0; v[0].y += o1; v[1].x += o2; v[1].y += o3;
+                        }
+                        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(v[0].x),
+                                     "d"(v[0].y), "d"(v[1].x), "d"(v[1].y) : "memory");
+                    } else {
+                        if (accumulate) { const double2 o = *dst; v[0].x += o.x; v[0].y += o.y; }
+                        *dst = v[0];
+                        if (second) {
+                            double2* d1 = Cout + ro + c1off;
+                            if (accumulate) { const double2 o = *d1; v[1].x += o.x; v[1].y += o.y; }
+                            *d1 = v[1];
                         }
                     }
                 }
