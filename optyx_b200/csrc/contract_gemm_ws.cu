@@ -12,18 +12,21 @@
 // reduction offsets or scatter a tile; a short reduction (K <= 128) pays the cold start of
 // the cp.async ring and the row / column decode once per 64 x 64 tile (~10 us next to
 // 8 - 17 us of math).  Here:
-//   * ONE CTA per SM, persistent: it walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-//     (grouped raster order, so that the tiles in flight share operand panels in L2);
-//   * a PRODUCER warp owns everything that is not math: per-tile row / column offset
-//     tables, reduction offsets (a two-level table: K = low x high, the low table lives
-//     in shared memory, the high offset is recomputed only when the low index wraps),
-//     and all cp.async gathers into a 5-stage ring; stages are handed over with
-//     mbarriers (cp.async.mbarrier.arrive), it runs ahead ACROSS tile boundaries, so
-//     the ring never drains between tiles;
-//   * 8 MMA warps (2 x 4, warp tile 32 x 16) only wait for a stage, issue LDS + DMMA
-//     (3M complex multiplication: P1 = ar*br, P2 = ai*bi, P3 = (ar+ai)(br+bi)), release
-//     the stage, and scatter their part of the tile at its end -- each warp on its own
-//     clock, so one warp's epilogue overlaps the others' math.
+//   * ONE CTA per SM, persistent: it walks work items blockIdx.x, blockIdx.x + gridDim.x, ...
+//     (an item = a tile, or a tile x a part of the reduction range when the tiles alone would
+//     leave most SMs idle; grouped raster order, batch index fastest, so that the items in
+//     flight share operand panels in L2);
+//   * two PRODUCER warps, one per operand, own everything that is not math: per-tile row /
+//     column offset tables, reduction offsets (a two-level table: K = low x high, the low
+//     table lives in shared memory, the high offset is recomputed only when the low index
+//     wraps), and all cp.async gathers into a 5-stage ring; stages are handed over with
+//     mbarriers (cp.async.mbarrier.arrive), the producers run ahead ACROSS tile boundaries,
+//     so the ring never drains between tiles;
+//   * 8 MMA warps (warp tile 8 RT x 16) only wait for a stage, issue LDS + DMMA (3M complex
+//     multiplication: P1 = ar*br, P2 = ai*bi, P3 = (ar+ai)(br+bi)), release the stage, and
+//     scatter their part of the tile at its end (32-byte stores where two columns are
+//     adjacent in C) -- each warp on its own clock, so one warp's epilogue overlaps the
+//     others' math.
 #include <stdlib.h>
 #include "b2_common.cuh"
 
@@ -500,7 +503,7 @@ int launch_gemm_ws(const b2_gemm_modes& g_in, const void* a, const void* b, void
         for (int i = 0; i < f_free; ++i) span += (long long)(g.dim[i] - 1) * g.sc[i];
         if (span + 1 != Bt * M * N && !accumulate) return 0;
         const long long chunks = (K + BK - 1) / BK;
-        long long want = (2ll * num_sms() + tiles - 1) / tiles;
+        long long want = 2ll * num_sms() / tiles;             // items just under two full rounds
         if (want > chunks / 4) want = chunks / 4;            // >= 4 chunks per item
         if (want > 1) ksplit = (int)want;
     }

@@ -467,3 +467,21 @@ def test_subtree_reconfiguration_never_hurts_and_keeps_the_tensor():
                 used.update((a, b))
             plan = planner.plan_from_ssa_path(net, [tuple(x) for x in p2.tolist()], sliced)
             assert np.allclose(emulate_plan(net, plan)[0], contract_network(net), rtol=1e-12, atol=1e-12)
+
+
+def test_threaded_native_search_does_not_depend_on_the_thread_count(monkeypatch):
+    """The C++ trials, the subtree reconfigurations and the slicing of the candidate trees run
+    on a thread pool; every rank of a sliced job must still find the SAME plan whatever its
+    core count: same pair order, same sliced indices with 1 thread and with many."""
+    import os
+    import cases
+    from optyx_b200 import planner
+    net = cases.compile_channel(cases.random_clifford_t(12, 10, seed=4))
+    inputs = [frozenset(l.inds) for l in net.leaves]
+    output = frozenset(net.output_inds)
+    assert len(inputs) >= planner.NATIVE_MIN_TENSORS
+    many = planner.find_path(inputs, net.dims, output, trials=2, seed=3, target_size=64.0, min_slices=8)
+    monkeypatch.setattr(os, "cpu_count", lambda: 1)
+    one = planner.find_path(inputs, net.dims, output, trials=2, seed=3, target_size=64.0, min_slices=8)
+    assert many.path == one.path and tuple(many.sliced) == tuple(one.sliced)
+    assert many.nslices >= 8 and many.peak <= 64

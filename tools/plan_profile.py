@@ -28,8 +28,10 @@ if w["kind"] == "batch":
 else:
     nets = [backend._get_network(w["factory"](), nested_eval=backend._nested_eval)]
     batch = 1
+thr = tuple(float(x) for x in os.environ["B2_GEMM_THRESHOLD"].split(",")) if "B2_GEMM_THRESHOLD" in os.environ \
+    else (32, 16, 8, 4.0)       # experiment knob: planner's (M, N, K, flop/B) bar for the DMMA kernels
 plan = executor.get_plan(nets[0], batch=batch, target_size=w["target"], trials=w["trials"],
-                         min_slices=w.get("min_slices", 1))
+                         min_slices=w.get("min_slices", 1), gemm_threshold=thr)
 sess = executor.Session(plan)
 sess.set_leaves(nets)
 sess.build_leaves()
