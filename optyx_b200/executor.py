@@ -35,6 +35,16 @@ def leaf_table(net: Network, plan: Plan, varying=None) -> Tuple[np.ndarray, np.n
     (they index the per-eval params buffer); the others are flagged ``shared`` and index
     one vector for the whole batch.  ``None``: every host-valued leaf is per-eval, and the
     returned vector holds them all."""
+    if varying is None:
+        # everything in the table follows from the network STRUCTURE (kinds, shapes, integer
+        # parameters -- Network.structure_key, which is also what the plan is cached by), so
+        # it is built once per plan; per eval only the host values are gathered (cfg4: 3588
+        # leaves, 25 ms of per-row Python on every eval before)
+        cached = getattr(plan, "_leaf_table_static", None)
+        if cached is not None and len(cached[0]) == len(net.leaves) + 1:
+            table, host_leaves = cached
+            ps = [np.asarray(net.leaves[k].params, dtype=np.complex128).reshape(-1) for k in host_leaves]
+            return table, (np.concatenate(ps) if ps else np.zeros(1, dtype=np.complex128))
     n = len(net.leaves)
     table = np.zeros(n + 1, dtype=rt.LEAF_DESC_DTYPE)
     params: List[np.ndarray] = []
@@ -64,6 +74,10 @@ def leaf_table(net: Network, plan: Plan, varying=None) -> Tuple[np.ndarray, np.n
     unit["dims"][0] = 1
     unit["offset"], unit["nelem"] = plan.unit_offset, 1
     pvec = np.concatenate(params) if params else np.zeros(1, dtype=np.complex128)
+    if varying is None:
+        table.setflags(write=False)
+        plan._leaf_table_static = (table, [k for k, l in enumerate(net.leaves)
+                                           if l.kind in (K_VEC, K_DENSE)])
     return table, pvec
 
 
@@ -191,6 +205,12 @@ class Session:
         torch = self.torch
         plan = self.plan
         assert len(nets) == plan.batch
+        if (plan.batch == 1 and self.desc_dev is not None and getattr(self, "_varying", None) is None
+                and getattr(self, "_uploaded_net", None) is nets[0]):
+            # the very same (cached, immutable) Network object as the last upload: its values
+            # are already on the device -- a re-built identical diagram maps to it through
+            # the fingerprint cache
+            return
         table, p0 = leaf_table(nets[0], plan)
         if self.desc_dev is None or getattr(self, "_varying", None) is not None:
             self._upload_table(table)
@@ -214,6 +234,7 @@ class Session:
         if self._params_copied is None:
             self._params_copied = torch.cuda.Event()
         self._params_copied.record()
+        self._uploaded_net = nets[0] if plan.batch == 1 else None
 
     def set_leaves_batched(self, net: Network) -> None:
         """The same for ONE network whose parameters are array-valued (``net.batch``
@@ -223,6 +244,7 @@ class Session:
         torch, plan = self.torch, self.plan
         batch = net.batch or 1
         assert batch == plan.batch, (batch, plan.batch)
+        self._uploaded_net = None
         varying = frozenset(k for k, l in enumerate(net.leaves)
                             if l.params is not None and l.params.ndim == 2)
         if self.desc_dev is None or getattr(self, "_varying", None) != varying:
