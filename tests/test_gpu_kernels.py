@@ -123,8 +123,9 @@ def test_batched_evals_share_one_plan(batch):
             assert np.abs(got[e] - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
 
 
-def _gemm_case(rng, mshape, nshape, kshape, bshape=(), dtype=np.complex128):
-    """A[b,m,k] x B[b,k,n] with every operand stored in a random axis order."""
+def _gemm_case(rng, mshape, nshape, kshape, bshape=(), dtype=np.complex128, accumulate=0):
+    """A[b,m,k] x B[b,k,n] with every operand stored in a random axis order
+    (``accumulate``: C starts from random values and the product is added to it)."""
     torch = _torch()
     lib = rt.load()
     names = {}
@@ -159,14 +160,17 @@ def _gemm_case(rng, mshape, nshape, kshape, bshape=(), dtype=np.complex128):
     spec = "".join(letters[a] for a in axA) + "," + "".join(letters[a] for a in axB) + "->" + \
         "".join(letters[a] for a in axC)
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(Bm).cuda()
-    dC = torch.zeros(Cz.shape, dtype=dA.dtype, device="cuda")
+    dC = torch.from_numpy(Cz.copy()).cuda() if accumulate else \
+        torch.zeros(Cz.shape, dtype=dA.dtype, device="cuda")
     alpha = 0.5 - 0.25j
     stream = torch.cuda.current_stream().cuda_stream
     code = rt.B2_C128 if dtype == np.complex128 else rt.B2_C64
     rt.check(lib.b2_contract_gemm(C.byref(desc), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(),
-                                  alpha.real, alpha.imag, 0, code, stream))
+                                  alpha.real, alpha.imag, int(accumulate), code, stream))
     torch.cuda.synchronize()
     want = alpha * torch.einsum(spec, dA.to(torch.complex128), dB.to(torch.complex128))
+    if accumulate:
+        want = want + torch.from_numpy(Cz).cuda().to(torch.complex128)
     return dC.to(torch.complex128), want
 
 
@@ -289,6 +293,23 @@ def test_gemm_thin_and_3m_kernels(case, kernel):
     got, want = _gemm_case(rng, *case)
     if kernel is not None:
         assert rt.load().b2_last_kernel().decode() == kernel
+    err = (got - want).abs().max().item()
+    assert err <= 1e-10 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("case,kernel", [
+    (((4,) * 6, (4,) * 5, (4, 4, 2), ()), "gemm_ws"),                # 32-byte load + store pairs
+    (((13, 11, 9), (7, 11, 3), (5, 7), (2, 2, 2)), "gemm_ws"),       # ragged: pair and single stores
+    (((64,), (48,), (4096,), ()), "gemm_ws_splitk"),                 # atomics onto the running sum
+    (((4, 4), (2, 2, 2, 2), (2,) * 13, (2,)), "gemm_thin"),
+    (((13, 11, 9), (3, 3), (5, 7), (2, 2, 2, 2)), "gemm_ws16"),
+])
+def test_gemm_kernels_accumulate_into_c(case, kernel):
+    """accumulate = 1 (a slice or a formal-sum term added to the running result): C keeps its
+    values and receives alpha * A.B on top -- no zero fill in the split-K kernels."""
+    rng = np.random.default_rng(6)
+    got, want = _gemm_case(rng, *case, accumulate=1)
+    assert rt.load().b2_last_kernel().decode() == kernel
     err = (got - want).abs().max().item()
     assert err <= 1e-10 * max(1.0, want.abs().max().item()), err
 

@@ -485,3 +485,29 @@ def test_threaded_native_search_does_not_depend_on_the_thread_count(monkeypatch)
     one = planner.find_path(inputs, net.dims, output, trials=2, seed=3, target_size=64.0, min_slices=8)
     assert many.path == one.path and tuple(many.sliced) == tuple(one.sliced)
     assert many.nslices >= 8 and many.peak <= 64
+
+
+def test_descriptor_table_is_cached_per_plan_and_values_follow_the_network():
+    """executor.leaf_table: the descriptor table depends on the network STRUCTURE only and is
+    built once per plan; the host values are gathered from whichever network is passed --
+    a structurally identical network with other parameters must get ITS values."""
+    import cases
+    from optyx_b200 import executor
+    from optyx_b200.core import network as nw
+    net_a = cases.compile_channel(cases.lossy_hom(0.8))
+    net_b = cases.compile_channel(cases.lossy_hom(0.3))
+    assert net_a.structure_key() == net_b.structure_key()
+    plan = plan_network(net_a)
+    t1, p_a = executor.leaf_table(net_a, plan)
+    t2, p_b = executor.leaf_table(net_b, plan)
+    assert t2 is t1 and not t1.flags.writeable            # one table per plan
+    want_a = executor.params_vector(net_a)
+    want_b = executor.params_vector(net_b)
+    assert np.array_equal(p_a, want_a) and np.array_equal(p_b, want_b)
+    assert not np.array_equal(p_a, p_b)                    # the loss parameter differs
+    # the cached table equals a from-scratch build
+    fresh = plan_network(net_b)
+    t3, _ = executor.leaf_table(net_b, fresh)
+    assert t3 is not t1 and t3.tobytes() == t1.tobytes()
+    host = [k for k, l in enumerate(net_a.leaves) if l.kind in (nw.K_VEC, nw.K_DENSE)]
+    assert len(host) > 0
