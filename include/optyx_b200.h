@@ -99,7 +99,9 @@ typedef struct {
 int b2_abi_version(void);
 const char* b2_last_error(void);
 /* which kernel variant the last contraction call of this thread launched
- * ("fma", "tiled", "generic", "ctile", "gemm"): profiling aid */
+ * ("fma ...", "tiled", "reduce", "generic", "ctile", "dot", "gemm_ws" / "gemm_ws32" /
+ * "gemm_ws16" / "gemm_ws_splitk", "gemm_thin", "gemm3m[_splitk]", "gemm[_splitk]",
+ * "gemm_c64_tcgen05", "small_program"): profiling aid */
 const char* b2_last_kernel(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int b2_device_sms(void);

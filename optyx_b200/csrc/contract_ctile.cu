@@ -429,13 +429,13 @@ int launch_ctile(const b2_gemm_modes& g, const void* a, const void* b, void* c, 
     if (!make_ctile(g, d, n_tiles, smem)) return 0;
     int sms = num_sms();
     if (sms <= 0) return 1;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static b2::once_flags attr_set;                    // kernel attributes are per device
+    if (!b2::is_done(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(contract_ctile_c128_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)CT_SMEM_MAX);
         if (e != cudaSuccess) { set_error("ctile smem attr: %s", cudaGetErrorString(e)); return 1; }
-        attr_smem = CT_SMEM_MAX;
+        b2::mark_done(attr_set);
     }
     long long blocks = n_tiles;
     const long long cap = (long long)sms * 2;
