@@ -478,7 +478,11 @@ class Bench:
             / per_step / 1e12,
             "leaf_build": {"ms": leaf_secs * 1e3, "bytes": arena_bytes,
                            "gbs": arena_bytes / leaf_secs / 1e9,
-                           "frac_of_hbm": arena_bytes / leaf_secs / 1e9 / self.hbm},
+                           "frac_of_hbm": arena_bytes / leaf_secs / 1e9 / self.hbm,
+                           "note": ("one launch builds every leaf array of the step; below a few MB it "
+                                    "is launch-bound (~10 us) and the GB/s figure says nothing -- the "
+                                    "bandwidth of the array build is on the cfg5a line (58 MB batched "
+                                    "arena, profiles/r02_bench_cfg5a.json)")},
         }
         if out_host is not None:
             line["result_head"] = [[float(v.real), float(v.imag)] for v in out_host]
