@@ -200,6 +200,13 @@ def cpu_reference(name: str, budget_s: float = 25.0, max_evals: int = 3):
     from oracle.contract import contract_along_path, contract_arrays
     w = workload(name)
     cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: give the CPU arm all host threads back,
+    # so that the baseline is the same at every N (r01: 6.0 -> 7.4 s per eval under torchrun)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     if w["kind"] == "sliced":
         from optyx_b200 import executor
         from optyx_b200.core.backends import B200Backend
