@@ -38,7 +38,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC, UNIT = "eval_diagrams_per_sec", "diagrams/s"
 FP64_PIPE_TFLOPS = 37.0      # DMMA m8n8k4 / DFMA, measured on this pool (profiles/r01_probe.json)
-THREE_M_VARIANTS = ("gemm_ws", "gemm3m", "gemm3m_splitk", "gemm_pk", "gemm_thin")
+THREE_M_VARIANTS = ("gemm_ws", "gemm_ws32", "gemm_ws16", "gemm_ws_splitk", "gemm3m", "gemm3m_splitk",
+                    "gemm_thin")      # kernels that multiply complex numbers with 3 real products
 CFG4_TARGET = float(2 ** 27)       # <= 2^27 elements (2 GiB complex128) per slice
 CFG4_TRIALS = 128                  # path-search budget (cotengra's default hyper-optimiser: 128 repeats)
 CFG4_MIN_SLICES = 32               # ... and >= 32 slices, so that 8 GPUs get >= 4 each
